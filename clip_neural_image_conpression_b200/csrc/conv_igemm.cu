@@ -1,0 +1,535 @@
+// conv_igemm.cu — implicit-GEMM convolution on the Blackwell tensor cores (tcgen05.mma + TMEM + TMA), sm_100a.
+//
+// Replaces the cuDNN calls behind nn.Conv2d / nn.ConvTranspose2d of the reference
+// (PKG/models/blocks.py:34,36 ResBlock convs; PKG/models/unet.py:63 stride-2 convs, :75 transposed convs, :79 out).
+//
+// GEMM view:  D[M = pixels, N = Cout] = A[M, K = taps*Cin] * W[N, K]^T, bf16 operands, fp32 accumulation in TMEM.
+//   * A is never materialised: an M tile is a (wbox x hbox) patch of ONE image, and the k-block of tap (r,s) is the
+//     same patch shifted by (r-1, s-1).  One tiled TMA load over a 5-D view of the NHWC activation fetches it, with
+//     the conv zero padding produced by TMA out-of-bounds fill.  Views (innermost first):
+//        3x3 s1 / convT : [C, W, 1, H, B]
+//        3x3 s2         : [2C, W/2, 2, H/2, B]   (x = wpar*C + c, p = hpar)  -> stride-2 taps become unit-stride boxes
+//   * ConvTranspose2d(4,2,1) = 4 output phases, each a 2x2-tap stride-1 conv of the input (K = 4*Cin) whose result is
+//     scattered to (2h+ph, 2w+pw).
+//   * Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer (+TMEM
+//     alloc), warps 2..5 = epilogue (TMEM -> registers -> bias/FiLM/residual -> global).  smem ring of `stages`
+//     k-blocks; TMEM accumulator double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "conv_igemm.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace clpk {
+
+constexpr int kNumThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 232448;  // 227 KB
+
+struct __align__(8) PipeBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+struct TileCoord {
+  int phase, b, h0, w0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+  TileCoord c;
+  int nt = tile % p.n_tiles_n;
+  int r = tile / p.n_tiles_n;
+  int tw = r % p.tiles_w;
+  r /= p.tiles_w;
+  int th = r % p.tiles_h;
+  r /= p.tiles_h;
+  c.b = r % p.batch;
+  c.phase = r / p.batch;
+  c.h0 = th * p.hbox;
+  c.w0 = tw * p.wbox;
+  c.n0 = nt * p.block_n;
+  return c;
+}
+
+template <int BLOCK_K>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ IgemmParams p) {
+  constexpr int kSwizzle = BLOCK_K * 2;           // bytes per smem row
+  constexpr int kABytes = kTileM * BLOCK_K * 2;   // one A stage
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* smem = smem_raw + pad;  // 1024-byte aligned (swizzle atoms)
+
+  const int b_bytes = p.block_n * BLOCK_K * 2;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.stages * kABytes;
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem_b + (size_t)p.stages * b_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int k_blocks = p.taps * p.kpt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->tmem_full[s], 1);
+      mbar_init(&bars->tmem_empty[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      const uint32_t rows = (uint32_t)(p.wbox * p.hbox);
+      const uint32_t tx_bytes = rows * BLOCK_K * 2 + (uint32_t)b_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int w_row = tc.phase * p.cout_pad + tc.n0;
+        int tap = 0, kc = 0;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          const int ti = tc.phase * p.taps + tap;
+          mbar_wait(&bars->empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
+          tma_load_5d(smem_a + (size_t)stage * kABytes, &map_a, &bars->full[stage], p.tap_x[ti] + kc * BLOCK_K,
+                      tc.w0 + p.tap_dw[ti], p.tap_p[ti], tc.h0 + p.tap_dh[ti], tc.b);
+          tma_load_2d(smem_b + (size_t)stage * b_bytes, &map_w, &bars->full[stage], kb * BLOCK_K, w_row);
+          if (++kc == p.kpt) { kc = 0; ++tap; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&bars->full[stage], phase);  // TMA bytes have landed
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_desc<kSwizzle>(smem_u32(smem_a + (size_t)stage * kABytes));
+          const uint64_t bdesc = make_kmajor_desc<kSwizzle>(smem_u32(smem_b + (size_t)stage * b_bytes));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&bars->empty[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&bars->tmem_full[as]);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int hl = row / p.wbox;
+    const int wl = row - hl * p.wbox;
+    const clpk_conv_epilogue& ep = p.ep;
+    const int ldc = ep.cout_valid;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const TileCoord tc = decode_tile(p, tile);
+      const int h = tc.h0 + hl, w = tc.w0 + wl;
+      const bool valid = (hl < p.hbox) && (h < p.grid_h) && (w < p.grid_w);
+      const int oh = h * p.out_scale + (tc.phase >> 1), ow = w * p.out_scale + (tc.phase & 1);
+      const long long opix = ((long long)tc.b * p.out_h + oh) * p.out_w + ow;
+      mbar_wait(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.block_n);
+      for (int c = 0; c < p.block_n; c += 16) {
+        uint32_t r[16];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores of the last chunk
+        tmem_ld16(taddr + (uint32_t)c, r);
+        tmem_ld_wait();
+        const int n = tc.n0 + c;
+        if (valid && n < ldc) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (ldc - n >= 16) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n) + j4);
+              v[4 * j4 + 0] += bv.x; v[4 * j4 + 1] += bv.y; v[4 * j4 + 2] += bv.z; v[4 * j4 + 3] += bv.w;
+            }
+            if (ep.film_scale1p) {
+              const float* fs = ep.film_scale1p + (long long)tc.b * ep.film_stride + n;
+              const float* fb = ep.film_shift + (long long)tc.b * ep.film_stride + n;
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(fs) + j4);
+                const float4 t = __ldg(reinterpret_cast<const float4*>(fb) + j4);
+                v[4 * j4 + 0] = fmaf(v[4 * j4 + 0], s.x, t.x); v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], s.y, t.y);
+                v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], s.z, t.z); v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], s.w, t.w);
+              }
+            }
+            if (ep.resid) {
+              const float4* rp = reinterpret_cast<const float4*>(ep.resid + opix * ldc + n);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 q = rp[j4];
+                v[4 * j4 + 0] += q.x; v[4 * j4 + 1] += q.y; v[4 * j4 + 2] += q.z; v[4 * j4 + 3] += q.w;
+              }
+            }
+            if (ep.out_f32) {
+              float4* op = reinterpret_cast<float4*>(ep.out_f32 + opix * ldc + n);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                op[j4] = make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+            }
+            if (ep.out_bf16) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + opix * ldc + n);
+              op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                 pack_bf16x2(v[6], v[7]));
+              op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                 pack_bf16x2(v[14], v[15]));
+            }
+            if (ep.out_nchw) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                ep.out_nchw[(((long long)tc.b * ldc + n + j) * p.out_h + oh) * p.out_w + ow] = v[j];
+            }
+          } else {
+            // ragged tail (e.g. the 3-channel `out` conv padded to N = 16): scalar path, NCHW output only
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (n + j < ldc) {
+                float y = v[j] + __ldg(ep.bias + n + j);
+                if (ep.film_scale1p)
+                  y = fmaf(y, __ldg(ep.film_scale1p + (long long)tc.b * ep.film_stride + n + j),
+                           __ldg(ep.film_shift + (long long)tc.b * ep.film_stride + n + j));
+                if (ep.out_nchw) ep.out_nchw[(((long long)tc.b * ldc + n + j) * p.out_h + oh) * p.out_w + ow] = y;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ cross-check kernel
+// One thread per output element, same operands / tap tables / epilogue, plain fp32 FMAs.
+__global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wpk,
+                                   const IgemmParams p) {
+  const long long total = (long long)p.phases * p.batch * p.grid_h * p.grid_w * p.cout_pad;
+  const clpk_conv_epilogue& ep = p.ep;
+  const int ldc = ep.cout_valid;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % p.cout_pad);
+    long long r = idx / p.cout_pad;
+    const int w = (int)(r % p.grid_w); r /= p.grid_w;
+    const int h = (int)(r % p.grid_h); r /= p.grid_h;
+    const int b = (int)(r % p.batch);
+    const int phase = (int)(r / p.batch);
+    if (n >= ldc) continue;
+    const long long ktot = (long long)p.taps * p.cin;
+    const __nv_bfloat16* wrow = wpk + ((long long)phase * p.cout_pad + n) * ktot;
+    float acc = 0.f;
+    for (int t = 0; t < p.taps; ++t) {
+      const int ti = phase * p.taps + t;
+      const int cw = w + p.tap_dw[ti], ch = h + p.tap_dh[ti], cp = p.tap_p[ti];
+      if (cw < 0 || cw >= p.a_dim_w || ch < 0 || ch >= p.a_dim_h) continue;  // zero padding
+      const __nv_bfloat16* xp =
+          x + (long long)b * p.a_stride_b + (long long)ch * p.a_stride_h + (long long)cp * p.a_stride_p +
+          (long long)cw * p.a_stride_w + p.tap_x[ti];
+      const __nv_bfloat16* wp = wrow + (long long)t * p.cin;
+      for (int c = 0; c < p.cin; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
+    }
+    float y = acc + ep.bias[n];
+    if (ep.film_scale1p)
+      y = fmaf(y, ep.film_scale1p[(long long)b * ep.film_stride + n], ep.film_shift[(long long)b * ep.film_stride + n]);
+    const int oh = h * p.out_scale + (phase >> 1), ow = w * p.out_scale + (phase & 1);
+    const long long opix = ((long long)b * p.out_h + oh) * p.out_w + ow;
+    if (ep.resid) y += ep.resid[opix * ldc + n];
+    if (ep.out_f32) ep.out_f32[opix * ldc + n] = y;
+    if (ep.out_bf16) reinterpret_cast<__nv_bfloat16*>(ep.out_bf16)[opix * ldc + n] = __float2bfloat16_rn(y);
+    if (ep.out_nchw) ep.out_nchw[(((long long)b * ldc + n) * p.out_h + oh) * p.out_w + ow] = y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// Conv2d [Cout,Cin,3,3] -> [cout_pad][tap][Cin];  ConvTranspose2d [Cin,Cout,4,4] -> [phase][cout_pad][tap][Cin]
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kind, int cin,
+                                   int cout, int cout_pad) {
+  const int taps = (kind == CLPK_CONVT_4X4_S2) ? 4 : 9;
+  const int phases = (kind == CLPK_CONVT_4X4_S2) ? 4 : 1;
+  const long long total = (long long)phases * cout_pad * taps * cin;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cin);
+    long long r = idx / cin;
+    const int t = (int)(r % taps); r /= taps;
+    const int n = (int)(r % cout_pad);
+    const int phase = (int)(r / cout_pad);
+    float v = 0.f;
+    if (n < cout) {
+      if (kind == CLPK_CONVT_4X4_S2) {
+        // phase (ph,pw), tap (a,b): kernel index kh = ph + 1 - 2*dh with dh = {0,-1} (ph=0) / {+1,0} (ph=1)
+        const int ph = phase >> 1, pw = phase & 1, a = t >> 1, bb = t & 1;
+        const int dh = (ph == 0) ? (a == 0 ? 0 : -1) : (a == 0 ? 1 : 0);
+        const int dw = (pw == 0) ? (bb == 0 ? 0 : -1) : (bb == 0 ? 1 : 0);
+        const int kh = ph + 1 - 2 * dh, kw = pw + 1 - 2 * dw;
+        v = w[(((long long)c * cout + n) * 4 + kh) * 4 + kw];
+      } else {
+        v = w[((long long)n * cin + c) * 9 + t];
+      }
+    }
+    out[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+int igemm_cout_pad(int cout) { return (cout + 15) / 16 * 16; }
+int igemm_block_n(int cout_pad) {
+  int best = 16;
+  for (int n = 16; n <= 256 && n <= cout_pad; n += 16)
+    if (cout_pad % n == 0) best = n;
+  return best;
+}
+
+// ------------------------------------------------------------------------------------------------ host setup
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                      const cuuint32_t* box, int swizzle_bytes) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return CLPK_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu box %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return CLPK_ERR_CUDA;
+  }
+  return CLPK_OK;
+}
+
+int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, int h_in, int w_in, int cin, int cout,
+                const clpk_conv_epilogue* ep, IgemmLaunch* out) {
+  CLPK_REQUIRE(kind >= 0 && kind <= 2, "conv kind %d unknown", kind);
+  CLPK_REQUIRE(batch > 0 && h_in > 0 && w_in > 0, "bad conv geometry");
+  CLPK_REQUIRE(cin % 32 == 0, "implicit-GEMM conv needs Cin %% 32 == 0 (got %d)", cin);
+  CLPK_REQUIRE(ep && ep->bias, "conv epilogue needs a bias");
+  CLPK_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+               "conv operands must be 16-byte aligned");
+  if (kind == CLPK_CONV_3X3_S2) CLPK_REQUIRE(h_in % 2 == 0 && w_in % 2 == 0, "stride-2 conv needs even H, W");
+  IgemmParams& p = out->p;
+  memset(&p, 0, sizeof(p));
+  p.batch = batch;
+  p.cin = cin;
+  p.cout_pad = igemm_cout_pad(cout);
+  p.block_k = (cin % 64 == 0) ? 64 : 32;
+  p.block_n = igemm_block_n(p.cout_pad);
+  p.n_tiles_n = p.cout_pad / p.block_n;
+  p.kpt = cin / p.block_k;
+  p.ep = *ep;
+  if (p.ep.cout_valid <= 0) p.ep.cout_valid = cout;
+  CLPK_REQUIRE(p.ep.cout_valid == cout, "cout_valid must equal cout");
+  if (cout % 16 != 0)
+    CLPK_REQUIRE(!p.ep.out_f32 && !p.ep.out_bf16 && !p.ep.resid, "Cout %% 16 != 0 supports the NCHW output only");
+
+  cuuint64_t dims[5], strides[4];
+  const long long C = cin, W = w_in, H = h_in;
+  if (kind == CLPK_CONV_3X3_S2) {
+    p.grid_h = h_in / 2; p.grid_w = w_in / 2;
+    p.phases = 1; p.taps = 9;
+    p.out_h = p.grid_h; p.out_w = p.grid_w; p.out_scale = 1;
+    for (int r = 0; r < 3; ++r)
+      for (int s = 0; s < 3; ++s) {
+        const int t = r * 3 + s;
+        p.tap_p[t] = (r == 1) ? 0 : 1;
+        p.tap_dh[t] = (r == 0) ? -1 : 0;
+        p.tap_x[t] = (s == 1) ? 0 : cin;
+        p.tap_dw[t] = (s == 0) ? -1 : 0;
+      }
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = batch;
+    strides[0] = 2 * C * 2; strides[1] = W * C * 2; strides[2] = 2 * W * C * 2; strides[3] = H * W * C * 2;
+    p.a_stride_w = 2 * C; p.a_stride_p = W * C; p.a_stride_h = 2 * W * C; p.a_stride_b = H * W * C;
+    p.a_dim_w = w_in / 2; p.a_dim_p = 2; p.a_dim_h = h_in / 2;
+  } else {
+    p.grid_h = h_in; p.grid_w = w_in;
+    if (kind == CLPK_CONV_3X3_S1) {
+      p.phases = 1; p.taps = 9;
+      p.out_h = h_in; p.out_w = w_in; p.out_scale = 1;
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+          const int t = r * 3 + s;
+          p.tap_dh[t] = r - 1; p.tap_dw[t] = s - 1;
+        }
+    } else {
+      p.phases = 4; p.taps = 4;
+      p.out_h = 2 * h_in; p.out_w = 2 * w_in; p.out_scale = 2;
+      for (int phase = 0; phase < 4; ++phase)
+        for (int t = 0; t < 4; ++t) {
+          const int ph = phase >> 1, pw = phase & 1, a = t >> 1, bb = t & 1;
+          p.tap_dh[phase * 4 + t] = (ph == 0) ? (a == 0 ? 0 : -1) : (a == 0 ? 1 : 0);
+          p.tap_dw[phase * 4 + t] = (pw == 0) ? (bb == 0 ? 0 : -1) : (bb == 0 ? 1 : 0);
+        }
+    }
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = batch;
+    strides[0] = C * 2; strides[1] = W * C * 2; strides[2] = W * C * 2; strides[3] = H * W * C * 2;
+    p.a_stride_w = C; p.a_stride_p = 0; p.a_stride_h = W * C; p.a_stride_b = H * W * C;
+    p.a_dim_w = w_in; p.a_dim_p = 1; p.a_dim_h = h_in;
+  }
+  // M tile = wbox x hbox patch, wbox*hbox <= 128
+  p.wbox = std::min(p.grid_w, kTileM);
+  p.hbox = std::max(1, std::min(p.grid_h, kTileM / p.wbox));
+  p.tiles_w = (p.grid_w + p.wbox - 1) / p.wbox;
+  p.tiles_h = (p.grid_h + p.hbox - 1) / p.hbox;
+  const long long nt = (long long)p.phases * batch * p.tiles_h * p.tiles_w * p.n_tiles_n;
+  CLPK_REQUIRE(nt < (1ll << 30), "too many tiles");
+  p.num_tiles = (int)nt;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
+  const int stage_bytes = kTileM * p.block_k * 2 + p.block_n * p.block_k * 2;
+  p.stages = std::min(kMaxStages, (kSmemBudget - 2048) / stage_bytes);
+  CLPK_REQUIRE(p.stages >= 2, "tile does not fit shared memory");
+  out->smem_bytes = p.stages * stage_bytes + 2048;
+  out->grid = std::min(p.num_tiles, num_sms());
+
+  const int swz = p.block_k * 2;
+  cuuint32_t box_a[5] = {(cuuint32_t)p.block_k, (cuuint32_t)p.wbox, 1, (cuuint32_t)p.hbox, 1};
+  int rc = encode_map(&out->map_a, x_bf16, 5, dims, strides, box_a, swz);
+  if (rc) return rc;
+  cuuint64_t wdims[2] = {(cuuint64_t)p.taps * cin, (cuuint64_t)p.phases * p.cout_pad};
+  cuuint64_t wstr[1] = {(cuuint64_t)p.taps * cin * 2};
+  cuuint32_t box_w[2] = {(cuuint32_t)p.block_k, (cuuint32_t)p.block_n};
+  rc = encode_map(&out->map_w, w_packed, 2, wdims, wstr, box_w, swz);
+  return rc;
+}
+
+int igemm_init() {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  });
+  CLPK_CHECK_CUDA(attr_err);
+  return CLPK_OK;
+}
+
+int igemm_launch(const IgemmLaunch& L, cudaStream_t stream) {
+  int irc = igemm_init();
+  if (irc) return irc;
+  if (L.p.block_k == 64)
+    conv_igemm_kernel<64><<<L.grid, kNumThreads, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.p);
+  else
+    conv_igemm_kernel<32><<<L.grid, kNumThreads, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.p);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+int direct_launch(const IgemmLaunch& L, const void* x_bf16, const void* w_packed, cudaStream_t stream) {
+  const long long total = (long long)L.p.phases * L.p.batch * L.p.grid_h * L.p.grid_w * L.p.cout_pad;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 65535ll * 8);
+  conv_direct_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16),
+                                                 reinterpret_cast<const __nv_bfloat16*>(w_packed), L.p);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+}  // namespace clpk
+
+using namespace clpk;
+
+extern "C" int64_t clpk_pack_conv_weight(const float* w_dev, void* out_bf16_dev, int kind, int cin, int cout,
+                                         void* stream) {
+  if (kind < 0 || kind > 2 || cin <= 0 || cout <= 0) {
+    set_error("clpk_pack_conv_weight: bad arguments");
+    return -1;
+  }
+  const int cout_pad = igemm_cout_pad(cout);
+  const int taps = (kind == CLPK_CONVT_4X4_S2) ? 4 : 9, phases = (kind == CLPK_CONVT_4X4_S2) ? 4 : 1;
+  const long long total = (long long)phases * cout_pad * taps * cin;
+  if (!out_bf16_dev) return total;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 65535);
+  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_dev, reinterpret_cast<__nv_bfloat16*>(out_bf16_dev),
+                                                               kind, cin, cout, cout_pad);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("pack_weight_kernel launch failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  count_launch();
+  return total;
+}
+
+extern "C" int clpk_conv_igemm(const void* x, const void* w, int kind, int batch, int h_in, int w_in, int cin, int cout,
+                               const clpk_conv_epilogue* ep, void* stream) {
+  IgemmLaunch L;
+  int rc = igemm_setup(x, w, kind, batch, h_in, w_in, cin, cout, ep, &L);
+  if (rc) return rc;
+  return igemm_launch(L, (cudaStream_t)stream);
+}
+
+extern "C" int clpk_conv_direct(const void* x, const void* w, int kind, int batch, int h_in, int w_in, int cin,
+                                int cout, const clpk_conv_epilogue* ep, void* stream) {
+  IgemmLaunch L;
+  int rc = igemm_setup(x, w, kind, batch, h_in, w_in, cin, cout, ep, &L);
+  if (rc) return rc;
+  return direct_launch(L, x, w, (cudaStream_t)stream);
+}

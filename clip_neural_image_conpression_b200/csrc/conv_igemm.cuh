@@ -1,0 +1,49 @@
+// conv_igemm.cuh — host-visible description of one implicit-GEMM convolution launch.
+#pragma once
+#include "common.cuh"
+
+namespace clpk {
+
+constexpr int kMaxTapEntries = 16;  // 9 taps (3x3) or 4 phases x 4 taps (ConvTranspose 4x4 s2)
+
+// Everything the kernels need, passed by value.
+struct IgemmParams {
+  // tile grid: output pixels for the 3x3 convs, INPUT pixels for the transposed conv (each phase maps them 1:1)
+  int batch, grid_h, grid_w;
+  int cin, cout_pad;        // cout_pad = GEMM N per phase (multiple of block_n)
+  int block_k;              // 64 (128B swizzle) or 32 (64B swizzle)
+  int block_n, n_tiles_n;
+  int wbox, hbox;           // an M tile is a wbox x hbox patch of one image (wbox*hbox <= 128 rows)
+  int tiles_w, tiles_h;
+  int phases, taps, kpt;    // kpt = k-blocks per tap = cin / block_k
+  int num_tiles, stages, tmem_cols;
+  // A-operand coordinates (5-D view of the NHWC input, see make_a_map): per (phase*taps + tap)
+  int tap_x[kMaxTapEntries], tap_dw[kMaxTapEntries], tap_p[kMaxTapEntries], tap_dh[kMaxTapEntries];
+  // element strides of that 5-D view (used by the CUDA-core cross-check kernel only)
+  long long a_stride_w, a_stride_p, a_stride_h, a_stride_b;
+  int a_dim_w, a_dim_p, a_dim_h;
+  // output addressing: pixel (h, w) of the tile grid, phase (ph, pw) -> (h*out_scale + ph, w*out_scale + pw)
+  int out_h, out_w, out_scale;
+  clpk_conv_epilogue ep;
+};
+
+struct IgemmLaunch {
+  IgemmParams p;
+  CUtensorMap map_a;
+  CUtensorMap map_w;
+  int grid;
+  int smem_bytes;
+};
+
+// Fills `out` for a convolution of `kind` over x (bf16 NHWC [batch,h_in,w_in,cin]) with packed weights.
+int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, int h_in, int w_in, int cin, int cout,
+                const clpk_conv_epilogue* ep, IgemmLaunch* out);
+int igemm_init();  // one-time function attributes; call outside stream capture
+int igemm_launch(const IgemmLaunch& L, cudaStream_t stream);
+int direct_launch(const IgemmLaunch& L, const void* x_bf16, const void* w_packed, cudaStream_t stream);
+
+// padded GEMM-N of a conv with `cout` output channels, and the UMMA N tile chosen for it
+int igemm_cout_pad(int cout);
+int igemm_block_n(int cout_pad);
+
+}  // namespace clpk

@@ -1,0 +1,439 @@
+// elementwise.cu — library plumbing + the small bandwidth/latency-bound kernels of the decode path:
+// dequantise + L2 renorm, quantiser fit/encode, DDIM update, timestep embedding, small fp32 Linear, uint8 post-process,
+// uint8-domain squared error (PSNR).  sm_100a.
+#include "common.cuh"
+#include "kernels.cuh"
+
+#include <atomic>
+#include <stdarg.h>
+#include <string.h>
+
+namespace clpk {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// ------------------------------------------------------------------------------------------------ dequant + L2 norm
+// One block per row (image).  The dequantisation is __fmul_rn then __fadd_rn (numpy does two separately rounded ops,
+// reconstruct_diffusion.py:43); the norm is an fp32 tree sum -> sqrt -> max(.,1e-9) -> true division (:21-23).
+__global__ void dequant_l2norm_kernel(const uint8_t* __restrict__ q, const float* __restrict__ scale,
+                                      const float* __restrict__ zero, float* __restrict__ z, float* __restrict__ z_raw,
+                                      int dim, int l2norm) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const uint8_t* qr = q + (long long)b * dim;
+  float ss = 0.f;
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    const float v = __fadd_rn(__fmul_rn((float)qr[d], scale[d]), zero[d]);
+    if (z_raw) z_raw[(long long)b * dim + d] = v;
+    if (!l2norm) z[(long long)b * dim + d] = v;
+    ss = __fadd_rn(ss, __fmul_rn(v, v));
+  }
+  if (!l2norm) return;
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = fmaxf(__fsqrt_rn(t), 1e-9f);
+  }
+  __syncthreads();
+  const float nrm = red[0];
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    const float v = __fadd_rn(__fmul_rn((float)qr[d], scale[d]), zero[d]);
+    z[(long long)b * dim + d] = __fdiv_rn(v, nrm);
+  }
+}
+
+// q = uint8(clamp(rint((x - zero) / scale), 0, 255)) — torch.round is round-half-even == rintf (quantizer.py:32)
+__global__ void quant_encode_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                    const float* __restrict__ zero, uint8_t* __restrict__ q, long long total, int dim) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % dim);
+    float v = rintf(__fdiv_rn(__fsub_rn(x[i], zero[d]), scale[d]));
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    q[i] = (uint8_t)v;
+  }
+}
+
+// per-channel min / max over n rows (quantizer.py:23-26); one thread per channel, coalesced across channels
+__global__ void quant_fit_kernel(const float* __restrict__ x, float* __restrict__ scale, float* __restrict__ zero, int n,
+                                 int dim) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= dim) return;
+  float mn = x[d], mx = x[d];
+  for (int i = 1; i < n; ++i) {
+    const float v = x[(long long)i * dim + d];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  zero[d] = mn;
+  scale[d] = __fdiv_rn(fmaxf(__fsub_rn(mx, mn), 1e-8f), 255.f);
+}
+
+// ------------------------------------------------------------------------------------------------ DDIM update
+// ddim.py:36-45.  Every arithmetic op is individually rounded (no FMA contraction) to stay bit-identical to ATen.
+struct DdimCoef { float c_eps, c_den, c_s, c_dir, sigma; };
+
+__device__ __forceinline__ float ddim_update(float x, float e, const DdimCoef& k) {
+  float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.c_eps, e)), k.c_den);
+  // torch.clamp propagates NaN; fminf/fmaxf would drop it
+  x0 = (x0 != x0) ? x0 : fminf(fmaxf(x0, -1.f), 1.f);
+  return __fadd_rn(__fmul_rn(k.c_s, x0), __fmul_rn(k.c_dir, e));
+}
+
+// Philox4x32-10 (Salmon et al.), counter = (element quad, step), key = seed; Box-Muller to N(0,1).
+__device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+    const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n1 = lo1, n2 = hi0 ^ ctr[3] ^ k1, n3 = lo0;
+    ctr[0] = n0; ctr[1] = n1; ctr[2] = n2; ctr[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  const float u = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+  const float v = (float)b * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * __logf(u));
+  float s, c;
+  __sincosf(6.283185307179586f * v, &s, &c);
+  n0 = r * c; n1 = r * s;
+}
+
+// coef_tab: [steps][5] on the device; the step index, noise source and seed come from the device-resident DdimRun so
+// that one captured graph serves every step of every run.
+__global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                 const float* __restrict__ coef_tab, const DdimRun* __restrict__ run,
+                                 float* __restrict__ x_out, long long n) {
+  const int step = run->step;
+  const float* noise = run->noise;
+  const long long noise_step_stride = run->noise_step_stride;
+  const unsigned long long seed = run->seed;
+  DdimCoef k;
+  k.c_eps = coef_tab[step * 5 + 0]; k.c_den = coef_tab[step * 5 + 1]; k.c_s = coef_tab[step * 5 + 2];
+  k.c_dir = coef_tab[step * 5 + 3]; k.sigma = coef_tab[step * 5 + 4];
+  const bool stochastic = k.sigma > 0.f;  // ddim.py:44 `if eta > 0 and sigma_t > 0`
+  const float* nz = (noise && stochastic) ? noise + (long long)step * noise_step_stride : nullptr;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 ev = reinterpret_cast<const float4*>(eps)[i];
+    float4 o;
+    o.x = ddim_update(xv.x, ev.x, k); o.y = ddim_update(xv.y, ev.y, k);
+    o.z = ddim_update(xv.z, ev.z, k); o.w = ddim_update(xv.w, ev.w, k);
+    if (stochastic) {
+      float4 z;
+      if (nz) {
+        z = reinterpret_cast<const float4*>(nz)[i];
+      } else {
+        uint32_t ctr[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)step, 0x636c706bu};
+        philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+        box_muller(ctr[0], ctr[1], z.x, z.y);
+        box_muller(ctr[2], ctr[3], z.z, z.w);
+      }
+      o.x = __fadd_rn(o.x, __fmul_rn(k.sigma, z.x)); o.y = __fadd_rn(o.y, __fmul_rn(k.sigma, z.y));
+      o.z = __fadd_rn(o.z, __fmul_rn(k.sigma, z.z)); o.w = __fadd_rn(o.w, __fmul_rn(k.sigma, z.w));
+    }
+    reinterpret_cast<float4*>(x_out)[i] = o;
+  }
+  // tail (n % 4)
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float o = ddim_update(x[i], eps[i], k);
+    if (stochastic) {
+      float z;
+      if (nz) {
+        z = nz[i];
+      } else {
+        uint32_t ctr[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)step, 0x7461696cu};
+        philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+        float z1;
+        box_muller(ctr[0], ctr[1], z, z1);
+      }
+      o = __fadd_rn(o, __fmul_rn(k.sigma, z));
+    }
+    x_out[i] = o;
+  }
+}
+
+int launch_ddim_step(const float* x, const float* eps, const float* coef_tab_dev, const DdimRun* run_dev, float* x_out,
+                     long long n, cudaStream_t stream) {
+  const long long work = (n + 3) / 4;
+  const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)num_sms() * 8);
+  ddim_step_kernel<<<std::max(blocks, 1), 256, 0, stream>>>(x, eps, coef_tab_dev, run_dev, x_out, n);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+__global__ void ddim_advance_kernel(DdimRun* run) { run->step += 1; }
+int launch_ddim_advance(DdimRun* run_dev, cudaStream_t stream) {
+  ddim_advance_kernel<<<1, 1, 0, stream>>>(run_dev);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+// h[b,:] = zemb[b,:] + ht_tab[run->step,:]   (unet.py:86 with the step-invariant / batch-invariant halves hoisted)
+__global__ void cond_combine_kernel(const float* __restrict__ zemb, const float* __restrict__ ht_tab,
+                                    const DdimRun* __restrict__ run, float* __restrict__ h, int batch, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * dim) return;
+  const int d = i % dim;
+  h[i] = __fadd_rn(ht_tab[(long long)run->step * dim + d], zemb[i]);
+}
+int launch_cond_combine(const float* zemb, const float* ht_tab, const DdimRun* run, float* h, int batch, int dim,
+                        cudaStream_t stream) {
+  cond_combine_kernel<<<(batch * dim + 255) / 256, 256, 0, stream>>>(zemb, ht_tab, run, h, batch, dim);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+__global__ void add_const_kernel(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += v;
+}
+int launch_add_const(float* p, float v, int n, cudaStream_t stream) {
+  add_const_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p, v, n);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ timestep embedding
+// unet.py:33-36: freqs = exp(float32(-ln(max_period)) * k / half) evaluated in fp32; args = float(t) * freqs.
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int batch, int dim,
+                                          float neg_log_period) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * half) return;
+  const int b = i / half, k = i - b * half;
+  const float f = expf(__fdiv_rn(__fmul_rn(neg_log_period, (float)k), (float)half));
+  const float a = __fmul_rn((float)t[b], f);
+  out[(long long)b * dim + k] = cosf(a);
+  out[(long long)b * dim + half + k] = sinf(a);
+  if ((dim & 1) && k == 0) out[(long long)b * dim + dim - 1] = 0.f;
+}
+
+int launch_timestep_embedding(const int64_t* t, float* out, int batch, int dim, float max_period, cudaStream_t stream) {
+  const int total = batch * (dim / 2);
+  // float32(-math.log(max_period)): the reference evaluates the log in double and rounds once (unet.py:33)
+  const float neg_log_period = (float)(-log((double)max_period));
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, stream>>>(t, out, batch, dim, neg_log_period);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ small fp32 Linear
+// y[m,n] = act(dot(x[m,:], w[n,:]) + b[n]) (+ add[m % add_rows, n]).  One warp per output column n, looping over rows
+// in groups of 8 so each weight row is read once per 8 rows.  M is the batch (<= a few hundred): FLOPs are negligible.
+__global__ void linear_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                              const float* __restrict__ add, int add_rows, float* __restrict__ y, int m, int n, int k,
+                              int act) {
+  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (col >= n) return;
+  const float* wr = w + (long long)col * k;
+  const float bias = b ? b[col] : 0.f;
+  for (int m0 = blockIdx.y * 8; m0 < m; m0 += gridDim.y * 8) {
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int kk = lane; kk < k; kk += 32) {
+      const float wv = wr[kk];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (m0 + r < m) acc[r] = fmaf(x[(long long)(m0 + r) * k + kk], wv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float s = warp_sum(acc[r]);
+      if (lane == 0 && m0 + r < m) {
+        float v = s + bias;
+        if (act == 1) v = v / (1.0f + expf(-v));
+        if (add) v += add[(long long)((m0 + r) % add_rows) * n + col];
+        y[(long long)(m0 + r) * n + col] = v;
+      }
+    }
+  }
+}
+
+int launch_linear(const float* x, const float* w, const float* b, const float* add, int add_rows, float* y, int m, int n,
+                  int k, int act, cudaStream_t stream) {
+  dim3 grid((n + 7) / 8, std::min((m + 7) / 8, 64));
+  linear_kernel<<<grid, 256, 0, stream>>>(x, w, b, add, add_rows > 0 ? add_rows : m, y, m, n, k, act);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ standalone FiLM
+// y = x * scale1p[b,c] + shift[b,c] over NCHW (blocks.py:22-25); inside the UNet this lives in the conv1 epilogue.
+__global__ void film_apply_kernel(const float* __restrict__ x, const float* __restrict__ sc, const float* __restrict__ sh,
+                                  float* __restrict__ y, long long total, int hw) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long bc = i / hw;
+    y[i] = __fadd_rn(__fmul_rn(x[i], sc[bc]), sh[bc]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ output post-process
+__device__ __forceinline__ uint8_t to_u8_trunc(float v) {
+  // ((clamp(v,-1,1) + 1) * 127.5).astype(uint8): separately rounded add and mul, C truncation
+  const float c = fminf(fmaxf(v, -1.f), 1.f);
+  return (uint8_t)(int)__fmul_rn(__fadd_rn(c, 1.0f), 127.5f);
+}
+
+__global__ void to_uint8_hwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int batch, int ch, int h,
+                                    int w) {
+  const long long total = (long long)batch * h * w * ch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ch);
+    long long r = i / ch;
+    const int xx = (int)(r % w); r /= w;
+    const int yy = (int)(r % h);
+    const int b = (int)(r / h);
+    out[i] = to_u8_trunc(x[(((long long)b * ch + c) * h + yy) * w + xx]);
+  }
+}
+
+// metrics.py:16-19 _to_uint8: ((img+1)*127.5).clip(0,255).astype(uint8);  :26 squared difference summed exactly in int64
+__device__ __forceinline__ int metric_u8(float v) {
+  const float s = __fmul_rn(__fadd_rn(v, 1.0f), 127.5f);
+  return (int)fminf(fmaxf(s, 0.f), 255.f);
+}
+__global__ void psnr_sqerr_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                  unsigned long long* __restrict__ out, long long per_image) {
+  const int img = blockIdx.y;
+  const float* pa = a + (long long)img * per_image;
+  const float* pb = b + (long long)img * per_image;
+  unsigned long long acc = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_image;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = metric_u8(pa[i]) - metric_u8(pb[i]);
+    acc += (unsigned long long)(d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out + img, acc);  // integer atomics: order independent, exact
+}
+
+}  // namespace clpk
+
+using namespace clpk;
+
+extern "C" const char* clpk_last_error(void) { return g_err; }
+extern "C" int clpk_version(void) { return 100; }
+extern "C" uint64_t clpk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int clpk_dequant_l2norm_u8(const uint8_t* q, const float* scale, const float* zero, float* z, float* z_raw,
+                                      int batch, int dim, int l2norm, void* stream) {
+  CLPK_REQUIRE(batch >= 0 && dim > 0, "clpk_dequant_l2norm_u8: bad shape");
+  CLPK_REQUIRE(q && scale && zero && z, "clpk_dequant_l2norm_u8: null pointer");
+  if (batch == 0) return CLPK_OK;
+  dequant_l2norm_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(q, scale, zero, z, z_raw, dim, l2norm);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+extern "C" int clpk_quant_encode_u8(const float* x, const float* scale, const float* zero, uint8_t* q, int batch, int dim,
+                                    void* stream) {
+  CLPK_REQUIRE(batch >= 0 && dim > 0 && x && scale && zero && q, "clpk_quant_encode_u8: bad arguments");
+  if (batch == 0) return CLPK_OK;
+  const long long total = (long long)batch * dim;
+  quant_encode_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, (cudaStream_t)stream>>>(
+      x, scale, zero, q, total, dim);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+extern "C" int clpk_quant_fit(const float* x, float* scale, float* zero, int n, int dim, void* stream) {
+  CLPK_REQUIRE(n > 0 && dim > 0 && x && scale && zero, "clpk_quant_fit: bad arguments");
+  quant_fit_kernel<<<(dim + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, scale, zero, n, dim);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+extern "C" int clpk_ddim_step(const float* x, const float* eps, const float* noise, const float* coef5_host,
+                              float* x_out, int64_t n, void* stream) {
+  CLPK_REQUIRE(x && eps && coef5_host && x_out && n >= 0, "clpk_ddim_step: bad arguments");
+  if (n == 0) return CLPK_OK;
+  CLPK_REQUIRE((((uintptr_t)x | (uintptr_t)eps | (uintptr_t)x_out | (uintptr_t)noise) & 15) == 0,
+               "clpk_ddim_step: pointers must be 16-byte aligned");
+  // coefficients + run state travel through a small device block so the kernel is the same one the graph replays
+  struct { float coef[8]; DdimRun run; } host_blk;
+  memset(&host_blk, 0, sizeof(host_blk));
+  memcpy(host_blk.coef, coef5_host, 5 * sizeof(float));
+  host_blk.run.step = 0;
+  host_blk.run.noise = noise;
+  char* blk = nullptr;
+  CLPK_CHECK_CUDA(cudaMalloc(&blk, sizeof(host_blk)));
+  cudaError_t e = cudaMemcpyAsync(blk, &host_blk, sizeof(host_blk), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  int rc = CLPK_OK;
+  if (e != cudaSuccess) { set_error("clpk_ddim_step: memcpy failed: %s", cudaGetErrorString(e)); rc = CLPK_ERR_CUDA; }
+  if (!rc)
+    rc = launch_ddim_step(x, eps, reinterpret_cast<const float*>(blk),
+                          reinterpret_cast<const DdimRun*>(blk + 8 * sizeof(float)), x_out, n, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);  // host_blk is on this stack frame; blk is freed right below
+  cudaFree(blk);
+  return rc;
+}
+
+extern "C" int clpk_timestep_embedding(const int64_t* t, float* out, int batch, int dim, float max_period,
+                                       void* stream) {
+  CLPK_REQUIRE(t && out && batch > 0 && dim >= 2, "clpk_timestep_embedding: bad arguments");
+  return launch_timestep_embedding(t, out, batch, dim, max_period, (cudaStream_t)stream);
+}
+
+extern "C" int clpk_linear(const float* x, const float* w, const float* b, const float* add, float* y, int m, int n,
+                           int k, int act, void* stream) {
+  CLPK_REQUIRE(x && w && y && m > 0 && n > 0 && k > 0, "clpk_linear: bad arguments");
+  return launch_linear(x, w, b, add, m, y, m, n, k, act, (cudaStream_t)stream);
+}
+
+extern "C" int clpk_film_apply(const float* x, const float* scale1p, const float* shift, float* y, int batch, int ch,
+                               int hw, void* stream) {
+  CLPK_REQUIRE(x && scale1p && shift && y && batch > 0 && ch > 0 && hw > 0, "clpk_film_apply: bad arguments");
+  const long long total = (long long)batch * ch * hw;
+  film_apply_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16), 256, 0,
+                      (cudaStream_t)stream>>>(x, scale1p, shift, y, total, hw);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+extern "C" int clpk_to_uint8_hwc(const float* x, uint8_t* out, int batch, int ch, int h, int w, void* stream) {
+  CLPK_REQUIRE(x && out && batch > 0 && ch > 0 && h > 0 && w > 0, "clpk_to_uint8_hwc: bad arguments");
+  const long long total = (long long)batch * ch * h * w;
+  to_uint8_hwc_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16), 256, 0,
+                        (cudaStream_t)stream>>>(x, out, batch, ch, h, w);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+extern "C" int clpk_psnr_sqerr_u8(const float* a, const float* b, int64_t* out, int batch, int64_t per_image,
+                                  void* stream) {
+  CLPK_REQUIRE(a && b && out && batch > 0 && per_image > 0, "clpk_psnr_sqerr_u8: bad arguments");
+  CLPK_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t) * batch, (cudaStream_t)stream));
+  dim3 grid((unsigned)std::min<long long>((per_image + 255) / 256, 256), (unsigned)batch);
+  psnr_sqerr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, reinterpret_cast<unsigned long long*>(out),
+                                                           per_image);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}

@@ -1,0 +1,215 @@
+// groupnorm.cu — GroupNorm(groups, C) [+ SiLU] over NHWC fp32 activations, bf16 NHWC output (the conv A operand).
+//
+// Replaces nn.GroupNorm + nn.SiLU of the reference ResBlock (PKG/models/blocks.py:33,35,41,43) and out_norm
+// (PKG/models/unet.py:78,105 — no SiLU there).  Statistics are per (image, group) over (C/groups)*H*W elements,
+// biased variance, eps inside the sqrt (torch semantics).
+//
+// Two memory-bound passes (HBM roofline): (1) gn_stats: one read of x, fp32 per-thread sums, deterministic block
+// reduction, per-block partials; the LAST block of each image folds the partials in fp64 and publishes (mean, rstd)
+// — no float atomics, so results are run-to-run identical.  (2) gn_apply: one read of x, one bf16 write.
+#include "kernels.cuh"
+
+namespace clpk {
+
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxJ = 4;
+
+GnShape gn_shape(int batch, int hw, int c, int groups) {
+  GnShape s;
+  s.batch = batch; s.hw = hw; s.c = c; s.groups = groups;
+  // enough blocks to fill the machine a few times, but >= 32 pixels per block
+  const int want = std::max(1, (num_sms() * 4 + batch - 1) / batch);
+  s.chunks = std::max(1, std::min(want, (hw + 31) / 32));
+  return s;
+}
+
+// ws layout: int counter[B] (always at offset 0 and always left at zero, so one ws can serve every shape of a plan)
+//            | float2 stats[B][G] | float2 partial[B][chunks][G]
+static inline long long ws_counter_bytes(const GnShape& s) { return ((long long)s.batch * 4 + 255) / 256 * 256; }
+static inline long long ws_stats_bytes(const GnShape& s) { return ((long long)s.batch * s.groups * 8 + 255) / 256 * 256; }
+static inline long long ws_partial_bytes(const GnShape& s) { return (long long)s.batch * s.chunks * s.groups * 8; }
+long long gn_ws_bytes(const GnShape& s) {
+  return ((ws_counter_bytes(s) + ws_stats_bytes(s) + ws_partial_bytes(s) + 255) / 256) * 256;
+}
+
+template <int J>
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float2* __restrict__ stats,
+                int* __restrict__ counter, int hw, int c, int groups, int chunks, int pix_per_chunk, float eps) {
+  __shared__ float2 red[kGnThreads * J];
+  __shared__ int is_last;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int qc = c >> 2;           // float4 quads per pixel
+  const int cpg = c / groups;
+  const int tid = threadIdx.x, T = blockDim.x;
+  int ppb, poff, q[J];
+  if (J == 1) {
+    // ppb whole pixels per block iteration; threads beyond ppb*qc (block rounded up to a warp multiple) idle
+    ppb = kGnThreads / qc; poff = tid / qc; q[0] = (poff < ppb) ? tid - poff * qc : qc;
+  } else {
+    ppb = 1; poff = 0;
+#pragma unroll
+    for (int j = 0; j < J; ++j) q[j] = tid + j * T;
+  }
+  float s[J], ss[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+  const int p0 = chunk * pix_per_chunk;
+  const int p1 = min(hw, p0 + pix_per_chunk);
+  const float4* xb = reinterpret_cast<const float4*>(x) + (long long)b * hw * qc;
+  int p = p0 + poff;
+  // 4 pixels in flight per thread
+  for (; p + 3 * ppb < p1; p += 4 * ppb) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      if (q[j] < qc) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + (long long)(p + u * ppb) * qc + q[j]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          s[j] += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+          ss[j] += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w);
+        }
+      }
+    }
+  }
+  for (; p < p1; p += ppb) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      if (q[j] < qc) {
+        const float4 v = __ldg(xb + (long long)p * qc + q[j]);
+        s[j] += (v.x + v.y) + (v.z + v.w);
+        ss[j] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) red[j * T + tid] = make_float2(s[j], ss[j]);
+  __syncthreads();
+  // fixed-order reduction: warp w folds the entries of groups w, w+nwarps, ...
+  const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  for (int g = warp; g < groups; g += nwarps) {
+    float gs = 0.f, gss = 0.f;
+    for (int e = lane; e < J * T; e += 32) {
+      const int et = e % T;
+      const int eq = (J == 1) ? (et % qc) : e;  // J>1: entry index == quad index
+      const bool live = (J == 1) ? (et < ppb * qc) : (eq < qc);
+      if (live && (eq * 4) / cpg == g) { gs += red[e].x; gss += red[e].y; }
+    }
+    gs = warp_sum(gs); gss = warp_sum(gss);
+    if (lane == 0) partial[((long long)b * chunks + chunk) * groups + g] = make_float2(gs, gss);
+  }
+  // last block of this image publishes (mean, rstd)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(counter + b, 1) == chunks - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (tid < groups) {
+      double S = 0.0, SS = 0.0;
+      const float2* pp = partial + (long long)b * chunks * groups + tid;
+      for (int k = 0; k < chunks; ++k) {
+        const float2 v = __ldcg(pp + (long long)k * groups);
+        S += (double)v.x; SS += (double)v.y;
+      }
+      const double n = (double)hw * (double)cpg;
+      const double mean = S / n;
+      double var = SS / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[(long long)b * groups + tid] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    if (tid == 0) counter[b] = 0;  // ready for the next launch / graph replay
+  }
+}
+
+// y = (x - mean) * rstd * gamma + beta, optional SiLU, 8 channels (32 B in, 16 B out) per thread iteration.
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float2* __restrict__ stats, __nv_bfloat16* __restrict__ y, int hw, int c, int groups, int silu) {
+  const int b = blockIdx.y;
+  const unsigned oc = (unsigned)c >> 3;  // 8-channel octets per pixel
+  const int cpg = c / groups;
+  const unsigned total = (unsigned)hw * oc;
+  const float4* xb = reinterpret_cast<const float4*>(x) + (long long)b * total * 2;
+  uint4* yb = reinterpret_cast<uint4*>(y) + (long long)b * total;
+  const float2* st = stats + (long long)b * groups;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned o = i % oc;
+    const int ch = (int)o * 8;
+    const float4 v0 = __ldcs(xb + 2ll * i), v1 = __ldcs(xb + 2ll * i + 1);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch) + 1);
+    const float2 s0 = __ldg(st + ch / cpg), s1 = __ldg(st + (ch + 4) / cpg);
+    float r[8];
+    r[0] = (v0.x - s0.x) * s0.y * g0.x + b0.x; r[1] = (v0.y - s0.x) * s0.y * g0.y + b0.y;
+    r[2] = (v0.z - s0.x) * s0.y * g0.z + b0.z; r[3] = (v0.w - s0.x) * s0.y * g0.w + b0.w;
+    r[4] = (v1.x - s1.x) * s1.y * g1.x + b1.x; r[5] = (v1.y - s1.x) * s1.y * g1.y + b1.y;
+    r[6] = (v1.z - s1.x) * s1.y * g1.z + b1.z; r[7] = (v1.w - s1.x) * s1.y * g1.w + b1.w;
+    if (silu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = silu_f(r[k]);
+    }
+    yb[i] = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                       pack_bf16x2(r[6], r[7]));
+  }
+}
+
+int launch_groupnorm(const float* x, const float* gamma, const float* beta, void* y_bf16, void* ws, const GnShape& s,
+                     float eps, int silu, cudaStream_t stream) {
+  CLPK_REQUIRE(s.c % 8 == 0 && s.c % s.groups == 0 && (s.c / s.groups) % 4 == 0,
+               "GroupNorm needs C %% 8 == 0 and (C/groups) %% 4 == 0 (C=%d groups=%d)", s.c, s.groups);
+  CLPK_REQUIRE(s.c <= 4 * kGnMaxJ * kGnThreads, "GroupNorm supports C <= %d", 4 * kGnMaxJ * kGnThreads);
+  int* counter = reinterpret_cast<int*>(ws);
+  float2* stats = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) + ws_counter_bytes(s));
+  float2* partial = reinterpret_cast<float2*>(reinterpret_cast<char*>(stats) + ws_stats_bytes(s));
+  const int qc = s.c / 4;
+  const int pix_per_chunk = (s.hw + s.chunks - 1) / s.chunks;
+  dim3 grid(s.chunks, s.batch);
+  if (qc <= kGnThreads) {
+    const int threads = ((kGnThreads / qc) * qc + 31) / 32 * 32;
+    gn_stats_kernel<1><<<grid, threads, 0, stream>>>(x, partial, stats, counter, s.hw, s.c, s.groups, s.chunks,
+                                                     pix_per_chunk, eps);
+  } else {
+    const int j = (qc + kGnThreads - 1) / kGnThreads;
+    if (j == 2)
+      gn_stats_kernel<2><<<grid, kGnThreads, 0, stream>>>(x, partial, stats, counter, s.hw, s.c, s.groups, s.chunks,
+                                                          pix_per_chunk, eps);
+    else if (j == 3)
+      gn_stats_kernel<3><<<grid, kGnThreads, 0, stream>>>(x, partial, stats, counter, s.hw, s.c, s.groups, s.chunks,
+                                                          pix_per_chunk, eps);
+    else
+      gn_stats_kernel<4><<<grid, kGnThreads, 0, stream>>>(x, partial, stats, counter, s.hw, s.c, s.groups, s.chunks,
+                                                          pix_per_chunk, eps);
+  }
+  CLPK_CHECK_LAUNCH();
+  const long long octs = (long long)s.hw * (s.c / 8);
+  CLPK_REQUIRE(octs < (1ll << 31), "image too large for GroupNorm indexing");
+  const int per_img_blocks = (int)std::min<long long>((octs + kGnThreads - 1) / kGnThreads,
+                                                      std::max(1, num_sms() * 8 / s.batch));
+  dim3 agrid(std::max(per_img_blocks, 1), s.batch);
+  gn_apply_kernel<<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, reinterpret_cast<__nv_bfloat16*>(y_bf16),
+                                                   s.hw, s.c, s.groups, silu);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+}  // namespace clpk
+
+using namespace clpk;
+
+extern "C" int64_t clpk_groupnorm_ws_bytes(int batch, int hw, int c, int groups) {
+  if (batch <= 0 || hw <= 0 || c <= 0 || groups <= 0) return -1;
+  return gn_ws_bytes(gn_shape(batch, hw, c, groups));
+}
+
+extern "C" int clpk_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* y, void* ws, int batch,
+                                   int hw, int c, int groups, float eps, int silu, void* stream) {
+  CLPK_REQUIRE(x && gamma && beta && y && ws && batch > 0 && hw > 0 && c > 0 && groups > 0,
+               "clpk_groupnorm_silu: bad arguments");
+  const GnShape s = gn_shape(batch, hw, c, groups);
+  // the leaf entry point cannot assume the counters (start of ws) are zero
+  CLPK_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)batch * 4, (cudaStream_t)stream));
+  return launch_groupnorm(x, gamma, beta, y, ws, s, eps, silu, (cudaStream_t)stream);
+}

@@ -1,0 +1,43 @@
+// kernels.cuh — internal launchers shared between translation units of libclpk.so.
+#pragma once
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace clpk {
+
+// Device-resident state of one DDIM run (read by the captured step graph, advanced by ddim_advance).
+struct DdimRun {
+  int step;
+  int pad_;
+  const float* noise;            // [steps][n] pre-drawn N(0,1) or nullptr (-> in-kernel Philox)
+  long long noise_step_stride;   // n
+  unsigned long long seed;
+};
+
+// elementwise.cu
+int launch_ddim_step(const float* x, const float* eps, const float* coef_tab_dev, const DdimRun* run_dev, float* x_out,
+                     long long n, cudaStream_t stream);
+int launch_ddim_advance(DdimRun* run_dev, cudaStream_t stream);
+int launch_cond_combine(const float* zemb, const float* ht_tab, const DdimRun* run, float* h, int batch, int dim,
+                        cudaStream_t stream);
+int launch_add_const(float* p, float v, int n, cudaStream_t stream);
+int launch_timestep_embedding(const int64_t* t, float* out, int batch, int dim, float max_period, cudaStream_t stream);
+int launch_linear(const float* x, const float* w, const float* b, const float* add, int add_rows, float* y, int m, int n,
+                  int k, int act, cudaStream_t stream);
+
+// groupnorm.cu
+struct GnShape {
+  int batch, hw, c, groups;
+  int chunks;  // partial-sum blocks per image
+};
+GnShape gn_shape(int batch, int hw, int c, int groups);
+long long gn_ws_bytes(const GnShape& s);
+int launch_groupnorm(const float* x, const float* gamma, const float* beta, void* y_bf16, void* ws, const GnShape& s,
+                     float eps, int silu, cudaStream_t stream);
+
+// conv_in.cu
+int launch_conv_in(const float* x_nchw, const float* w, const float* b, float* y_nhwc, int batch, int cin, int h, int w_,
+                   int cout, cudaStream_t stream);
+
+}  // namespace clpk

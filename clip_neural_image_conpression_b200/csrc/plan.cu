@@ -1,0 +1,505 @@
+// plan.cu — plan-level entry points: the whole CLIPCondUNet forward (PKG/models/unet.py:81-106) and the DDIM loop
+// (PKG/diffusion/ddim.py:21-46) as a fixed launch sequence over plan-owned device memory, captured into a CUDA graph.
+//
+// HBM layout (all plan-owned, sized for the plan's fixed batch B and image size):
+//   X[l]  fp32 NHWC  residual stream of resolution level l (l = 0 .. n_levels); X[l] doubles as the skip tensor
+//   Y     fp32 NHWC  conv1 output of the current ResBlock (max size over levels)
+//   T     bf16 NHWC  GroupNorm+SiLU output = A operand of the ResBlock convs (max size)
+//   D     bf16 NHWC  bf16 copy of x feeding the stride-2 / transposed convs (max size)
+//   packed bf16 weights [Cout][tap][Cin] per conv, fp32 bias / gamma / beta / Linear weights, FiLM weights of all
+//   ResBlocks concatenated into one [2*sumC, time_dim] matrix so ONE small GEMV launch yields every (1+scale, shift).
+#include "conv_igemm.cuh"
+#include "kernels.cuh"
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace clpk {
+
+struct ConvPlan {
+  int kind = 0, cin = 0, cout = 0, h_in = 0, w_in = 0;
+  __nv_bfloat16* w = nullptr;
+  float* bias = nullptr;
+  IgemmLaunch L;
+  double flops = 0;
+};
+
+struct ResBlockPlan {
+  int c = 0, h = 0, w = 0, level = 0;
+  float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+  ConvPlan conv1, conv2;
+  int film_off = 0;      // scale1p at [film_off, film_off+c), shift at [film_off+c, film_off+2c)
+  bool emit_bf16 = false;  // conv2 also writes a bf16 copy of x into D (feeds the next resampling conv)
+};
+
+}  // namespace clpk
+
+using namespace clpk;
+
+struct clpk_plan {
+  clpk_unet_config cfg;
+  int B = 0, H = 0, W = 0;
+  int n_levels = 0;
+  std::vector<int> lv_c, lv_h, lv_w;  // size n_levels + 1
+  std::vector<void*> allocs;
+  long long bytes = 0;
+  // parameters
+  float *tp0_w = nullptr, *tp0_b = nullptr, *tp2_w = nullptr, *tp2_b = nullptr, *zp_w = nullptr, *zp_b = nullptr;
+  float *in_w = nullptr, *in_b = nullptr, *on_g = nullptr, *on_b = nullptr;
+  float *film_w = nullptr, *film_b = nullptr;
+  int film_n = 0;  // 2 * sum of ResBlock channels
+  std::vector<ResBlockPlan> rbs;     // execution order
+  std::vector<ConvPlan> downs, ups;  // per level
+  ConvPlan out_conv;
+  // workspace
+  std::vector<float*> X;
+  float* Y = nullptr;
+  __nv_bfloat16 *T = nullptr, *D = nullptr;
+  void* gn_ws = nullptr;
+  float *temb = nullptr, *h1 = nullptr, *ht = nullptr, *hcond = nullptr, *film = nullptr, *zemb = nullptr;
+  int64_t* t_buf = nullptr;
+  float* eps_buf = nullptr;  // NCHW eps of the current step
+  float* x_buf = nullptr;    // NCHW DDIM state
+  double flops_fwd = 0;
+  int launches_fwd = 0;
+  // DDIM state
+  int steps = 0;
+  float *ht_tab = nullptr, *coef_tab = nullptr;
+  DdimRun* run_dev = nullptr;
+  bool any_sigma = false;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+
+  template <typename Tp>
+  int alloc(Tp** p, long long n_elems) {
+    void* q = nullptr;
+    const size_t nb = (size_t)std::max<long long>(n_elems, 1) * sizeof(Tp);
+    cudaError_t e = cudaMalloc(&q, nb);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", nb, cudaGetErrorString(e));
+      return CLPK_ERR_CUDA;
+    }
+    allocs.push_back(q);
+    bytes += (long long)nb;
+    *p = reinterpret_cast<Tp*>(q);
+    return CLPK_OK;
+  }
+};
+
+namespace {
+
+struct ParamTable {
+  std::map<std::string, std::pair<const float*, int64_t>> m;
+  int get(const std::string& name, int64_t numel, const float** out) const {
+    auto it = m.find(name);
+    if (it == m.end()) {
+      set_error("state dict is missing parameter '%s'", name.c_str());
+      return CLPK_ERR_ARG;
+    }
+    if (it->second.second != numel) {
+      set_error("parameter '%s' has %lld elements, expected %lld", name.c_str(), (long long)it->second.second,
+                (long long)numel);
+      return CLPK_ERR_ARG;
+    }
+    *out = it->second.first;
+    return CLPK_OK;
+  }
+};
+
+#define CLPK_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != CLPK_OK) return _rc; \
+  } while (0)
+
+int copy_param(clpk_plan* P, const ParamTable& tab, const std::string& name, int64_t numel, float** dst) {
+  const float* src = nullptr;
+  CLPK_TRY(tab.get(name, numel, &src));
+  CLPK_TRY(P->alloc(dst, numel));
+  CLPK_CHECK_CUDA(cudaMemcpy(*dst, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice));
+  return CLPK_OK;
+}
+
+int make_conv(clpk_plan* P, const ParamTable& tab, const std::string& prefix, int kind, int cin, int cout, int h_in,
+              int w_in, ConvPlan* cv) {
+  cv->kind = kind; cv->cin = cin; cv->cout = cout; cv->h_in = h_in; cv->w_in = w_in;
+  const int taps = (kind == CLPK_CONVT_4X4_S2) ? 16 : 9;
+  const float* w = nullptr;
+  CLPK_TRY(tab.get(prefix + ".weight", (int64_t)cin * cout * taps, &w));
+  const int64_t n = clpk_pack_conv_weight(nullptr, nullptr, kind, cin, cout, nullptr);
+  if (n < 0) return CLPK_ERR_ARG;
+  CLPK_TRY(P->alloc(&cv->w, n));
+  if (clpk_pack_conv_weight(w, cv->w, kind, cin, cout, nullptr) < 0) return CLPK_ERR_CUDA;
+  // bias padded to the GEMM N (zeros beyond cout) so the vectorised epilogue may read whole 16-wide chunks
+  const int cout_pad = igemm_cout_pad(cout);
+  const float* b = nullptr;
+  CLPK_TRY(tab.get(prefix + ".bias", cout, &b));
+  CLPK_TRY(P->alloc(&cv->bias, cout_pad));
+  CLPK_CHECK_CUDA(cudaMemset(cv->bias, 0, (size_t)cout_pad * sizeof(float)));
+  CLPK_CHECK_CUDA(cudaMemcpy(cv->bias, b, (size_t)cout * sizeof(float), cudaMemcpyDeviceToDevice));
+  const long long out_pix = (kind == CLPK_CONV_3X3_S2) ? (long long)(h_in / 2) * (w_in / 2) : (long long)h_in * w_in;
+  cv->flops = 2.0 * P->B * (double)out_pix * cout * cin * (kind == CLPK_CONVT_4X4_S2 ? 16 : 9);
+  return CLPK_OK;
+}
+
+int make_resblock(clpk_plan* P, const ParamTable& tab, const std::string& prefix, int level, ResBlockPlan* rb) {
+  const int c = P->lv_c[level], h = P->lv_h[level], w = P->lv_w[level], td = P->cfg.time_dim;
+  rb->c = c; rb->h = h; rb->w = w; rb->level = level;
+  CLPK_TRY(copy_param(P, tab, prefix + ".norm1.weight", c, &rb->g1));
+  CLPK_TRY(copy_param(P, tab, prefix + ".norm1.bias", c, &rb->b1));
+  CLPK_TRY(copy_param(P, tab, prefix + ".norm2.weight", c, &rb->g2));
+  CLPK_TRY(copy_param(P, tab, prefix + ".norm2.bias", c, &rb->b2));
+  CLPK_TRY(make_conv(P, tab, prefix + ".conv1", CLPK_CONV_3X3_S1, c, c, h, w, &rb->conv1));
+  CLPK_TRY(make_conv(P, tab, prefix + ".conv2", CLPK_CONV_3X3_S1, c, c, h, w, &rb->conv2));
+  // FiLM rows into the concatenated matrix: [scale rows | shift rows]; "+1" folded into the scale bias
+  const float *sw, *sb, *hw_, *hb;
+  CLPK_TRY(tab.get(prefix + ".film.to_scale.weight", (int64_t)c * td, &sw));
+  CLPK_TRY(tab.get(prefix + ".film.to_scale.bias", c, &sb));
+  CLPK_TRY(tab.get(prefix + ".film.to_shift.weight", (int64_t)c * td, &hw_));
+  CLPK_TRY(tab.get(prefix + ".film.to_shift.bias", c, &hb));
+  const size_t row = (size_t)td * sizeof(float);
+  CLPK_CHECK_CUDA(cudaMemcpy(P->film_w + (size_t)rb->film_off * td, sw, row * c, cudaMemcpyDeviceToDevice));
+  CLPK_CHECK_CUDA(cudaMemcpy(P->film_w + (size_t)(rb->film_off + c) * td, hw_, row * c, cudaMemcpyDeviceToDevice));
+  CLPK_CHECK_CUDA(cudaMemcpy(P->film_b + rb->film_off, sb, (size_t)c * sizeof(float), cudaMemcpyDeviceToDevice));
+  CLPK_CHECK_CUDA(cudaMemcpy(P->film_b + rb->film_off + c, hb, (size_t)c * sizeof(float), cudaMemcpyDeviceToDevice));
+  CLPK_TRY(launch_add_const(P->film_b + rb->film_off, 1.0f, c, nullptr));
+  return CLPK_OK;
+}
+
+// bind the buffers of a conv (A operand, epilogue) and encode its tensor maps
+int bind_conv(clpk_plan* P, ConvPlan* cv, const void* a, const clpk_conv_epilogue& ep) {
+  return igemm_setup(a, cv->w, cv->kind, P->B, cv->h_in, cv->w_in, cv->cin, cv->cout, &ep, &cv->L);
+}
+
+int run_groupnorm(clpk_plan* P, const float* x, const float* g, const float* b, int level, int silu, cudaStream_t s) {
+  const GnShape shp = gn_shape(P->B, P->lv_h[level] * P->lv_w[level], P->lv_c[level], std::min(P->cfg.groups, P->lv_c[level]));
+  return launch_groupnorm(x, g, b, P->T, P->gn_ws, shp, 1e-5f, silu, s);
+}
+
+int run_resblock(clpk_plan* P, ResBlockPlan& rb, cudaStream_t s) {
+  float* X = P->X[rb.level];
+  CLPK_TRY(run_groupnorm(P, X, rb.g1, rb.b1, rb.level, 1, s));     // blocks.py:41 act(norm1(x))
+  CLPK_TRY(igemm_launch(rb.conv1.L, s));                           // conv1 + FiLM -> Y   (blocks.py:41-42)
+  CLPK_TRY(run_groupnorm(P, P->Y, rb.g2, rb.b2, rb.level, 1, s));  // blocks.py:43 act(norm2(y))
+  CLPK_TRY(igemm_launch(rb.conv2.L, s));                           // conv2 + x -> X      (blocks.py:43-44)
+  return CLPK_OK;
+}
+
+// everything after the conditioning vector: in_conv ... out   (unet.py:88-105).  film = [B, film_n].
+int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s) {
+  const clpk_unet_config& c = P->cfg;
+  CLPK_TRY(launch_conv_in(x_nchw, P->in_w, P->in_b, P->X[0], P->B, c.img_ch, P->H, P->W, c.base, s));
+  size_t r = 0;
+  for (int l = 0; l < P->n_levels; ++l) {
+    CLPK_TRY(run_resblock(P, P->rbs[r++], s));
+    CLPK_TRY(run_resblock(P, P->rbs[r++], s));
+    CLPK_TRY(igemm_launch(P->downs[l].L, s));  // D (bf16 copy of X[l]) -> X[l+1]
+  }
+  CLPK_TRY(run_resblock(P, P->rbs[r++], s));
+  CLPK_TRY(run_resblock(P, P->rbs[r++], s));
+  for (int l = P->n_levels - 1; l >= 0; --l) {
+    CLPK_TRY(run_resblock(P, P->rbs[r++], s));
+    CLPK_TRY(run_resblock(P, P->rbs[r++], s));
+    CLPK_TRY(igemm_launch(P->ups[l].L, s));  // D (bf16 copy of X[l+1]) -> X[l] += convT  (skip add, unet.py:102-104)
+  }
+  CLPK_TRY(run_groupnorm(P, P->X[0], P->on_g, P->on_b, 0, 0, s));  // out_norm, no activation (unet.py:105)
+  CLPK_TRY(igemm_launch(P->out_conv.L, s));                        // -> eps_buf (NCHW)
+  return CLPK_OK;
+}
+
+// film[B, film_n] = Linear_film(h) ; h = time_proj(temb(t)) + z_proj(z)   (unet.py:83-86, blocks.py:22-24)
+int film_from_h(clpk_plan* P, cudaStream_t s) {
+  return launch_linear(P->hcond, P->film_w, P->film_b, nullptr, 0, P->film, P->B, P->film_n, P->cfg.time_dim, 0, s);
+}
+
+}  // namespace
+
+extern "C" void clpk_plan_destroy(clpk_plan* P) {
+  if (!P) return;
+  if (P->graph_exec) cudaGraphExecDestroy(P->graph_exec);
+  if (P->graph) cudaGraphDestroy(P->graph);
+  for (void* q : P->allocs) cudaFree(q);
+  delete P;
+}
+
+extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int height, int width, int n_params,
+                                const char* const* names, const float* const* ptrs, const int64_t* numels,
+                                clpk_plan** out_plan) {
+  CLPK_REQUIRE(cfg && out_plan && names && ptrs && numels, "clpk_plan_create: null argument");
+  CLPK_REQUIRE(batch > 0 && height > 0 && width > 0, "clpk_plan_create: bad batch/size");
+  CLPK_REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= CLPK_MAX_LEVELS, "clpk_plan_create: bad n_levels");
+  CLPK_REQUIRE(cfg->base % 32 == 0, "base channels must be a multiple of 32 (got %d)", cfg->base);
+  CLPK_REQUIRE(height % (1 << cfg->n_levels) == 0 && width % (1 << cfg->n_levels) == 0,
+               "H, W must be divisible by 2^len(ch_mult)");
+  int dev_count = 0;
+  CLPK_CHECK_CUDA(cudaGetDeviceCount(&dev_count));
+  CLPK_REQUIRE(dev_count > 0, "no CUDA device");
+  CLPK_TRY(igemm_init());
+
+  ParamTable tab;
+  for (int i = 0; i < n_params; ++i) tab.m[names[i]] = {ptrs[i], numels[i]};
+
+  clpk_plan* P = new clpk_plan();
+  struct Guard {
+    clpk_plan* p;
+    ~Guard() { if (p) clpk_plan_destroy(p); }
+  } guard{P};
+  P->cfg = *cfg;
+  P->B = batch; P->H = height; P->W = width;
+  P->n_levels = cfg->n_levels;
+  const int td = cfg->time_dim, L = cfg->n_levels;
+  int ch = cfg->base, hh = height, ww = width;
+  for (int l = 0; l <= L; ++l) {
+    P->lv_c.push_back(ch); P->lv_h.push_back(hh); P->lv_w.push_back(ww);
+    if (l < L) {
+      CLPK_REQUIRE(cfg->ch_mult[l] >= 1, "bad ch_mult");
+      ch *= cfg->ch_mult[l]; hh /= 2; ww /= 2;
+    }
+  }
+  // ---- conditioning MLPs (unet.py:47-53)
+  CLPK_TRY(copy_param(P, tab, "time_proj.0.weight", (int64_t)4 * td * td, &P->tp0_w));
+  CLPK_TRY(copy_param(P, tab, "time_proj.0.bias", 4 * td, &P->tp0_b));
+  CLPK_TRY(copy_param(P, tab, "time_proj.2.weight", (int64_t)4 * td * td, &P->tp2_w));
+  CLPK_TRY(copy_param(P, tab, "time_proj.2.bias", td, &P->tp2_b));
+  CLPK_TRY(copy_param(P, tab, "z_proj.0.weight", (int64_t)td * cfg->z_dim, &P->zp_w));
+  CLPK_TRY(copy_param(P, tab, "z_proj.0.bias", td, &P->zp_b));
+  CLPK_TRY(copy_param(P, tab, "in_conv.weight", (int64_t)cfg->base * cfg->img_ch * 9, &P->in_w));
+  CLPK_TRY(copy_param(P, tab, "in_conv.bias", cfg->base, &P->in_b));
+  CLPK_TRY(copy_param(P, tab, "out_norm.weight", cfg->base, &P->on_g));
+  CLPK_TRY(copy_param(P, tab, "out_norm.bias", cfg->base, &P->on_b));
+
+  // ---- ResBlock list in execution order + FiLM offsets
+  struct RbSpec { std::string prefix; int level; bool emit; };
+  std::vector<RbSpec> specs;
+  for (int l = 0; l < L; ++l) {
+    specs.push_back({"down." + std::to_string(3 * l), l, false});
+    specs.push_back({"down." + std::to_string(3 * l + 1), l, true});
+  }
+  specs.push_back({"mid1", L, false});
+  specs.push_back({"mid2", L, false});
+  for (int i = 0; i < L; ++i) {
+    const int l = L - i;  // ResBlocks of up stage i run at level l = L - i... (coarse to fine)
+    specs.push_back({"up." + std::to_string(3 * i), l, false});
+    specs.push_back({"up." + std::to_string(3 * i + 1), l, true});
+  }
+  int film_n = 0;
+  for (auto& sp : specs) film_n += 2 * P->lv_c[sp.level];
+  P->film_n = film_n;
+  CLPK_TRY(P->alloc(&P->film_w, (long long)film_n * td));
+  CLPK_TRY(P->alloc(&P->film_b, film_n));
+
+  // ---- workspace
+  long long max_act = 0;
+  for (int l = 0; l <= L; ++l) {
+    const long long n = (long long)batch * P->lv_h[l] * P->lv_w[l] * P->lv_c[l];
+    max_act = std::max(max_act, n);
+    float* x = nullptr;
+    CLPK_TRY(P->alloc(&x, n));
+    P->X.push_back(x);
+  }
+  CLPK_TRY(P->alloc(&P->Y, max_act));
+  CLPK_TRY(P->alloc(&P->T, max_act));
+  CLPK_TRY(P->alloc(&P->D, max_act));
+  long long gn_bytes = 0;
+  for (int l = 0; l <= L; ++l)
+    gn_bytes = std::max(gn_bytes, gn_ws_bytes(gn_shape(batch, P->lv_h[l] * P->lv_w[l], P->lv_c[l],
+                                                       std::min(cfg->groups, P->lv_c[l]))));
+  {
+    char* ws = nullptr;
+    CLPK_TRY(P->alloc(&ws, gn_bytes));
+    CLPK_CHECK_CUDA(cudaMemset(ws, 0, (size_t)gn_bytes));
+    P->gn_ws = ws;
+  }
+  CLPK_TRY(P->alloc(&P->temb, (long long)batch * td));
+  CLPK_TRY(P->alloc(&P->h1, (long long)batch * 4 * td));
+  CLPK_TRY(P->alloc(&P->ht, (long long)batch * td));
+  CLPK_TRY(P->alloc(&P->hcond, (long long)batch * td));
+  CLPK_TRY(P->alloc(&P->zemb, (long long)batch * td));
+  CLPK_TRY(P->alloc(&P->film, (long long)batch * film_n));
+  CLPK_TRY(P->alloc(&P->t_buf, batch));
+  const long long img_elems = (long long)batch * cfg->img_ch * height * width;
+  CLPK_TRY(P->alloc(&P->eps_buf, img_elems));
+  CLPK_TRY(P->alloc(&P->x_buf, img_elems));
+  CLPK_TRY(P->alloc(&P->run_dev, 1));
+  CLPK_CHECK_CUDA(cudaMemset(P->run_dev, 0, sizeof(DdimRun)));
+
+  // ---- ResBlocks
+  P->rbs.resize(specs.size());
+  int off = 0;
+  for (size_t i = 0; i < specs.size(); ++i) {
+    ResBlockPlan& rb = P->rbs[i];
+    rb.film_off = off;
+    rb.emit_bf16 = specs[i].emit;
+    CLPK_TRY(make_resblock(P, tab, specs[i].prefix, specs[i].level, &rb));
+    off += 2 * rb.c;
+    clpk_conv_epilogue e1{};
+    e1.bias = rb.conv1.bias;
+    e1.film_scale1p = P->film + rb.film_off;
+    e1.film_shift = P->film + rb.film_off + rb.c;
+    e1.film_stride = film_n;
+    e1.out_f32 = P->Y;
+    e1.cout_valid = rb.c;
+    CLPK_TRY(bind_conv(P, &rb.conv1, P->T, e1));
+    clpk_conv_epilogue e2{};
+    e2.bias = rb.conv2.bias;
+    e2.resid = P->X[rb.level];
+    e2.out_f32 = P->X[rb.level];
+    e2.out_bf16 = rb.emit_bf16 ? P->D : nullptr;
+    e2.cout_valid = rb.c;
+    CLPK_TRY(bind_conv(P, &rb.conv2, P->T, e2));
+    P->flops_fwd += rb.conv1.flops + rb.conv2.flops;
+  }
+  // ---- resampling convs
+  P->downs.resize(L);
+  P->ups.resize(L);
+  for (int l = 0; l < L; ++l) {
+    ConvPlan& dn = P->downs[l];
+    CLPK_TRY(make_conv(P, tab, "down." + std::to_string(3 * l + 2), CLPK_CONV_3X3_S2, P->lv_c[l], P->lv_c[l + 1],
+                       P->lv_h[l], P->lv_w[l], &dn));
+    clpk_conv_epilogue ed{};
+    ed.bias = dn.bias;
+    ed.out_f32 = P->X[l + 1];
+    ed.cout_valid = P->lv_c[l + 1];
+    CLPK_TRY(bind_conv(P, &dn, P->D, ed));
+    P->flops_fwd += dn.flops;
+    // up stage i = L-1-l maps level l+1 -> l: module up.(3*i+2), ConvTranspose2d(C[l+1] -> C[l])
+    const int i = L - 1 - l;
+    ConvPlan& up = P->ups[l];
+    CLPK_TRY(make_conv(P, tab, "up." + std::to_string(3 * i + 2), CLPK_CONVT_4X4_S2, P->lv_c[l + 1], P->lv_c[l],
+                       P->lv_h[l + 1], P->lv_w[l + 1], &up));
+    clpk_conv_epilogue eu{};
+    eu.bias = up.bias;
+    eu.resid = P->X[l];  // skip connection, added in place
+    eu.out_f32 = P->X[l];
+    eu.cout_valid = P->lv_c[l];
+    CLPK_TRY(bind_conv(P, &up, P->D, eu));
+    P->flops_fwd += up.flops;
+  }
+  // ---- head
+  CLPK_TRY(make_conv(P, tab, "out", CLPK_CONV_3X3_S1, cfg->base, cfg->img_ch, height, width, &P->out_conv));
+  {
+    clpk_conv_epilogue eo{};
+    eo.bias = P->out_conv.bias;
+    eo.out_nchw = P->eps_buf;
+    eo.cout_valid = cfg->img_ch;
+    CLPK_TRY(bind_conv(P, &P->out_conv, P->T, eo));
+    P->flops_fwd += P->out_conv.flops;
+  }
+  P->flops_fwd += 2.0 * batch * (double)height * width * cfg->base * cfg->img_ch * 9;  // in_conv
+  P->flops_fwd += 2.0 * batch * ((double)td * 4 * td * 2 + (double)cfg->z_dim * td + (double)film_n * td);
+  // launches per forward: conditioning (5) + in_conv + per ResBlock (2 GN x 2 + 2 conv) + resamplers + out_norm(2) + out
+  P->launches_fwd = 5 + 1 + (int)P->rbs.size() * 6 + 2 * L + 2 + 1;
+  CLPK_CHECK_CUDA(cudaDeviceSynchronize());
+  guard.p = nullptr;
+  *out_plan = P;
+  return CLPK_OK;
+}
+
+extern "C" int64_t clpk_plan_device_bytes(const clpk_plan* P) { return P ? P->bytes : 0; }
+extern "C" double clpk_plan_flops_per_forward(const clpk_plan* P) { return P ? P->flops_fwd : 0.0; }
+extern "C" int clpk_plan_launches_per_forward(const clpk_plan* P) { return P ? P->launches_fwd : 0; }
+
+extern "C" int clpk_unet_forward(clpk_plan* P, const float* x, const float* z, const int64_t* t, float* eps,
+                                 void* stream) {
+  CLPK_REQUIRE(P && x && z && t && eps, "clpk_unet_forward: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const clpk_unet_config& c = P->cfg;
+  const int td = c.time_dim;
+  CLPK_TRY(launch_timestep_embedding(t, P->temb, P->B, td, 10000.f, s));                             // unet.py:83
+  CLPK_TRY(launch_linear(P->temb, P->tp0_w, P->tp0_b, nullptr, 0, P->h1, P->B, 4 * td, td, 1, s));   // :84 Linear+SiLU
+  CLPK_TRY(launch_linear(P->h1, P->tp2_w, P->tp2_b, nullptr, 0, P->ht, P->B, td, 4 * td, 0, s));     // :84 Linear
+  CLPK_TRY(launch_linear(z, P->zp_w, P->zp_b, P->ht, P->B, P->hcond, P->B, td, c.z_dim, 1, s));      // :85-86
+  CLPK_TRY(film_from_h(P, s));
+  CLPK_TRY(forward_body(P, x, s));
+  const size_t nb = (size_t)P->B * c.img_ch * P->H * P->W * sizeof(float);
+  CLPK_CHECK_CUDA(cudaMemcpyAsync(eps, P->eps_buf, nb, cudaMemcpyDeviceToDevice, s));
+  return CLPK_OK;
+}
+
+// one DDIM step on plan-owned buffers: conditioning for run->step, eps = UNet(x_buf), x_buf <- update, step += 1
+static int ddim_step_body(clpk_plan* P, cudaStream_t s) {
+  const int td = P->cfg.time_dim;
+  CLPK_TRY(launch_cond_combine(P->zemb, P->ht_tab, P->run_dev, P->hcond, P->B, td, s));
+  CLPK_TRY(film_from_h(P, s));
+  CLPK_TRY(forward_body(P, P->x_buf, s));
+  const long long n = (long long)P->B * P->cfg.img_ch * P->H * P->W;
+  CLPK_TRY(launch_ddim_step(P->x_buf, P->eps_buf, P->coef_tab, P->run_dev, P->x_buf, n, s));
+  return CLPK_OK;
+}
+
+extern "C" int clpk_plan_prepare_ddim(clpk_plan* P, int steps, const int64_t* ts_host, const float* coef_host,
+                                      int use_graph, void* stream) {
+  CLPK_REQUIRE(P && steps > 0 && ts_host && coef_host, "clpk_plan_prepare_ddim: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int td = P->cfg.time_dim;
+  if (P->graph_exec) { cudaGraphExecDestroy(P->graph_exec); P->graph_exec = nullptr; }
+  if (P->graph) { cudaGraphDestroy(P->graph); P->graph = nullptr; }
+  // per-step tables (the time half of the conditioning is batch invariant: ddim.py:32 uses one t for the whole batch)
+  int64_t* ts_dev = nullptr;
+  float *temb = nullptr, *h1 = nullptr;
+  CLPK_TRY(P->alloc(&ts_dev, steps));
+  CLPK_TRY(P->alloc(&temb, (long long)steps * td));
+  CLPK_TRY(P->alloc(&h1, (long long)steps * 4 * td));
+  CLPK_TRY(P->alloc(&P->ht_tab, (long long)steps * td));
+  CLPK_TRY(P->alloc(&P->coef_tab, (long long)steps * 5));
+  CLPK_CHECK_CUDA(cudaMemcpyAsync(ts_dev, ts_host, (size_t)steps * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  CLPK_CHECK_CUDA(cudaMemcpyAsync(P->coef_tab, coef_host, (size_t)steps * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
+  CLPK_TRY(launch_timestep_embedding(ts_dev, temb, steps, td, 10000.f, s));
+  CLPK_TRY(launch_linear(temb, P->tp0_w, P->tp0_b, nullptr, 0, h1, steps, 4 * td, td, 1, s));
+  CLPK_TRY(launch_linear(h1, P->tp2_w, P->tp2_b, nullptr, 0, P->ht_tab, steps, td, 4 * td, 0, s));
+  CLPK_CHECK_CUDA(cudaStreamSynchronize(s));
+  P->steps = steps;
+  P->any_sigma = false;
+  for (int i = 0; i < steps; ++i) P->any_sigma = P->any_sigma || (coef_host[i * 5 + 4] > 0.f);
+  if (use_graph) {
+    CLPK_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int rc = ddim_step_body(P, s);
+    if (rc == CLPK_OK) rc = launch_ddim_advance(P->run_dev, s);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (rc != CLPK_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    CLPK_CHECK_CUDA(e);
+    P->graph = g;
+    CLPK_CHECK_CUDA(cudaGraphInstantiate(&P->graph_exec, P->graph, 0));
+  }
+  return CLPK_OK;
+}
+
+extern "C" int clpk_ddim_sample(clpk_plan* P, const float* z, float* x, const float* noise, uint64_t seed,
+                                float* eps_trace, float* x_trace, void* stream) {
+  CLPK_REQUIRE(P && z && x, "clpk_ddim_sample: null argument");
+  if (P->steps <= 0) {
+    set_error("clpk_ddim_sample: call clpk_plan_prepare_ddim first");
+    return CLPK_ERR_STATE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const clpk_unet_config& c = P->cfg;
+  const long long n = (long long)P->B * c.img_ch * P->H * P->W;
+  const size_t nb = (size_t)n * sizeof(float);
+  DdimRun run{};
+  run.step = 0;
+  run.noise = noise;
+  run.noise_step_stride = n;
+  run.seed = seed;
+  CLPK_CHECK_CUDA(cudaMemcpyAsync(P->run_dev, &run, sizeof(run), cudaMemcpyHostToDevice, s));
+  CLPK_CHECK_CUDA(cudaMemcpyAsync(P->x_buf, x, nb, cudaMemcpyDeviceToDevice, s));
+  // step-invariant half of the conditioning: zemb = SiLU(z_proj(z))  (unet.py:85)
+  CLPK_TRY(launch_linear(z, P->zp_w, P->zp_b, nullptr, 0, P->zemb, P->B, c.time_dim, c.z_dim, 1, s));
+  for (int i = 0; i < P->steps; ++i) {
+    if (x_trace) CLPK_CHECK_CUDA(cudaMemcpyAsync(x_trace + (size_t)i * n, P->x_buf, nb, cudaMemcpyDeviceToDevice, s));
+    if (P->graph_exec) {
+      CLPK_CHECK_CUDA(cudaGraphLaunch(P->graph_exec, s));
+      count_launch(P->launches_fwd - 5 + 2 + 2);
+    } else {
+      CLPK_TRY(ddim_step_body(P, s));
+      CLPK_TRY(launch_ddim_advance(P->run_dev, s));
+    }
+    if (eps_trace)
+      CLPK_CHECK_CUDA(cudaMemcpyAsync(eps_trace + (size_t)i * n, P->eps_buf, nb, cudaMemcpyDeviceToDevice, s));
+  }
+  CLPK_CHECK_CUDA(cudaMemcpyAsync(x, P->x_buf, nb, cudaMemcpyDeviceToDevice, s));
+  // `run` lives on this frame and was copied with cudaMemcpyAsync from pageable memory (staged synchronously by the
+  // runtime), so no extra synchronisation is needed here.
+  return CLPK_OK;
+}

@@ -1,0 +1,224 @@
+"""Thin torch-tensor wrappers over the leaf entry points of libclpk.so.
+
+torch is used for device memory and streams only; every computation happens in the CUDA kernels of csrc/.
+Layout notes: reference-facing tensors are NCHW fp32; the kernels' activations are NHWC (bf16 operands, fp32 stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import CONV_3X3_S1, CONV_3X3_S2, CONVT_4X4_S2, ConvEpilogue, check, ptr, require_cuda, stream_ptr
+
+__all__ = [
+    "dequant_l2norm", "quant_encode", "quant_fit", "ddim_step", "timestep_embedding", "linear", "film_apply",
+    "groupnorm_silu", "pack_conv_weight", "conv_igemm", "conv_direct", "conv_in", "to_uint8_hwc", "psnr_sqerr_u8",
+    "CONV_3X3_S1", "CONV_3X3_S2", "CONVT_4X4_S2",
+]
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous().float() if (t.dtype != torch.float32 or not t.is_contiguous()) else t
+
+
+def dequant_l2norm(q: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor, l2norm: bool = True,
+                   return_raw: bool = False):
+    """uint8 [B,D] -> fp32 [B,D]: q*scale+zero, then row L2 normalisation (reconstruct_diffusion.py:43-44)."""
+    require_cuda(q, scale, zero)
+    assert q.dtype == torch.uint8 and q.dim() == 2
+    b, d = q.shape
+    q = q.contiguous()
+    z = torch.empty((b, d), dtype=torch.float32, device=q.device)
+    raw = torch.empty_like(z) if return_raw else None
+    check(_lib.load().clpk_dequant_l2norm_u8(ptr(q), ptr(_f32c(scale)), ptr(_f32c(zero)), ptr(z), ptr(raw), b, d,
+                                             int(l2norm), stream_ptr()), "clpk_dequant_l2norm_u8")
+    return (z, raw) if return_raw else z
+
+
+def quant_encode(x: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor) -> torch.Tensor:
+    require_cuda(x, scale, zero)
+    x2 = _f32c(x).reshape(-1, x.shape[-1])
+    q = torch.empty(x2.shape, dtype=torch.uint8, device=x.device)
+    check(_lib.load().clpk_quant_encode_u8(ptr(x2), ptr(_f32c(scale)), ptr(_f32c(zero)), ptr(q), x2.shape[0],
+                                           x2.shape[1], stream_ptr()), "clpk_quant_encode_u8")
+    return q.reshape(x.shape)
+
+
+def quant_fit(x: torch.Tensor):
+    require_cuda(x)
+    x = _f32c(x)
+    n, d = x.shape
+    scale = torch.empty(d, dtype=torch.float32, device=x.device)
+    zero = torch.empty_like(scale)
+    check(_lib.load().clpk_quant_fit(ptr(x), ptr(scale), ptr(zero), n, d, stream_ptr()), "clpk_quant_fit")
+    return scale, zero
+
+
+def ddim_step(x: torch.Tensor, eps: torch.Tensor, coef, noise: torch.Tensor | None = None,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """One DDIM update (ddim.py:36-45); coef = (sqrt(1-a_t), sqrt(a_t), sqrt(a_s), sqrt(a_s-sigma^2), sigma)."""
+    require_cuda(x, eps, noise)
+    x, eps = _f32c(x), _f32c(eps)
+    noise = _f32c(noise) if noise is not None else None
+    out = torch.empty_like(x) if out is None else out
+    c5 = (C.c_float * 5)(*[float(v) for v in coef])
+    check(_lib.load().clpk_ddim_step(ptr(x), ptr(eps), ptr(noise), c5, ptr(out), x.numel(), stream_ptr()),
+          "clpk_ddim_step")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    require_cuda(t)
+    t = t.contiguous().to(torch.int64)
+    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    check(_lib.load().clpk_timestep_embedding(ptr(t), ptr(out), t.shape[0], dim, float(max_period), stream_ptr()),
+          "clpk_timestep_embedding")
+    return out
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, act: int = 0,
+           add: torch.Tensor | None = None) -> torch.Tensor:
+    require_cuda(x, w)
+    x, w = _f32c(x), _f32c(w)
+    m, k = x.shape
+    n = w.shape[0]
+    assert w.shape[1] == k
+    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    check(_lib.load().clpk_linear(ptr(x), ptr(w), ptr(_f32c(b)) if b is not None else None,
+                                  ptr(_f32c(add)) if add is not None else None, ptr(y), m, n, k, act, stream_ptr()),
+          "clpk_linear")
+    return y
+
+
+def film_apply(x_nchw: torch.Tensor, scale1p: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
+    require_cuda(x_nchw, scale1p, shift)
+    x = _f32c(x_nchw)
+    b, c = x.shape[:2]
+    hw = x.numel() // (b * c)
+    y = torch.empty_like(x)
+    check(_lib.load().clpk_film_apply(ptr(x), ptr(_f32c(scale1p)), ptr(_f32c(shift)), ptr(y), b, c, hw, stream_ptr()),
+          "clpk_film_apply")
+    return y
+
+
+def groupnorm_silu(x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float = 1e-5,
+                   silu: bool = True) -> torch.Tensor:
+    """fp32 NHWC [B,H,W,C] -> bf16 NHWC GroupNorm(+SiLU)."""
+    require_cuda(x_nhwc, gamma, beta)
+    x = _f32c(x_nhwc)
+    b, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (b * c)
+    lib = _lib.load()
+    ws = torch.empty(int(lib.clpk_groupnorm_ws_bytes(b, hw, c, groups)), dtype=torch.uint8, device=x.device)
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib.clpk_groupnorm_silu(ptr(x), ptr(_f32c(gamma)), ptr(_f32c(beta)), ptr(y), ptr(ws), b, hw, c, groups,
+                                  float(eps), int(silu), stream_ptr()), "clpk_groupnorm_silu")
+    return y
+
+
+def pack_conv_weight(w: torch.Tensor, kind: int) -> torch.Tensor:
+    """Reference-layout fp32 conv weight -> bf16 K-major GEMM layout (see include/clpk.h)."""
+    require_cuda(w)
+    w = _f32c(w)
+    if kind == CONVT_4X4_S2:
+        cin, cout = w.shape[0], w.shape[1]
+    else:
+        cout, cin = w.shape[0], w.shape[1]
+    lib = _lib.load()
+    n = int(lib.clpk_pack_conv_weight(None, None, kind, cin, cout, None))
+    if n < 0:
+        check(1, "clpk_pack_conv_weight")
+    out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    if lib.clpk_pack_conv_weight(ptr(w), ptr(out), kind, cin, cout, stream_ptr()) < 0:
+        check(2, "clpk_pack_conv_weight")
+    return out
+
+
+def _conv(fn_name: str, x_nhwc_bf16, w_packed, kind, cout, bias, film_scale1p, film_shift, resid, out_f32, out_bf16,
+          out_nchw):
+    require_cuda(x_nhwc_bf16, w_packed, bias)
+    assert x_nhwc_bf16.dtype == torch.bfloat16 and x_nhwc_bf16.is_contiguous()
+    b, h, w, cin = x_nhwc_bf16.shape
+    ep = ConvEpilogue()
+    keep = [_f32c(bias)]
+    ep.bias = ptr(keep[0])
+    if film_scale1p is not None:
+        fs, fb = _f32c(film_scale1p), _f32c(film_shift)
+        keep += [fs, fb]
+        ep.film_scale1p, ep.film_shift, ep.film_stride = ptr(fs), ptr(fb), fs.stride(0)
+    ep.resid = ptr(resid)
+    ep.out_f32 = ptr(out_f32)
+    ep.out_bf16 = ptr(out_bf16)
+    ep.out_nchw = ptr(out_nchw)
+    ep.cout_valid = cout
+    fn = getattr(_lib.load(), fn_name)
+    check(fn(ptr(x_nhwc_bf16), ptr(w_packed), kind, b, h, w, cin, cout, C.byref(ep), stream_ptr()), fn_name)
+
+
+def _conv_out_hw(kind: int, h: int, w: int):
+    if kind == CONV_3X3_S2:
+        return h // 2, w // 2
+    if kind == CONVT_4X4_S2:
+        return 2 * h, 2 * w
+    return h, w
+
+
+def conv_igemm(x_nhwc_bf16: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, bias: torch.Tensor, *,
+               film_scale1p=None, film_shift=None, resid=None, want_f32=True, want_bf16=False, want_nchw=False,
+               impl: str = "igemm"):
+    """Implicit-GEMM conv on the tensor cores.  Returns a dict of the requested outputs."""
+    b, h, w, _ = x_nhwc_bf16.shape
+    oh, ow = _conv_out_hw(kind, h, w)
+    dev = x_nhwc_bf16.device
+    outs = {}
+    if want_f32:
+        outs["f32"] = torch.empty((b, oh, ow, cout), dtype=torch.float32, device=dev)
+    if want_bf16:
+        outs["bf16"] = torch.empty((b, oh, ow, cout), dtype=torch.bfloat16, device=dev)
+    if want_nchw:
+        outs["nchw"] = torch.empty((b, cout, oh, ow), dtype=torch.float32, device=dev)
+    _conv("clpk_conv_igemm" if impl == "igemm" else "clpk_conv_direct", x_nhwc_bf16, w_packed, kind, cout, bias,
+          film_scale1p, film_shift, _f32c(resid) if resid is not None else None, outs.get("f32"), outs.get("bf16"),
+          outs.get("nchw"))
+    return outs
+
+
+def conv_direct(*args, **kwargs):
+    """CUDA-core evaluation of the same contract (on-device cross-check for tests)."""
+    return conv_igemm(*args, impl="direct", **kwargs)
+
+
+def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Stem conv (unet.py:55): fp32 NCHW -> fp32 NHWC."""
+    require_cuda(x_nchw, w, b)
+    x = _f32c(x_nchw)
+    bsz, cin, h, wd = x.shape
+    cout = w.shape[0]
+    y = torch.empty((bsz, h, wd, cout), dtype=torch.float32, device=x.device)
+    check(_lib.load().clpk_conv_in(ptr(x), ptr(_f32c(w)), ptr(_f32c(b)), ptr(y), bsz, cin, h, wd, cout, stream_ptr()),
+          "clpk_conv_in")
+    return y
+
+
+def to_uint8_hwc(x_nchw: torch.Tensor) -> torch.Tensor:
+    """clamp(-1,1) -> ((x+1)*127.5) truncated to uint8, HWC (reconstruct_diffusion.py:55-56)."""
+    require_cuda(x_nchw)
+    x = _f32c(x_nchw)
+    b, c, h, w = x.shape
+    out = torch.empty((b, h, w, c), dtype=torch.uint8, device=x.device)
+    check(_lib.load().clpk_to_uint8_hwc(ptr(x), ptr(out), b, c, h, w, stream_ptr()), "clpk_to_uint8_hwc")
+    return out
+
+
+def psnr_sqerr_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Per-image sum of squared uint8-domain differences (metrics.py:16-26) as int64 [B]."""
+    require_cuda(a, b)
+    a, b = _f32c(a), _f32c(b)
+    assert a.shape == b.shape
+    bsz = a.shape[0]
+    per = a.numel() // bsz
+    out = torch.empty(bsz, dtype=torch.int64, device=a.device)
+    check(_lib.load().clpk_psnr_sqerr_u8(ptr(a), ptr(b), ptr(out), bsz, per, stream_ptr()), "clpk_psnr_sqerr_u8")
+    return out

@@ -1,0 +1,190 @@
+/*
+ * clpk.h — C ABI of libclpk.so, the B200 (sm_100a) decode hot path of the CLIP-feature image codec.
+ *
+ * The reference (lionl1106/Clip-Neural-image-conpression, package clip_feature_codec) is pure Python and has
+ * NO FFI/plugin layer: its boundary is a Python class surface.  This header is therefore the
+ * boundary a maintainer would bind with ctypes; every entry point names the reference
+ * code (file:line, relative to the reference root, PKG = src/clip_feature_codec) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a caller-owned DEVICE pointer; "host" pointers are plain host memory;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value: 0 = CLPK_OK, otherwise an error code; clpk_last_error() gives the message (thread local);
+ *   - no entry point allocates device memory except clpk_plan_create / clpk_plan_prepare_ddim;
+ *   - no CPU fallback exists: without a CUDA device every compute entry point returns CLPK_ERR_CUDA.
+ *   - activations inside the library are NHWC; the reference-facing tensors (x_t, eps, images) are NCHW fp32.
+ */
+#ifndef CLPK_H_
+#define CLPK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLPK_OK 0
+#define CLPK_ERR_ARG 1     /* bad argument / unsupported shape */
+#define CLPK_ERR_CUDA 2    /* CUDA runtime / driver failure    */
+#define CLPK_ERR_STATE 3   /* call order (plan not prepared …) */
+
+#define CLPK_MAX_LEVELS 8
+
+const char* clpk_last_error(void);
+int clpk_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t clpk_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Codec side: PKG/codecs/quantizer.py, PKG/cli/reconstruct_diffusion.py:43-44, PKG/cli/eval.py:58-59
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* z[b,d] = float(q[b,d]) * scale[d] + zero[d]   (separately rounded mul and add: numpy semantics,
+ *          reconstruct_diffusion.py:43 / quantizer.py:38-39; bit exact)
+ * then, if l2norm != 0:  z[b,:] /= max(||z[b,:]||_2, 1e-9)   (reconstruct_diffusion.py:21-23,44)
+ * If z_raw (dev, may be NULL) is given it receives the un-normalised dequantised values. */
+int clpk_dequant_l2norm_u8(const uint8_t* q_dev, const float* scale_dev, const float* zero_dev,
+                           float* z_dev, float* z_raw_dev, int batch, int dim, int l2norm, void* stream);
+
+/* q[b,d] = uint8(clamp(rint((x[b,d] - zero[d]) / scale[d]), 0, 255))  — quantizer.py:29-33 (round half even). */
+int clpk_quant_encode_u8(const float* x_dev, const float* scale_dev, const float* zero_dev,
+                         uint8_t* q_dev, int batch, int dim, void* stream);
+
+/* per-channel fit: zero[d] = min_n x[n,d]; scale[d] = max(max_n x[n,d] - zero[d], 1e-8) / 255 — quantizer.py:22-27 */
+int clpk_quant_fit(const float* x_dev, float* scale_dev, float* zero_dev, int n, int dim, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Sampler side: PKG/diffusion/ddim.py:34-45 (one DDIM update, elementwise)
+ *   x0 = clamp((x - c[0]*eps) / c[1], -1, 1);  x' = c[2]*x0 + c[3]*eps  [+ c[4]*noise]
+ *   c = {sqrt(1-a_t), sqrt(a_t), sqrt(a_s), sqrt(a_s - sigma^2), sigma}  (host computed with the reference's ops)
+ *   noise_dev may be NULL (eta == 0 or sigma == 0).  All products/sums are individually rounded like the ATen
+ *   kernels, so the result is bit-identical to the reference for identical eps.  x_out may alias x.
+ * ------------------------------------------------------------------------------------------------------------- */
+int clpk_ddim_step(const float* x_dev, const float* eps_dev, const float* noise_dev, const float* coef5_host,
+                   float* x_out_dev, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Model leaf ops (used by the plan; exported so each one can be parity-tested alone)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* timestep_embedding (PKG/models/unet.py:22-39): out[b, 0:half] = cos(t*f_k), out[b, half:2*half] = sin(t*f_k) */
+int clpk_timestep_embedding(const int64_t* t_dev, float* out_dev, int batch, int dim, float max_period, void* stream);
+
+/* y[m,n] = act(sum_k x[m,k]*w[n,k] + b[n]) (+ add[m,n]); act: 0 none, 1 SiLU.  fp32.  nn.Linear of
+ * unet.py:47-53 and blocks.py:19-20. */
+int clpk_linear(const float* x_dev, const float* w_dev, const float* b_dev, const float* add_dev, float* y_dev,
+                int m, int n, int k, int act, void* stream);
+
+/* FiLM.forward standalone (blocks.py:22-25): y[b,c,:] = x[b,c,:] * scale1p[b,c] + shift[b,c], NCHW fp32, scale1p = 1+s
+ * (two separately rounded ops like ATen).  Inside the UNet this is fused into the conv1 epilogue instead. */
+int clpk_film_apply(const float* x_nchw_dev, const float* scale1p_dev, const float* shift_dev, float* y_nchw_dev,
+                    int batch, int ch, int hw, void* stream);
+
+/* GroupNorm(groups, C) over NHWC fp32 input, optional SiLU, bf16 NHWC output (blocks.py:33-36,41,43; unet.py:78,105).
+ * ws_dev: scratch of clpk_groupnorm_ws_bytes(batch, hw, c, groups) bytes. */
+int64_t clpk_groupnorm_ws_bytes(int batch, int hw, int c, int groups);
+int clpk_groupnorm_silu(const float* x_nhwc_dev, const float* gamma_dev, const float* beta_dev, void* y_bf16_nhwc_dev,
+                        void* ws_dev, int batch, int hw, int c, int groups, float eps, int silu, void* stream);
+
+/* Convolution kinds understood by the implicit-GEMM kernel. */
+#define CLPK_CONV_3X3_S1 0   /* Conv2d 3x3 stride 1 pad 1  (blocks.py:34,36; unet.py:79)   */
+#define CLPK_CONV_3X3_S2 1   /* Conv2d 3x3 stride 2 pad 1  (unet.py:63)                    */
+#define CLPK_CONVT_4X4_S2 2  /* ConvTranspose2d 4x4 stride 2 pad 1 (unet.py:75)            */
+
+/* Repack a reference-layout fp32 weight (Conv2d: [Cout,Cin,kh,kw]; ConvTranspose2d: [Cin,Cout,4,4]) into the bf16
+ * K-major GEMM layout the tcgen05 kernel reads: Conv: [Cout_pad][tap][Cin]; ConvT: [phase(4)][Cout_pad][tap(4)][Cin].
+ * Returns the number of bf16 elements written (or needed, when out_dev == NULL) or <0 on error. */
+int64_t clpk_pack_conv_weight(const float* w_dev, void* out_bf16_dev, int kind, int cin, int cout, void* stream);
+
+/* Epilogue description of one implicit-GEMM convolution launch.
+ *   y = conv(x) + bias;  if film: y = y * film_scale1p[b,c] + film_shift[b,c]   (blocks.py:22-25, scale1p = 1+s)
+ *   if resid: y += resid (same NHWC shape as the output; may alias out_f32)       (blocks.py:44, unet.py:104)
+ *   outputs (any subset): out_f32 NHWC fp32, out_bf16 NHWC bf16, out_nchw fp32 NCHW restricted to cout_valid channels. */
+typedef struct clpk_conv_epilogue {
+  const float* bias;          /* dev [cout]                       */
+  const float* film_scale1p;  /* dev, element (b,c) at [b*film_stride + c], or NULL */
+  const float* film_shift;    /* dev, same indexing, or NULL      */
+  int64_t film_stride;
+  const float* resid;         /* dev NHWC fp32 or NULL            */
+  float* out_f32;             /* dev NHWC fp32 or NULL            */
+  void* out_bf16;             /* dev NHWC bf16 or NULL            */
+  float* out_nchw;            /* dev NCHW fp32 or NULL            */
+  int cout_valid;             /* channels really present (<= cout_pad) */
+} clpk_conv_epilogue;
+
+/* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed).
+ * x: bf16 NHWC [batch, h_in, w_in, cin]; w_packed from clpk_pack_conv_weight.
+ * Output spatial size: S1: (h_in, w_in); S2: (h_in/2, w_in/2); ConvT: (2*h_in, 2*w_in). */
+int clpk_conv_igemm(const void* x_bf16_nhwc_dev, const void* w_packed_dev, int kind, int batch, int h_in, int w_in,
+                    int cin, int cout, const clpk_conv_epilogue* ep, void* stream);
+
+/* Same contract evaluated by a plain CUDA-core kernel (one thread per output element, fp32 accumulation of the same
+ * bf16 operands).  On-device cross-check for the tensor-core kernel in tests; never used by the plan. */
+int clpk_conv_direct(const void* x_bf16_nhwc_dev, const void* w_packed_dev, int kind, int batch, int h_in, int w_in,
+                     int cin, int cout, const clpk_conv_epilogue* ep, void* stream);
+
+/* in_conv (unet.py:55,88): fp32 NCHW [B,cin,H,W] -> fp32 NHWC [B,H,W,cout], 3x3 s1 p1, fp32 arithmetic. */
+int clpk_conv_in(const float* x_nchw_dev, const float* w_dev /*[cout,cin,3,3]*/, const float* b_dev, float* y_nhwc_dev,
+                 int batch, int cin, int h, int w, int cout, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Plan level: the whole CLIPCondUNet forward (unet.py:81-106) and the DDIM loop (ddim.py:21-46)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+typedef struct clpk_unet_config {
+  int z_dim;      /* 512 */
+  int base;       /* 128 */
+  int n_levels;   /* len(ch_mult) */
+  int ch_mult[CLPK_MAX_LEVELS];
+  int time_dim;   /* 256 */
+  int img_ch;     /* 3 */
+  int groups;     /* 8 */
+} clpk_unet_config;
+
+typedef struct clpk_plan clpk_plan;
+
+/* Creates a plan for fixed (batch, H, W).  `names`/`ptrs`/`numels` describe the state dict (unet.py:45-79,
+ * SURVEY Appendix B): n_params entries, names are the reference's parameter names, ptrs are DEVICE fp32 pointers that
+ * only need to stay valid during this call (weights are repacked into plan-owned memory). */
+int clpk_plan_create(const clpk_unet_config* cfg, int batch, int height, int width, int n_params,
+                     const char* const* names, const float* const* ptrs_dev, const int64_t* numels,
+                     clpk_plan** out_plan);
+void clpk_plan_destroy(clpk_plan* plan);
+int64_t clpk_plan_device_bytes(const clpk_plan* plan);
+/* algorithmic FLOPs of one forward at the plan's batch (conv + linear, 2*MAC) */
+double clpk_plan_flops_per_forward(const clpk_plan* plan);
+/* kernels launched by one forward / one DDIM step */
+int clpk_plan_launches_per_forward(const clpk_plan* plan);
+
+/* eps = CLIPCondUNet(x_t, z_clip, t):  x_t fp32 NCHW [B,img_ch,H,W], z_clip fp32 [B,z_dim], t int64 [B]. */
+int clpk_unet_forward(clpk_plan* plan, const float* x_nchw_dev, const float* z_clip_dev, const int64_t* t_dev,
+                      float* eps_nchw_dev, void* stream);
+
+/* Prepare a DDIM run: `steps` sub-sampled timesteps ts[] (host int64, ddim.py:25) and coef[steps][5] (host fp32,
+ * see clpk_ddim_step).  Builds the per-step conditioning tables and captures the CUDA graph of one step. */
+int clpk_plan_prepare_ddim(clpk_plan* plan, int steps, const int64_t* ts_host, const float* coef_host, int use_graph,
+                           void* stream);
+
+/* Runs the prepared loop.  x_dev: fp32 NCHW, holds x_T on entry and the result on exit (unclamped, ddim.py:46).
+ * noise_dev: NULL, or fp32 [steps][B*img_ch*H*W] of pre-drawn N(0,1) (parity runs);  if NULL and any coef sigma > 0
+ * the noise is generated in-kernel with Philox4x32-10 keyed by (seed, step, element).
+ * eps_trace_dev / x_trace_dev: NULL or [steps][...] buffers receiving every step's eps and input x (parity). */
+int clpk_ddim_sample(clpk_plan* plan, const float* z_clip_dev, float* x_dev, const float* noise_dev, uint64_t seed,
+                     float* eps_trace_dev, float* x_trace_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Output side: reconstruct_diffusion.py:55-56, PKG/eval/metrics.py:16-29
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* u8[b,h,w,c] = uint8((clamp(x[b,c,h,w],-1,1) + 1) * 127.5)  (truncation) — reconstruct_diffusion.py:55-56 */
+int clpk_to_uint8_hwc(const float* x_nchw_dev, uint8_t* out_hwc_dev, int batch, int ch, int h, int w, void* stream);
+
+/* per-image PSNR in the uint8 domain (metrics.py:16-29): sq_err_sum[b] = sum((u8(a)-u8(b))^2) as exact int64;
+ * the host finishes 20*log10(255/sqrt(mse)).  Inputs fp32 in [-1,1], any layout as long as both agree. */
+int clpk_psnr_sqerr_u8(const float* a_dev, const float* b_dev, int64_t* sq_err_sum_dev, int batch, int64_t per_image,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLPK_H_ */

@@ -1,0 +1,98 @@
+"""The oracle (oracle/codec_oracle.py) against the golden vectors produced by the unmodified reference
+(tests/golden/*.npz, generator: oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import torch
+
+TINY = dict(z_dim=512, base=32, ch_mult=(1, 2))
+MID = dict(z_dim=512, base=64, ch_mult=(1, 2))
+
+
+def test_scheduler_tables_bit_exact(oracle, golden):
+    g = golden("scheduler")
+    for sch in ("cosine", "linear"):
+        tabs = oracle.scheduler_tables(1000, sch)
+        for k in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
+                  "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas", "posterior_variance"):
+            assert np.array_equal(tabs[k].numpy(), g[f"{sch}.{k}"]), (sch, k)
+
+
+def test_timestep_embedding_bit_exact(oracle, golden):
+    g = golden("timestep_embedding")
+    t = torch.from_numpy(g["t"])
+    assert np.array_equal(oracle.timestep_embedding(t, 256).numpy(), g["emb256"])
+    assert np.array_equal(oracle.timestep_embedding(t, 64).numpy(), g["emb64"])
+
+
+def test_quantizer_bit_exact(oracle, golden):
+    g = golden("quantizer")
+    scale, zero = oracle.quant_fit(g["Z"])
+    assert np.array_equal(scale, g["scale"]) and np.array_equal(zero, g["zero"])
+    codes = oracle.quant_encode(g["Z"], scale, zero)
+    assert np.array_equal(codes, g["codes"])
+    assert np.array_equal(oracle.dequant(codes, scale, zero), g["decoded"])
+    assert np.array_equal(oracle.l2_normalize(oracle.dequant(codes, scale, zero)), g["z_dec"])
+
+
+def test_clp_container(oracle, golden):
+    g = golden("quantizer")
+    for i in range(4):
+        blob = g[f"clp{i}"].tobytes()
+        assert blob[:4] == b"CLPF"
+        assert np.array_equal(oracle.clp_decode(blob), g["codes"][i])
+        # our writer -> same container; frames from the same libzstd are byte identical
+        assert oracle.clp_encode(g["codes"][i].tobytes()) == blob
+    try:
+        oracle.clp_decode(b"XXXX" + blob[4:])
+        raise RuntimeError("bad magic accepted")
+    except AssertionError as e:
+        assert "Bad magic" in str(e)
+
+
+def test_unet_forward_matches_reference(oracle, golden):
+    g = golden("unet_forward")
+    for name, cfg in (("tiny", TINY), ("mid", MID)):
+        sd = oracle.make_state_dict(cfg["z_dim"], cfg["base"], cfg["ch_mult"], seed=11)
+        with torch.no_grad():
+            eps = oracle.unet_forward(sd, cfg["ch_mult"], torch.from_numpy(g[f"{name}.x"]), torch.from_numpy(g[f"{name}.z"]),
+                                      torch.from_numpy(g[f"{name}.t"]))
+        # same ATen kernels, same op order -> identical up to thread-partitioning of reductions
+        assert oracle.rel_l2(eps, torch.from_numpy(g[f"{name}.eps"])) < 1e-6
+
+
+def test_resblock_and_film_match_reference(oracle, golden):
+    g = golden("unet_forward")
+    sd = {"b." + k[len("rb.sd."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("rb.sd.")}
+    with torch.no_grad():
+        y = oracle._resblock(sd, "b", torch.from_numpy(g["rb.x"]), torch.from_numpy(g["rb.h"]))
+    assert oracle.rel_l2(y, torch.from_numpy(g["rb.y"])) < 1e-6
+
+
+def test_ddim_matches_reference(oracle, golden):
+    g = golden("ddim")
+    tabs = oracle.scheduler_tables(1000, "cosine")
+    z, x_T = torch.from_numpy(g["z"]), torch.from_numpy(g["x_T"])
+    for tag, gain in (("p0", 1.0), ("pg", 0.1)):
+        sd = oracle.make_state_dict(512, 32, (1, 2), seed=0, out_gain=gain)
+        fn = lambda x, zc, t: oracle.unet_forward(sd, (1, 2), x, zc, t)  # noqa: E731
+        with torch.no_grad():
+            x = oracle.ddim_sample(fn, tabs, z, x_T, steps=10, eta=0.0)
+        assert oracle.psnr_float(x, torch.from_numpy(g[f"{tag}.eta0.x"])) > 100.0, tag
+    sd = oracle.make_state_dict(512, 32, (1, 2), seed=0, out_gain=0.1)
+    fn = lambda x, zc, t: oracle.unet_forward(sd, (1, 2), x, zc, t)  # noqa: E731
+    torch.manual_seed(7)
+    noise = torch.stack([torch.randn(2, 3, 64, 64) for _ in range(10)])
+    assert np.array_equal(noise.numpy()[:, :1, :1, :4, :4], g["noise_seed7"])
+    with torch.no_grad():
+        x = oracle.ddim_sample(fn, tabs, z, x_T, steps=10, eta=1e-3, noise=noise)
+        assert oracle.psnr_float(x, torch.from_numpy(g["pg.eta1e-3.x"])) > 100.0
+        x = oracle.ddim_sample(fn, tabs, z, x_T, steps=10, eta=1.0, noise=noise)
+    assert float(torch.isnan(x).float().mean()) == float(g["pg.eta1.nan_fraction"]) == 1.0
+
+
+def test_metrics_match_reference(oracle, golden):
+    g = golden("metrics")
+    for i in range(3):
+        assert np.array_equal(oracle.to_uint8_image(g["a"][i]), g["u8"][i])
+        assert oracle.psnr(g["a"][i], g["b"][i]) == g["psnr"][i]
+    assert oracle.psnr(g["a"][0], g["a"][0]) == float("inf") == g["psnr"][3]
+    assert np.array_equal(oracle.metric_uint8(g["a"]), g["metric_u8"])

@@ -1,0 +1,195 @@
+"""GPU bring-up diagnostics: runs every leaf kernel against torch on the device and prints error magnitudes.
+
+Unlike the pytest suite it never stops at the first mismatch, so one gpurun call shows the state of every kernel.
+    python tools/gpu_diag.py [--quick]
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+import time
+import traceback
+from pathlib import Path
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+
+from clip_neural_image_conpression_b200 import ops  # noqa: E402
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+dev = torch.device("cuda")
+results = []
+
+
+def report(name, ok, detail):
+    results.append((name, ok))
+    print(f"[{'OK ' if ok else 'BAD'}] {name}: {detail}", flush=True)
+
+
+def guarded(fn):
+    def wrap(*a, **k):
+        try:
+            fn(*a, **k)
+        except Exception as e:  # noqa: BLE001
+            report(fn.__name__ + str(a), False, f"EXCEPTION {type(e).__name__}: {e}")
+            traceback.print_exc()
+            try:
+                torch.cuda.synchronize()
+            except Exception as e2:  # noqa: BLE001
+                print("device is in a failed state:", e2, flush=True)
+                summary_and_exit()
+    return wrap
+
+
+def summary_and_exit():
+    bad = [n for n, ok in results if not ok]
+    print(f"\nSUMMARY: {len(results) - len(bad)}/{len(results)} ok; failing: {bad}", flush=True)
+    sys.exit(1 if bad else 0)
+
+
+def bf16r(x):
+    return x.to(torch.bfloat16).float()
+
+
+@guarded
+def conv_case(kind, b, h, w, cin, cout, film=False, resid=False, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(b, h, w, cin, generator=g).to(dev)
+    xb = x.to(torch.bfloat16).contiguous()
+    if kind == ops.CONVT_4X4_S2:
+        wt = (torch.randn(cin, cout, 4, 4, generator=g) / (cin * 4) ** 0.5).to(dev)
+    else:
+        wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    wp = ops.pack_conv_weight(wt, kind)
+    xr = xb.float().permute(0, 3, 1, 2).double()
+    wr = bf16r(wt).double()
+    if kind == ops.CONV_3X3_S1:
+        ref = F.conv2d(xr, wr, bias.double(), padding=1)
+    elif kind == ops.CONV_3X3_S2:
+        ref = F.conv2d(xr, wr, bias.double(), stride=2, padding=1)
+    else:
+        ref = F.conv_transpose2d(xr, wr, bias.double(), stride=2, padding=1)
+    kw = {}
+    if film:
+        sc = (1 + 0.3 * torch.randn(b, cout, generator=g)).to(dev)
+        sh = torch.randn(b, cout, generator=g).to(dev)
+        kw.update(film_scale1p=sc, film_shift=sh)
+        ref = ref * sc.double()[:, :, None, None] + sh.double()[:, :, None, None]
+    if resid:
+        r = torch.randn(b, ref.shape[2], ref.shape[3], cout, generator=g).to(dev)
+        kw.update(resid=r)
+        ref = ref + r.permute(0, 3, 1, 2).double()
+    ref_nhwc = ref.permute(0, 2, 3, 1).float()
+    nchw = cout % 16 != 0
+    outs = {}
+    for impl in ("direct", "igemm"):
+        o = ops.conv_igemm(xb, wp, kind, cout, bias, want_f32=not nchw, want_bf16=not nchw, want_nchw=nchw, impl=impl, **kw)
+        torch.cuda.synchronize()
+        outs[impl] = o
+        y = o["nchw"].permute(0, 2, 3, 1) if nchw else o["f32"]
+        err = (y - ref_nhwc).abs().max().item()
+        scale = ref_nhwc.abs().max().item()
+        ok = err <= 2e-3 * max(scale, 1.0)
+        extra = ""
+        if not nchw:
+            eb = (o["bf16"].float() - ref_nhwc).abs().max().item()
+            extra = f" bf16copy_err={eb:.3e}"
+            ok = ok and eb <= 1.6e-2 * max(scale, 1.0)
+        if not ok and impl == "igemm":
+            d = (y - ref_nhwc).abs()
+            bad = (d > 2e-3 * max(scale, 1.0)).nonzero()
+            extra += f" n_bad={bad.shape[0]}/{d.numel()} first_bad={bad[:5].tolist()}"
+        report(f"conv kind={kind} B{b} {h}x{w} {cin}->{cout} film={film} resid={resid} [{impl}]", ok,
+               f"max_abs_err={err:.3e} (ref max {scale:.2f}){extra}")
+
+
+@guarded
+def gn_case(b, h, w, c, silu):
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(b, h, w, c, generator=g) * 2 + 0.5).to(dev)
+    gamma = (1 + 0.1 * torch.randn(c, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(c, generator=g)).to(dev)
+    groups = min(8, c)
+    y = ops.groupnorm_silu(x, gamma, beta, groups, 1e-5, silu)
+    ref = F.group_norm(x.permute(0, 3, 1, 2).double(), groups, gamma.double(), beta.double(), 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1).float()
+    err = (y.float() - ref).abs().max().item()
+    report(f"groupnorm B{b} {h}x{w} C{c} silu={silu}", err <= 2e-2 * max(1.0, ref.abs().max().item()),
+           f"max_abs_err={err:.3e} (bf16 output, ref max {ref.abs().max().item():.2f})")
+
+
+@guarded
+def misc_cases():
+    g = torch.Generator().manual_seed(2)
+    # linear
+    x, w, b = torch.randn(9, 256, generator=g).to(dev), torch.randn(1024, 256, generator=g).to(dev) / 16, torch.randn(1024, generator=g).to(dev)
+    y = ops.linear(x, w, b, act=1)
+    ref = F.silu(F.linear(x.double(), w.double(), b.double())).float()
+    report("linear 9x256->1024 silu", (y - ref).abs().max().item() < 1e-4, f"max_abs_err={(y - ref).abs().max().item():.3e}")
+    # conv_in
+    x = torch.randn(2, 3, 40, 24, generator=g).to(dev)
+    w = (torch.randn(128, 3, 3, 3, generator=g) / 5).to(dev)
+    b = torch.randn(128, generator=g).to(dev)
+    y = ops.conv_in(x, w, b)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).float()
+    report("conv_in 3->128", (y - ref).abs().max().item() < 1e-4, f"max_abs_err={(y - ref).abs().max().item():.3e}")
+    # timestep embedding
+    t = torch.tensor([0, 1, 500, 999], device=dev)
+    e = ops.timestep_embedding(t, 256)
+    import math
+    half = 128
+    fr = torch.exp(-math.log(10000) * torch.arange(0, half, device=dev) / half)
+    a = t.float()[:, None] * fr[None]
+    ref = torch.cat([torch.cos(a), torch.sin(a)], -1)
+    report("timestep_embedding", (e - ref).abs().max().item() < 2e-4, f"max_abs_err={(e - ref).abs().max().item():.3e}")
+    # ddim step
+    x, eps = torch.randn(2, 3, 32, 32, generator=g).to(dev), torch.randn(2, 3, 32, 32, generator=g).to(dev)
+    coef = [0.8, 0.6, 0.65, 0.7, 0.0]
+    y = ops.ddim_step(x, eps, coef)
+    ref = 0.65 * ((x - 0.8 * eps) / 0.6).clamp(-1, 1) + 0.7 * eps
+    report("ddim_step", (y - ref).abs().max().item() < 1e-5, f"max_abs_err={(y - ref).abs().max().item():.3e}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    print(torch.cuda.get_device_name(0), torch.version.cuda, flush=True)
+    t0 = time.time()
+    misc_cases()
+    gn_case(2, 16, 16, 32, True)
+    gn_case(2, 32, 32, 128, True)
+    gn_case(1, 8, 8, 512, False)
+    gn_case(2, 8, 8, 192, True)
+    # the simplest tensor-core case first: one M tile, one k-block per tap
+    conv_case(ops.CONV_3X3_S1, 1, 8, 16, 64, 64)
+    conv_case(ops.CONV_3X3_S1, 2, 16, 16, 64, 128)
+    conv_case(ops.CONV_3X3_S1, 1, 32, 32, 128, 128, film=True)
+    conv_case(ops.CONV_3X3_S1, 2, 32, 32, 128, 128, resid=True)
+    conv_case(ops.CONV_3X3_S1, 1, 16, 16, 32, 32)            # BLOCK_K = 32 / 64B swizzle path
+    conv_case(ops.CONV_3X3_S1, 1, 8, 8, 512, 512)            # two N tiles, 72 k-blocks, partial M tile (64 rows)
+    conv_case(ops.CONV_3X3_S1, 1, 4, 256, 128, 128)          # W > 128: two tiles along W
+    conv_case(ops.CONV_3X3_S1, 1, 24, 24, 64, 64)            # W does not divide 128 (ragged boxes)
+    conv_case(ops.CONV_3X3_S1, 2, 16, 16, 128, 3)            # `out` conv: N padded to 16, NCHW store
+    conv_case(ops.CONV_3X3_S2, 1, 32, 32, 64, 128)
+    conv_case(ops.CONV_3X3_S2, 2, 16, 16, 128, 256)
+    conv_case(ops.CONV_3X3_S2, 1, 16, 16, 32, 64)
+    conv_case(ops.CONVT_4X4_S2, 1, 8, 8, 128, 64, resid=True)
+    conv_case(ops.CONVT_4X4_S2, 2, 16, 16, 256, 128, resid=True)
+    conv_case(ops.CONVT_4X4_S2, 1, 8, 8, 64, 32)
+    if not args.quick:
+        conv_case(ops.CONV_3X3_S1, 8, 64, 64, 256, 256, film=True)   # many tiles per CTA: ring wrap + TMEM double buffer
+        conv_case(ops.CONV_3X3_S1, 2, 256, 256, 128, 128, resid=True)
+        conv_case(ops.CONV_3X3_S1, 1, 16, 16, 192, 192)
+    print(f"elapsed {time.time() - t0:.1f}s")
+    summary_and_exit()
+
+
+if __name__ == "__main__":
+    main()
