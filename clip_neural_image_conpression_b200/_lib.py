@@ -17,6 +17,9 @@ CONV_3X3_S1 = 0
 CONV_3X3_S2 = 1
 CONVT_4X4_S2 = 2
 
+OP_BF16 = 0
+OP_F16 = 1
+
 
 class ClpkError(RuntimeError):
     pass
@@ -30,7 +33,7 @@ class ConvEpilogue(C.Structure):
         ("film_stride", C.c_int64),
         ("resid", C.c_void_p),
         ("out_f32", C.c_void_p),
-        ("out_bf16", C.c_void_p),
+        ("out_op", C.c_void_p),
         ("out_nchw", C.c_void_p),
         ("cout_valid", C.c_int),
     ]
@@ -45,6 +48,7 @@ class UnetConfig(C.Structure):
         ("time_dim", C.c_int),
         ("img_ch", C.c_int),
         ("groups", C.c_int),
+        ("op_dtype", C.c_int),
     ]
 
 
@@ -63,10 +67,10 @@ SIGNATURES = {
     "clpk_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "clpk_film_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "clpk_groupnorm_ws_bytes": (_i64, [_i, _i, _i, _i]),
-    "clpk_groupnorm_silu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
-    "clpk_pack_conv_weight": (_i64, [_vp, _vp, _i, _i, _i, _vp]),
-    "clpk_conv_igemm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
-    "clpk_conv_direct": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
+    "clpk_groupnorm_silu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "clpk_pack_conv_weight": (_i64, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "clpk_conv_igemm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
+    "clpk_conv_direct": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
     "clpk_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "clpk_plan_create": (_i, [C.POINTER(UnetConfig), _i, _i, _i, _i, C.POINTER(C.c_char_p), C.POINTER(_vp),
                               C.POINTER(_i64), C.POINTER(_vp)]),
@@ -77,6 +81,8 @@ SIGNATURES = {
     "clpk_unet_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "clpk_plan_prepare_ddim": (_i, [_vp, _i, C.POINTER(_i64), C.POINTER(_f), _i, _vp]),
     "clpk_ddim_sample": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "clpk_plan_profile_steps": (_i, [_vp, _i, C.POINTER(_f), C.POINTER(_i), _vp]),
+    "clpk_plan_work_breakdown": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "clpk_to_uint8_hwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "clpk_psnr_sqerr_u8": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
 }
@@ -133,3 +139,14 @@ def stream_ptr() -> int:
 
 def ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
+
+
+def op_code(dtype) -> int:
+    """torch dtype of the 16-bit tensor-core operands -> CLPK_OP_* code."""
+    import torch
+
+    if dtype == torch.float16:
+        return OP_F16
+    if dtype == torch.bfloat16:
+        return OP_BF16
+    raise ValueError(f"tensor-core operand dtype must be torch.float16 or torch.bfloat16, got {dtype}")

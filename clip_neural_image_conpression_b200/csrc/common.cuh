@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -139,8 +140,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T ; bf16 inputs, fp32 accumulate; issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T ; 16-bit inputs (format in idesc), fp32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_f16kind(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -181,9 +182,11 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
-// Instruction descriptor for kind::f16, A=B=bf16 (K-major), D=fp32 (cute::UMMA::InstrDescriptor bit layout).
-__host__ __device__ inline uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor bit layout): D = fp32 (bit 4), A and B formats at
+// bits [7,10) / [10,13): 0 = fp16, 1 = bf16; both operands K-major; N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ inline uint32_t make_idesc_16bit(int m, int n, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ---- misc math ------------------------------------------------------------------------------------------------
@@ -192,6 +195,23 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// two fp32 -> two 16-bit operand values (fp16 when f16, else bf16), round to nearest even
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi, bool f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ uint16_t to_op(float v, bool f16) {
+  if (f16) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 b = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&b);
+}
+__device__ __forceinline__ float from_op(uint16_t raw, bool f16) {
+  if (f16) return __half2float(*reinterpret_cast<const __half*>(&raw));
+  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&raw));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

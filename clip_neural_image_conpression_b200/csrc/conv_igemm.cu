@@ -3,7 +3,8 @@
 // Replaces the cuDNN calls behind nn.Conv2d / nn.ConvTranspose2d of the reference
 // (PKG/models/blocks.py:34,36 ResBlock convs; PKG/models/unet.py:63 stride-2 convs, :75 transposed convs, :79 out).
 //
-// GEMM view:  D[M = pixels, N = Cout] = A[M, K = taps*Cin] * W[N, K]^T, bf16 operands, fp32 accumulation in TMEM.
+// GEMM view:  D[M = pixels, N = Cout] = A[M, K = taps*Cin] * W[N, K]^T, 16-bit operands (fp16 default, bf16
+//             selectable — same kind::f16 rate), fp32 accumulation in TMEM.
 //   * A is never materialised: an M tile is a (wbox x hbox) patch of ONE image, and the k-block of tap (r,s) is the
 //     same patch shifted by (r-1, s-1).  One tiled TMA load over a 5-D view of the NHWC activation fetches it, with
 //     the conv zero padding produced by TMA out-of-bounds fill.  Views (innermost first):
@@ -122,7 +123,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp == 1) {
     // ===================================================== MMA issuer (single thread)
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
+      const uint32_t idesc = make_idesc_16bit(kTileM, p.block_n, p.op_f16 != 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -140,7 +141,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            umma_f16kind(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
           }
           umma_commit(&bars->empty[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -209,12 +210,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int j4 = 0; j4 < 4; ++j4)
                 op[j4] = make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
             }
-            if (ep.out_bf16) {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + opix * ldc + n);
-              op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                 pack_bf16x2(v[6], v[7]));
-              op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                 pack_bf16x2(v[14], v[15]));
+            if (ep.out_op) {
+              const bool f16 = p.op_f16 != 0;
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out_op) + opix * ldc + n);
+              op[0] = make_uint4(pack_op2(v[0], v[1], f16), pack_op2(v[2], v[3], f16), pack_op2(v[4], v[5], f16),
+                                 pack_op2(v[6], v[7], f16));
+              op[1] = make_uint4(pack_op2(v[8], v[9], f16), pack_op2(v[10], v[11], f16), pack_op2(v[12], v[13], f16),
+                                 pack_op2(v[14], v[15], f16));
             }
             if (ep.out_nchw) {
 #pragma unroll
@@ -250,8 +252,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
 // ------------------------------------------------------------------------------------------------ cross-check kernel
 // One thread per output element, same operands / tap tables / epilogue, plain fp32 FMAs.
-__global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wpk,
+__global__ void conv_direct_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ wpk,
                                    const IgemmParams p) {
+  const bool f16 = p.op_f16 != 0;
   const long long total = (long long)p.phases * p.batch * p.grid_h * p.grid_w * p.cout_pad;
   const clpk_conv_epilogue& ep = p.ep;
   const int ldc = ep.cout_valid;
@@ -265,17 +268,17 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __
     const int phase = (int)(r / p.batch);
     if (n >= ldc) continue;
     const long long ktot = (long long)p.taps * p.cin;
-    const __nv_bfloat16* wrow = wpk + ((long long)phase * p.cout_pad + n) * ktot;
+    const uint16_t* wrow = wpk + ((long long)phase * p.cout_pad + n) * ktot;
     float acc = 0.f;
     for (int t = 0; t < p.taps; ++t) {
       const int ti = phase * p.taps + t;
       const int cw = w + p.tap_dw[ti], ch = h + p.tap_dh[ti], cp = p.tap_p[ti];
       if (cw < 0 || cw >= p.a_dim_w || ch < 0 || ch >= p.a_dim_h) continue;  // zero padding
-      const __nv_bfloat16* xp =
+      const uint16_t* xp =
           x + (long long)b * p.a_stride_b + (long long)ch * p.a_stride_h + (long long)cp * p.a_stride_p +
           (long long)cw * p.a_stride_w + p.tap_x[ti];
-      const __nv_bfloat16* wp = wrow + (long long)t * p.cin;
-      for (int c = 0; c < p.cin; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
+      const uint16_t* wp = wrow + (long long)t * p.cin;
+      for (int c = 0; c < p.cin; ++c) acc = fmaf(from_op(xp[c], f16), from_op(wp[c], f16), acc);
     }
     float y = acc + ep.bias[n];
     if (ep.film_scale1p)
@@ -284,15 +287,15 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __
     const long long opix = ((long long)b * p.out_h + oh) * p.out_w + ow;
     if (ep.resid) y += ep.resid[opix * ldc + n];
     if (ep.out_f32) ep.out_f32[opix * ldc + n] = y;
-    if (ep.out_bf16) reinterpret_cast<__nv_bfloat16*>(ep.out_bf16)[opix * ldc + n] = __float2bfloat16_rn(y);
+    if (ep.out_op) reinterpret_cast<uint16_t*>(ep.out_op)[opix * ldc + n] = to_op(y, f16);
     if (ep.out_nchw) ep.out_nchw[(((long long)b * ldc + n) * p.out_h + oh) * p.out_w + ow] = y;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
 // Conv2d [Cout,Cin,3,3] -> [cout_pad][tap][Cin];  ConvTranspose2d [Cin,Cout,4,4] -> [phase][cout_pad][tap][Cin]
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kind, int cin,
-                                   int cout, int cout_pad) {
+__global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int kind, int cin,
+                                   int cout, int cout_pad, int op_f16) {
   const int taps = (kind == CLPK_CONVT_4X4_S2) ? 4 : 9;
   const int phases = (kind == CLPK_CONVT_4X4_S2) ? 4 : 1;
   const long long total = (long long)phases * cout_pad * taps * cin;
@@ -316,7 +319,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
         v = w[((long long)n * cin + c) * 9 + t];
       }
     }
-    out[idx] = __float2bfloat16_rn(v);
+    out[idx] = to_op(v, op_f16 != 0);
   }
 }
 
@@ -347,14 +350,14 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                      const cuuint32_t* box, int swizzle_bytes) {
+                      const cuuint32_t* box, int swizzle_bytes, bool f16) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return CLPK_ERR_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -367,8 +370,9 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 }
 
 int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, int h_in, int w_in, int cin, int cout,
-                const clpk_conv_epilogue* ep, IgemmLaunch* out) {
+                int op_dtype, const clpk_conv_epilogue* ep, IgemmLaunch* out) {
   CLPK_REQUIRE(kind >= 0 && kind <= 2, "conv kind %d unknown", kind);
+  CLPK_REQUIRE(op_dtype == CLPK_OP_BF16 || op_dtype == CLPK_OP_F16, "operand dtype %d unknown", op_dtype);
   CLPK_REQUIRE(batch > 0 && h_in > 0 && w_in > 0, "bad conv geometry");
   CLPK_REQUIRE(cin % 32 == 0, "implicit-GEMM conv needs Cin %% 32 == 0 (got %d)", cin);
   CLPK_REQUIRE(ep && ep->bias, "conv epilogue needs a bias");
@@ -378,6 +382,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   IgemmParams& p = out->p;
   memset(&p, 0, sizeof(p));
   p.batch = batch;
+  p.op_f16 = (op_dtype == CLPK_OP_F16) ? 1 : 0;
   p.cin = cin;
   p.cout_pad = igemm_cout_pad(cout);
   p.block_k = (cin % 64 == 0) ? 64 : 32;
@@ -388,7 +393,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   if (p.ep.cout_valid <= 0) p.ep.cout_valid = cout;
   CLPK_REQUIRE(p.ep.cout_valid == cout, "cout_valid must equal cout");
   if (cout % 16 != 0)
-    CLPK_REQUIRE(!p.ep.out_f32 && !p.ep.out_bf16 && !p.ep.resid, "Cout %% 16 != 0 supports the NCHW output only");
+    CLPK_REQUIRE(!p.ep.out_f32 && !p.ep.out_op && !p.ep.resid, "Cout %% 16 != 0 supports the NCHW output only");
 
   cuuint64_t dims[5], strides[4];
   const long long C = cin, W = w_in, H = h_in;
@@ -451,12 +456,12 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
 
   const int swz = p.block_k * 2;
   cuuint32_t box_a[5] = {(cuuint32_t)p.block_k, (cuuint32_t)p.wbox, 1, (cuuint32_t)p.hbox, 1};
-  int rc = encode_map(&out->map_a, x_bf16, 5, dims, strides, box_a, swz);
+  int rc = encode_map(&out->map_a, x_bf16, 5, dims, strides, box_a, swz, p.op_f16 != 0);
   if (rc) return rc;
   cuuint64_t wdims[2] = {(cuuint64_t)p.taps * cin, (cuuint64_t)p.phases * p.cout_pad};
   cuuint64_t wstr[1] = {(cuuint64_t)p.taps * cin * 2};
   cuuint32_t box_w[2] = {(cuuint32_t)p.block_k, (cuuint32_t)p.block_n};
-  rc = encode_map(&out->map_w, w_packed, 2, wdims, wstr, box_w, swz);
+  rc = encode_map(&out->map_w, w_packed, 2, wdims, wstr, box_w, swz, p.op_f16 != 0);
   return rc;
 }
 
@@ -486,8 +491,8 @@ int igemm_launch(const IgemmLaunch& L, cudaStream_t stream) {
 int direct_launch(const IgemmLaunch& L, const void* x_bf16, const void* w_packed, cudaStream_t stream) {
   const long long total = (long long)L.p.phases * L.p.batch * L.p.grid_h * L.p.grid_w * L.p.cout_pad;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 65535ll * 8);
-  conv_direct_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16),
-                                                 reinterpret_cast<const __nv_bfloat16*>(w_packed), L.p);
+  conv_direct_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x_bf16),
+                                                 reinterpret_cast<const uint16_t*>(w_packed), L.p);
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }
@@ -497,8 +502,8 @@ int direct_launch(const IgemmLaunch& L, const void* x_bf16, const void* w_packed
 using namespace clpk;
 
 extern "C" int64_t clpk_pack_conv_weight(const float* w_dev, void* out_bf16_dev, int kind, int cin, int cout,
-                                         void* stream) {
-  if (kind < 0 || kind > 2 || cin <= 0 || cout <= 0) {
+                                         int op_dtype, void* stream) {
+  if (kind < 0 || kind > 2 || cin <= 0 || cout <= 0 || (op_dtype != CLPK_OP_BF16 && op_dtype != CLPK_OP_F16)) {
     set_error("clpk_pack_conv_weight: bad arguments");
     return -1;
   }
@@ -507,8 +512,8 @@ extern "C" int64_t clpk_pack_conv_weight(const float* w_dev, void* out_bf16_dev,
   const long long total = (long long)phases * cout_pad * taps * cin;
   if (!out_bf16_dev) return total;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 65535);
-  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_dev, reinterpret_cast<__nv_bfloat16*>(out_bf16_dev),
-                                                               kind, cin, cout, cout_pad);
+  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_dev, reinterpret_cast<uint16_t*>(out_bf16_dev), kind,
+                                                               cin, cout, cout_pad, op_dtype == CLPK_OP_F16);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("pack_weight_kernel launch failed: %s", cudaGetErrorString(e));
@@ -519,17 +524,17 @@ extern "C" int64_t clpk_pack_conv_weight(const float* w_dev, void* out_bf16_dev,
 }
 
 extern "C" int clpk_conv_igemm(const void* x, const void* w, int kind, int batch, int h_in, int w_in, int cin, int cout,
-                               const clpk_conv_epilogue* ep, void* stream) {
+                               int op_dtype, const clpk_conv_epilogue* ep, void* stream) {
   IgemmLaunch L;
-  int rc = igemm_setup(x, w, kind, batch, h_in, w_in, cin, cout, ep, &L);
+  int rc = igemm_setup(x, w, kind, batch, h_in, w_in, cin, cout, op_dtype, ep, &L);
   if (rc) return rc;
   return igemm_launch(L, (cudaStream_t)stream);
 }
 
 extern "C" int clpk_conv_direct(const void* x, const void* w, int kind, int batch, int h_in, int w_in, int cin,
-                                int cout, const clpk_conv_epilogue* ep, void* stream) {
+                                int cout, int op_dtype, const clpk_conv_epilogue* ep, void* stream) {
   IgemmLaunch L;
-  int rc = igemm_setup(x, w, kind, batch, h_in, w_in, cin, cout, ep, &L);
+  int rc = igemm_setup(x, w, kind, batch, h_in, w_in, cin, cout, op_dtype, ep, &L);
   if (rc) return rc;
   return direct_launch(L, x, w, (cudaStream_t)stream);
 }

@@ -17,6 +17,7 @@ struct IgemmParams {
   int tiles_w, tiles_h;
   int phases, taps, kpt;    // kpt = k-blocks per tap = cin / block_k
   int num_tiles, stages, tmem_cols;
+  int op_f16;               // operand format: 1 = fp16, 0 = bf16
   // A-operand coordinates (5-D view of the NHWC input, see make_a_map): per (phase*taps + tap)
   int tap_x[kMaxTapEntries], tap_dw[kMaxTapEntries], tap_p[kMaxTapEntries], tap_dh[kMaxTapEntries];
   // element strides of that 5-D view (used by the CUDA-core cross-check kernel only)
@@ -35,9 +36,9 @@ struct IgemmLaunch {
   int smem_bytes;
 };
 
-// Fills `out` for a convolution of `kind` over x (bf16 NHWC [batch,h_in,w_in,cin]) with packed weights.
-int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, int h_in, int w_in, int cin, int cout,
-                const clpk_conv_epilogue* ep, IgemmLaunch* out);
+// Fills `out` for a convolution of `kind` over x (16-bit NHWC [batch,h_in,w_in,cin]) with packed weights.
+int igemm_setup(const void* x_op, const void* w_packed, int kind, int batch, int h_in, int w_in, int cin, int cout,
+                int op_dtype, const clpk_conv_epilogue* ep, IgemmLaunch* out);
 int igemm_init();  // one-time function attributes; call outside stream capture
 int igemm_launch(const IgemmLaunch& L, cudaStream_t stream);
 int direct_launch(const IgemmLaunch& L, const void* x_bf16, const void* w_packed, cudaStream_t stream);

@@ -346,8 +346,8 @@ extern "C" uint64_t clpk_launch_count(void) { return g_launches.load(std::memory
 extern "C" int clpk_dequant_l2norm_u8(const uint8_t* q, const float* scale, const float* zero, float* z, float* z_raw,
                                       int batch, int dim, int l2norm, void* stream) {
   CLPK_REQUIRE(batch >= 0 && dim > 0, "clpk_dequant_l2norm_u8: bad shape");
-  CLPK_REQUIRE(q && scale && zero && z, "clpk_dequant_l2norm_u8: null pointer");
   if (batch == 0) return CLPK_OK;
+  CLPK_REQUIRE(q && scale && zero && z, "clpk_dequant_l2norm_u8: null pointer");
   dequant_l2norm_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(q, scale, zero, z, z_raw, dim, l2norm);
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
@@ -355,8 +355,9 @@ extern "C" int clpk_dequant_l2norm_u8(const uint8_t* q, const float* scale, cons
 
 extern "C" int clpk_quant_encode_u8(const float* x, const float* scale, const float* zero, uint8_t* q, int batch, int dim,
                                     void* stream) {
-  CLPK_REQUIRE(batch >= 0 && dim > 0 && x && scale && zero && q, "clpk_quant_encode_u8: bad arguments");
+  CLPK_REQUIRE(batch >= 0 && dim > 0, "clpk_quant_encode_u8: bad shape");
   if (batch == 0) return CLPK_OK;
+  CLPK_REQUIRE(x && scale && zero && q, "clpk_quant_encode_u8: null pointer");
   const long long total = (long long)batch * dim;
   quant_encode_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, (cudaStream_t)stream>>>(
       x, scale, zero, q, total, dim);

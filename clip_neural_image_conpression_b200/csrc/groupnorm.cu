@@ -127,7 +127,9 @@ gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float
 // y = (x - mean) * rstd * gamma + beta, optional SiLU, 8 channels (32 B in, 16 B out) per thread iteration.
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float2* __restrict__ stats, __nv_bfloat16* __restrict__ y, int hw, int c, int groups, int silu) {
+                const float2* __restrict__ stats, uint16_t* __restrict__ y, int hw, int c, int groups, int silu,
+                int op_f16) {
+  const bool f16 = op_f16 != 0;
   const int b = blockIdx.y;
   const unsigned oc = (unsigned)c >> 3;  // 8-channel octets per pixel
   const int cpg = c / groups;
@@ -151,13 +153,13 @@ gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
 #pragma unroll
       for (int k = 0; k < 8; ++k) r[k] = silu_f(r[k]);
     }
-    yb[i] = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
-                       pack_bf16x2(r[6], r[7]));
+    yb[i] = make_uint4(pack_op2(r[0], r[1], f16), pack_op2(r[2], r[3], f16), pack_op2(r[4], r[5], f16),
+                       pack_op2(r[6], r[7], f16));
   }
 }
 
 int launch_groupnorm(const float* x, const float* gamma, const float* beta, void* y_bf16, void* ws, const GnShape& s,
-                     float eps, int silu, cudaStream_t stream) {
+                     float eps, int silu, int op_dtype, cudaStream_t stream) {
   CLPK_REQUIRE(s.c % 8 == 0 && s.c % s.groups == 0 && (s.c / s.groups) % 4 == 0,
                "GroupNorm needs C %% 8 == 0 and (C/groups) %% 4 == 0 (C=%d groups=%d)", s.c, s.groups);
   CLPK_REQUIRE(s.c <= 4 * kGnMaxJ * kGnThreads, "GroupNorm supports C <= %d", 4 * kGnMaxJ * kGnThreads);
@@ -189,8 +191,8 @@ int launch_groupnorm(const float* x, const float* gamma, const float* beta, void
   const int per_img_blocks = (int)std::min<long long>((octs + kGnThreads - 1) / kGnThreads,
                                                       std::max(1, num_sms() * 8 / s.batch));
   dim3 agrid(std::max(per_img_blocks, 1), s.batch);
-  gn_apply_kernel<<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, reinterpret_cast<__nv_bfloat16*>(y_bf16),
-                                                   s.hw, s.c, s.groups, silu);
+  gn_apply_kernel<<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, reinterpret_cast<uint16_t*>(y_bf16), s.hw,
+                                                   s.c, s.groups, silu, op_dtype == CLPK_OP_F16);
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }
@@ -205,11 +207,12 @@ extern "C" int64_t clpk_groupnorm_ws_bytes(int batch, int hw, int c, int groups)
 }
 
 extern "C" int clpk_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* y, void* ws, int batch,
-                                   int hw, int c, int groups, float eps, int silu, void* stream) {
+                                   int hw, int c, int groups, float eps, int silu, int op_dtype, void* stream) {
+  CLPK_REQUIRE(op_dtype == CLPK_OP_BF16 || op_dtype == CLPK_OP_F16, "clpk_groupnorm_silu: operand dtype %d unknown", op_dtype);
   CLPK_REQUIRE(x && gamma && beta && y && ws && batch > 0 && hw > 0 && c > 0 && groups > 0,
                "clpk_groupnorm_silu: bad arguments");
   const GnShape s = gn_shape(batch, hw, c, groups);
   // the leaf entry point cannot assume the counters (start of ws) are zero
   CLPK_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)batch * 4, (cudaStream_t)stream));
-  return launch_groupnorm(x, gamma, beta, y, ws, s, eps, silu, (cudaStream_t)stream);
+  return launch_groupnorm(x, gamma, beta, y, ws, s, eps, silu, op_dtype, (cudaStream_t)stream);
 }

@@ -33,8 +33,8 @@ struct GnShape {
 };
 GnShape gn_shape(int batch, int hw, int c, int groups);
 long long gn_ws_bytes(const GnShape& s);
-int launch_groupnorm(const float* x, const float* gamma, const float* beta, void* y_bf16, void* ws, const GnShape& s,
-                     float eps, int silu, cudaStream_t stream);
+int launch_groupnorm(const float* x, const float* gamma, const float* beta, void* y_op, void* ws, const GnShape& s,
+                     float eps, int silu, int op_dtype, cudaStream_t stream);
 
 // conv_in.cu
 int launch_conv_in(const float* x_nchw, const float* w, const float* b, float* y_nhwc, int batch, int cin, int h, int w_,

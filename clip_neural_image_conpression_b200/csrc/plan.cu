@@ -19,7 +19,7 @@ namespace clpk {
 
 struct ConvPlan {
   int kind = 0, cin = 0, cout = 0, h_in = 0, w_in = 0;
-  __nv_bfloat16* w = nullptr;
+  uint16_t* w = nullptr;  // packed 16-bit operand (fp16 or bf16)
   float* bias = nullptr;
   IgemmLaunch L;
   double flops = 0;
@@ -55,7 +55,7 @@ struct clpk_plan {
   // workspace
   std::vector<float*> X;
   float* Y = nullptr;
-  __nv_bfloat16 *T = nullptr, *D = nullptr;
+  uint16_t *T = nullptr, *D = nullptr;  // 16-bit operand buffers (fp16 or bf16, cfg.op_dtype)
   void* gn_ws = nullptr;
   float *temb = nullptr, *h1 = nullptr, *ht = nullptr, *hcond = nullptr, *film = nullptr, *zemb = nullptr;
   int64_t* t_buf = nullptr;
@@ -70,6 +70,23 @@ struct clpk_plan {
   bool any_sigma = false;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t cap_stream = nullptr;  // private stream used only to capture the step graph (the caller's stream may be
+                                      // the legacy default stream, which cannot be captured)
+  // optional per-launch timing (clpk_plan_profile_forward): event pairs around every launch, tagged by class
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_cat;
+  size_t prof_used = 0;
+  void prof_mark(int cat, cudaStream_t s) {
+    if (!prof_on) return;
+    if (prof_used == prof_ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      prof_ev.push_back(e);
+    }
+    cudaEventRecord(prof_ev[prof_used++], s);
+    prof_cat.push_back(cat);
+  }
 
   template <typename Tp>
   int alloc(Tp** p, long long n_elems) {
@@ -113,6 +130,17 @@ struct ParamTable {
     if (_rc != CLPK_OK) return _rc; \
   } while (0)
 
+// launch `expr` on stream `s`, bracketed by profiling events of class `cat` when profiling is on
+#define CLPK_TIMED(P, cat, s, expr) \
+  do {                              \
+    (P)->prof_mark((cat), (s));     \
+    int _rc = (expr);               \
+    (P)->prof_mark(-1, (s));        \
+    if (_rc != CLPK_OK) return _rc; \
+  } while (0)
+
+enum ProfClass { kProfConvRes = 0, kProfConvOther = 1, kProfGroupNorm = 2, kProfConvIn = 3, kProfCond = 4, kProfDdim = 5 };
+
 int copy_param(clpk_plan* P, const ParamTable& tab, const std::string& name, int64_t numel, float** dst) {
   const float* src = nullptr;
   CLPK_TRY(tab.get(name, numel, &src));
@@ -127,10 +155,10 @@ int make_conv(clpk_plan* P, const ParamTable& tab, const std::string& prefix, in
   const int taps = (kind == CLPK_CONVT_4X4_S2) ? 16 : 9;
   const float* w = nullptr;
   CLPK_TRY(tab.get(prefix + ".weight", (int64_t)cin * cout * taps, &w));
-  const int64_t n = clpk_pack_conv_weight(nullptr, nullptr, kind, cin, cout, nullptr);
+  const int64_t n = clpk_pack_conv_weight(nullptr, nullptr, kind, cin, cout, P->cfg.op_dtype, nullptr);
   if (n < 0) return CLPK_ERR_ARG;
   CLPK_TRY(P->alloc(&cv->w, n));
-  if (clpk_pack_conv_weight(w, cv->w, kind, cin, cout, nullptr) < 0) return CLPK_ERR_CUDA;
+  if (clpk_pack_conv_weight(w, cv->w, kind, cin, cout, P->cfg.op_dtype, nullptr) < 0) return CLPK_ERR_CUDA;
   // bias padded to the GEMM N (zeros beyond cout) so the vectorised epilogue may read whole 16-wide chunks
   const int cout_pad = igemm_cout_pad(cout);
   const float* b = nullptr;
@@ -169,48 +197,51 @@ int make_resblock(clpk_plan* P, const ParamTable& tab, const std::string& prefix
 
 // bind the buffers of a conv (A operand, epilogue) and encode its tensor maps
 int bind_conv(clpk_plan* P, ConvPlan* cv, const void* a, const clpk_conv_epilogue& ep) {
-  return igemm_setup(a, cv->w, cv->kind, P->B, cv->h_in, cv->w_in, cv->cin, cv->cout, &ep, &cv->L);
+  return igemm_setup(a, cv->w, cv->kind, P->B, cv->h_in, cv->w_in, cv->cin, cv->cout, P->cfg.op_dtype, &ep, &cv->L);
 }
 
 int run_groupnorm(clpk_plan* P, const float* x, const float* g, const float* b, int level, int silu, cudaStream_t s) {
   const GnShape shp = gn_shape(P->B, P->lv_h[level] * P->lv_w[level], P->lv_c[level], std::min(P->cfg.groups, P->lv_c[level]));
-  return launch_groupnorm(x, g, b, P->T, P->gn_ws, shp, 1e-5f, silu, s);
+  CLPK_TIMED(P, kProfGroupNorm, s, launch_groupnorm(x, g, b, P->T, P->gn_ws, shp, 1e-5f, silu, P->cfg.op_dtype, s));
+  return CLPK_OK;
 }
 
 int run_resblock(clpk_plan* P, ResBlockPlan& rb, cudaStream_t s) {
   float* X = P->X[rb.level];
   CLPK_TRY(run_groupnorm(P, X, rb.g1, rb.b1, rb.level, 1, s));     // blocks.py:41 act(norm1(x))
-  CLPK_TRY(igemm_launch(rb.conv1.L, s));                           // conv1 + FiLM -> Y   (blocks.py:41-42)
+  CLPK_TIMED(P, kProfConvRes, s, igemm_launch(rb.conv1.L, s));     // conv1 + FiLM -> Y   (blocks.py:41-42)
   CLPK_TRY(run_groupnorm(P, P->Y, rb.g2, rb.b2, rb.level, 1, s));  // blocks.py:43 act(norm2(y))
-  CLPK_TRY(igemm_launch(rb.conv2.L, s));                           // conv2 + x -> X      (blocks.py:43-44)
+  CLPK_TIMED(P, kProfConvRes, s, igemm_launch(rb.conv2.L, s));     // conv2 + x -> X      (blocks.py:43-44)
   return CLPK_OK;
 }
 
 // everything after the conditioning vector: in_conv ... out   (unet.py:88-105).  film = [B, film_n].
 int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s) {
   const clpk_unet_config& c = P->cfg;
-  CLPK_TRY(launch_conv_in(x_nchw, P->in_w, P->in_b, P->X[0], P->B, c.img_ch, P->H, P->W, c.base, s));
+  CLPK_TIMED(P, kProfConvIn, s, launch_conv_in(x_nchw, P->in_w, P->in_b, P->X[0], P->B, c.img_ch, P->H, P->W, c.base, s));
   size_t r = 0;
   for (int l = 0; l < P->n_levels; ++l) {
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
-    CLPK_TRY(igemm_launch(P->downs[l].L, s));  // D (bf16 copy of X[l]) -> X[l+1]
+    CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->downs[l].L, s));  // D (bf16 copy of X[l]) -> X[l+1]
   }
   CLPK_TRY(run_resblock(P, P->rbs[r++], s));
   CLPK_TRY(run_resblock(P, P->rbs[r++], s));
   for (int l = P->n_levels - 1; l >= 0; --l) {
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
-    CLPK_TRY(igemm_launch(P->ups[l].L, s));  // D (bf16 copy of X[l+1]) -> X[l] += convT  (skip add, unet.py:102-104)
+    CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->ups[l].L, s));  // D (bf16 of X[l+1]) -> X[l] += convT (unet.py:102-104)
   }
   CLPK_TRY(run_groupnorm(P, P->X[0], P->on_g, P->on_b, 0, 0, s));  // out_norm, no activation (unet.py:105)
-  CLPK_TRY(igemm_launch(P->out_conv.L, s));                        // -> eps_buf (NCHW)
+  CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->out_conv.L, s));  // -> eps_buf (NCHW)
   return CLPK_OK;
 }
 
 // film[B, film_n] = Linear_film(h) ; h = time_proj(temb(t)) + z_proj(z)   (unet.py:83-86, blocks.py:22-24)
 int film_from_h(clpk_plan* P, cudaStream_t s) {
-  return launch_linear(P->hcond, P->film_w, P->film_b, nullptr, 0, P->film, P->B, P->film_n, P->cfg.time_dim, 0, s);
+  CLPK_TIMED(P, kProfCond, s,
+             launch_linear(P->hcond, P->film_w, P->film_b, nullptr, 0, P->film, P->B, P->film_n, P->cfg.time_dim, 0, s));
+  return CLPK_OK;
 }
 
 }  // namespace
@@ -219,6 +250,8 @@ extern "C" void clpk_plan_destroy(clpk_plan* P) {
   if (!P) return;
   if (P->graph_exec) cudaGraphExecDestroy(P->graph_exec);
   if (P->graph) cudaGraphDestroy(P->graph);
+  if (P->cap_stream) cudaStreamDestroy(P->cap_stream);
+  for (cudaEvent_t e : P->prof_ev) cudaEventDestroy(e);
   for (void* q : P->allocs) cudaFree(q);
   delete P;
 }
@@ -230,6 +263,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   CLPK_REQUIRE(batch > 0 && height > 0 && width > 0, "clpk_plan_create: bad batch/size");
   CLPK_REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= CLPK_MAX_LEVELS, "clpk_plan_create: bad n_levels");
   CLPK_REQUIRE(cfg->base % 32 == 0, "base channels must be a multiple of 32 (got %d)", cfg->base);
+  CLPK_REQUIRE(cfg->op_dtype == CLPK_OP_BF16 || cfg->op_dtype == CLPK_OP_F16, "bad op_dtype %d", cfg->op_dtype);
   CLPK_REQUIRE(height % (1 << cfg->n_levels) == 0 && width % (1 << cfg->n_levels) == 0,
                "H, W must be divisible by 2^len(ch_mult)");
   int dev_count = 0;
@@ -345,7 +379,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     e2.bias = rb.conv2.bias;
     e2.resid = P->X[rb.level];
     e2.out_f32 = P->X[rb.level];
-    e2.out_bf16 = rb.emit_bf16 ? P->D : nullptr;
+    e2.out_op = rb.emit_bf16 ? P->D : nullptr;
     e2.cout_valid = rb.c;
     CLPK_TRY(bind_conv(P, &rb.conv2, P->T, e2));
     P->flops_fwd += rb.conv1.flops + rb.conv2.flops;
@@ -420,11 +454,11 @@ extern "C" int clpk_unet_forward(clpk_plan* P, const float* x, const float* z, c
 // one DDIM step on plan-owned buffers: conditioning for run->step, eps = UNet(x_buf), x_buf <- update, step += 1
 static int ddim_step_body(clpk_plan* P, cudaStream_t s) {
   const int td = P->cfg.time_dim;
-  CLPK_TRY(launch_cond_combine(P->zemb, P->ht_tab, P->run_dev, P->hcond, P->B, td, s));
+  CLPK_TIMED(P, kProfCond, s, launch_cond_combine(P->zemb, P->ht_tab, P->run_dev, P->hcond, P->B, td, s));
   CLPK_TRY(film_from_h(P, s));
   CLPK_TRY(forward_body(P, P->x_buf, s));
   const long long n = (long long)P->B * P->cfg.img_ch * P->H * P->W;
-  CLPK_TRY(launch_ddim_step(P->x_buf, P->eps_buf, P->coef_tab, P->run_dev, P->x_buf, n, s));
+  CLPK_TIMED(P, kProfDdim, s, launch_ddim_step(P->x_buf, P->eps_buf, P->coef_tab, P->run_dev, P->x_buf, n, s));
   return CLPK_OK;
 }
 
@@ -453,11 +487,13 @@ extern "C" int clpk_plan_prepare_ddim(clpk_plan* P, int steps, const int64_t* ts
   P->any_sigma = false;
   for (int i = 0; i < steps; ++i) P->any_sigma = P->any_sigma || (coef_host[i * 5 + 4] > 0.f);
   if (use_graph) {
-    CLPK_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    int rc = ddim_step_body(P, s);
-    if (rc == CLPK_OK) rc = launch_ddim_advance(P->run_dev, s);
+    if (!P->cap_stream) CLPK_CHECK_CUDA(cudaStreamCreateWithFlags(&P->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = P->cap_stream;
+    CLPK_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = ddim_step_body(P, cs);
+    if (rc == CLPK_OK) rc = launch_ddim_advance(P->run_dev, cs);
     cudaGraph_t g = nullptr;
-    cudaError_t e = cudaStreamEndCapture(s, &g);
+    cudaError_t e = cudaStreamEndCapture(cs, &g);
     if (rc != CLPK_OK) { if (g) cudaGraphDestroy(g); return rc; }
     CLPK_CHECK_CUDA(e);
     P->graph = g;
@@ -501,5 +537,61 @@ extern "C" int clpk_ddim_sample(clpk_plan* P, const float* z, float* x, const fl
   CLPK_CHECK_CUDA(cudaMemcpyAsync(x, P->x_buf, nb, cudaMemcpyDeviceToDevice, s));
   // `run` lives on this frame and was copied with cudaMemcpyAsync from pageable memory (staged synchronously by the
   // runtime), so no extra synchronisation is needed here.
+  return CLPK_OK;
+}
+
+// Runs `iters` eager (non-graph) DDIM steps of the prepared run on the plan's own buffers with CUDA events around every
+// launch and returns, per kernel class, the summed device time (ms) and the launch-pair count:
+//   0 ResBlock 3x3 convs (tcgen05)  1 other tcgen05 convs (stride 2, transposed, out)  2 GroupNorm (stats+apply)
+//   3 stem conv  4 conditioning (combine + FiLM GEMV)  5 DDIM update
+// The state advances like a real run (step counter wraps), so the numbers are those of the production kernels on
+// production-shaped data.  Used by bench.py for the live roofline figures.
+extern "C" int clpk_plan_profile_steps(clpk_plan* P, int iters, float* ms_out6, int* count_out6, void* stream) {
+  CLPK_REQUIRE(P && ms_out6 && count_out6 && iters > 0, "clpk_plan_profile_steps: bad arguments");
+  if (P->steps <= 0) {
+    set_error("clpk_plan_profile_steps: call clpk_plan_prepare_ddim first");
+    return CLPK_ERR_STATE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int k = 0; k < 6; ++k) { ms_out6[k] = 0.f; count_out6[k] = 0; }
+  DdimRun run{};
+  for (int it = 0; it < iters; ++it) {
+    run.step = it % P->steps;
+    run.noise = nullptr;
+    run.seed = 0;
+    run.noise_step_stride = 0;
+    CLPK_CHECK_CUDA(cudaMemcpyAsync(P->run_dev, &run, sizeof(run), cudaMemcpyHostToDevice, s));
+    P->prof_on = true;
+    P->prof_used = 0;
+    P->prof_cat.clear();
+    int rc = ddim_step_body(P, s);
+    P->prof_on = false;
+    if (rc != CLPK_OK) return rc;
+    CLPK_CHECK_CUDA(cudaStreamSynchronize(s));
+    for (size_t i = 0; i + 1 < P->prof_used; i += 2) {
+      float ms = 0.f;
+      CLPK_CHECK_CUDA(cudaEventElapsedTime(&ms, P->prof_ev[i], P->prof_ev[i + 1]));
+      const int cat = P->prof_cat[i];
+      if (cat >= 0 && cat < 6) { ms_out6[cat] += ms; count_out6[cat] += 1; }
+    }
+  }
+  return CLPK_OK;
+}
+
+// algorithmic FLOPs per forward of the two tcgen05 conv classes (0: ResBlock convs, 1: other) and the number of fp32
+// elements GroupNorm reads per forward (all 2*n_resblocks + 1 instances), at the plan's batch.
+extern "C" int clpk_plan_work_breakdown(const clpk_plan* P, double* conv_res_flops, double* conv_other_flops,
+                                        double* gn_elements) {
+  CLPK_REQUIRE(P && conv_res_flops && conv_other_flops && gn_elements, "clpk_plan_work_breakdown: null argument");
+  double a = 0, b = 0, g = 0;
+  for (const ResBlockPlan& rb : P->rbs) {
+    a += rb.conv1.flops + rb.conv2.flops;
+    g += 2.0 * P->B * (double)rb.h * rb.w * rb.c;
+  }
+  for (const ConvPlan& c : P->downs) b += c.flops;
+  for (const ConvPlan& c : P->ups) b += c.flops;
+  b += P->out_conv.flops;
+  g += (double)P->B * P->H * P->W * P->cfg.base;  // out_norm
+  *conv_res_flops = a; *conv_other_flops = b; *gn_elements = g;
   return CLPK_OK;
 }

@@ -50,6 +50,7 @@ class ResBlock(nn.Module):
         self.conv2 = nn.Conv2d(c, c, 3, padding=1)
         self.film = FiLM(c, cond_dim)
         self.act = nn.SiLU()
+        self.operand_dtype = torch.float16  # tensor-core operand format (torch.bfloat16 also supported)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
@@ -57,10 +58,11 @@ class ResBlock(nn.Module):
         c = self.conv1.out_channels
         x_nhwc = x.float().permute(0, 2, 3, 1).contiguous()
         sc, sh = self.film.scale_shift(h)
-        a = ops.groupnorm_silu(x_nhwc, self.norm1.weight, self.norm1.bias, self.norm1.num_groups, self.norm1.eps)
-        y = ops.conv_igemm(a, ops.pack_conv_weight(self.conv1.weight, ops.CONV_3X3_S1), ops.CONV_3X3_S1, c,
+        dt = self.operand_dtype
+        a = ops.groupnorm_silu(x_nhwc, self.norm1.weight, self.norm1.bias, self.norm1.num_groups, self.norm1.eps, dtype=dt)
+        y = ops.conv_igemm(a, ops.pack_conv_weight(self.conv1.weight, ops.CONV_3X3_S1, dt), ops.CONV_3X3_S1, c,
                            self.conv1.bias, film_scale1p=sc, film_shift=sh)["f32"]
-        a = ops.groupnorm_silu(y, self.norm2.weight, self.norm2.bias, self.norm2.num_groups, self.norm2.eps)
-        out = ops.conv_igemm(a, ops.pack_conv_weight(self.conv2.weight, ops.CONV_3X3_S1), ops.CONV_3X3_S1, c,
+        a = ops.groupnorm_silu(y, self.norm2.weight, self.norm2.bias, self.norm2.num_groups, self.norm2.eps, dtype=dt)
+        out = ops.conv_igemm(a, ops.pack_conv_weight(self.conv2.weight, ops.CONV_3X3_S1, dt), ops.CONV_3X3_S1, c,
                              self.conv2.bias, resid=x_nhwc)["f32"]
         return out.permute(0, 3, 1, 2).contiguous()

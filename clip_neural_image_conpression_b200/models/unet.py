@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from .. import _lib, ops
-from .._lib import UnetConfig, check, ptr, require_cuda, stream_ptr
+from .._lib import UnetConfig, check, op_code, ptr, require_cuda, stream_ptr
 from .blocks import FiLM, ResBlock  # noqa: F401  (FiLM re-exported like the reference module does)
 
 
@@ -35,6 +35,7 @@ class _Plan:
         for i, m in enumerate(net.ch_mult):
             cfg.ch_mult[i] = int(m)
         cfg.time_dim, cfg.img_ch, cfg.groups = net.time_dim, net.img_ch, 8
+        cfg.op_dtype = op_code(net.operand_dtype)
         sd = {k: v.detach().float().contiguous() for k, v in net.state_dict().items()}
         names = (C.c_char_p * len(sd))(*[k.encode() for k in sd])
         ptrs = (C.c_void_p * len(sd))(*[v.data_ptr() for v in sd.values()])
@@ -99,6 +100,9 @@ class CLIPCondUNet(nn.Module):
         self.up = nn.ModuleList(stages)
         self.out_norm = nn.GroupNorm(8, width)
         self.out = nn.Conv2d(width, img_ch, 3, padding=1)
+        # Tensor-core operand format.  fp16 (default) and bf16 run at the same tcgen05 rate with fp32 accumulation;
+        # fp16's 3 extra mantissa bits keep the per-step epsilon error ~8x lower (DESIGN.md "Precision").
+        self.operand_dtype = torch.float16
         self._plans: dict = {}
         self._plan_version = None
 
@@ -108,7 +112,7 @@ class CLIPCondUNet(nn.Module):
 
     def plan_for(self, batch: int, height: int, width: int) -> _Plan:
         """Returns the (cached) plan for this shape; rebuilt when parameters were replaced or modified in place."""
-        ver = self._weights_version()
+        ver = (self._weights_version(), self.operand_dtype)
         if ver != self._plan_version:
             self._plans.clear()
             self._plan_version = ver

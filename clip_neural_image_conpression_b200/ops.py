@@ -1,7 +1,8 @@
 """Thin torch-tensor wrappers over the leaf entry points of libclpk.so.
 
 torch is used for device memory and streams only; every computation happens in the CUDA kernels of csrc/.
-Layout notes: reference-facing tensors are NCHW fp32; the kernels' activations are NHWC (bf16 operands, fp32 stream).
+Layout notes: reference-facing tensors are NCHW fp32; the kernels' activations are NHWC (16-bit tensor-core operands —
+fp16 by default, bf16 selectable — and an fp32 residual stream).
 """
 from __future__ import annotations
 
@@ -10,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import CONV_3X3_S1, CONV_3X3_S2, CONVT_4X4_S2, ConvEpilogue, check, ptr, require_cuda, stream_ptr
+from ._lib import CONV_3X3_S1, CONV_3X3_S2, CONVT_4X4_S2, ConvEpilogue, check, op_code, ptr, require_cuda, stream_ptr
 
 __all__ = [
     "dequant_l2norm", "quant_encode", "quant_fit", "ddim_step", "timestep_embedding", "linear", "film_apply",
@@ -104,22 +105,22 @@ def film_apply(x_nchw: torch.Tensor, scale1p: torch.Tensor, shift: torch.Tensor)
 
 
 def groupnorm_silu(x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float = 1e-5,
-                   silu: bool = True) -> torch.Tensor:
-    """fp32 NHWC [B,H,W,C] -> bf16 NHWC GroupNorm(+SiLU)."""
+                   silu: bool = True, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """fp32 NHWC [B,H,W,C] -> 16-bit (fp16 default / bf16) NHWC GroupNorm(+SiLU) = the conv A operand."""
     require_cuda(x_nhwc, gamma, beta)
     x = _f32c(x_nhwc)
     b, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (b * c)
     lib = _lib.load()
     ws = torch.empty(int(lib.clpk_groupnorm_ws_bytes(b, hw, c, groups)), dtype=torch.uint8, device=x.device)
-    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
     check(lib.clpk_groupnorm_silu(ptr(x), ptr(_f32c(gamma)), ptr(_f32c(beta)), ptr(y), ptr(ws), b, hw, c, groups,
-                                  float(eps), int(silu), stream_ptr()), "clpk_groupnorm_silu")
+                                  float(eps), int(silu), op_code(dtype), stream_ptr()), "clpk_groupnorm_silu")
     return y
 
 
-def pack_conv_weight(w: torch.Tensor, kind: int) -> torch.Tensor:
-    """Reference-layout fp32 conv weight -> bf16 K-major GEMM layout (see include/clpk.h)."""
+def pack_conv_weight(w: torch.Tensor, kind: int, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """Reference-layout fp32 conv weight -> 16-bit K-major GEMM layout (see include/clpk.h)."""
     require_cuda(w)
     w = _f32c(w)
     if kind == CONVT_4X4_S2:
@@ -127,20 +128,20 @@ def pack_conv_weight(w: torch.Tensor, kind: int) -> torch.Tensor:
     else:
         cout, cin = w.shape[0], w.shape[1]
     lib = _lib.load()
-    n = int(lib.clpk_pack_conv_weight(None, None, kind, cin, cout, None))
+    n = int(lib.clpk_pack_conv_weight(None, None, kind, cin, cout, op_code(dtype), None))
     if n < 0:
         check(1, "clpk_pack_conv_weight")
-    out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
-    if lib.clpk_pack_conv_weight(ptr(w), ptr(out), kind, cin, cout, stream_ptr()) < 0:
+    out = torch.empty(n, dtype=dtype, device=w.device)
+    if lib.clpk_pack_conv_weight(ptr(w), ptr(out), kind, cin, cout, op_code(dtype), stream_ptr()) < 0:
         check(2, "clpk_pack_conv_weight")
     return out
 
 
-def _conv(fn_name: str, x_nhwc_bf16, w_packed, kind, cout, bias, film_scale1p, film_shift, resid, out_f32, out_bf16,
+def _conv(fn_name: str, x_nhwc_op, w_packed, kind, cout, bias, film_scale1p, film_shift, resid, out_f32, out_op,
           out_nchw):
-    require_cuda(x_nhwc_bf16, w_packed, bias)
-    assert x_nhwc_bf16.dtype == torch.bfloat16 and x_nhwc_bf16.is_contiguous()
-    b, h, w, cin = x_nhwc_bf16.shape
+    require_cuda(x_nhwc_op, w_packed, bias)
+    assert x_nhwc_op.is_contiguous() and x_nhwc_op.dtype == w_packed.dtype, "operands must share one 16-bit dtype"
+    b, h, w, cin = x_nhwc_op.shape
     ep = ConvEpilogue()
     keep = [_f32c(bias)]
     ep.bias = ptr(keep[0])
@@ -150,11 +151,12 @@ def _conv(fn_name: str, x_nhwc_bf16, w_packed, kind, cout, bias, film_scale1p, f
         ep.film_scale1p, ep.film_shift, ep.film_stride = ptr(fs), ptr(fb), fs.stride(0)
     ep.resid = ptr(resid)
     ep.out_f32 = ptr(out_f32)
-    ep.out_bf16 = ptr(out_bf16)
+    ep.out_op = ptr(out_op)
     ep.out_nchw = ptr(out_nchw)
     ep.cout_valid = cout
     fn = getattr(_lib.load(), fn_name)
-    check(fn(ptr(x_nhwc_bf16), ptr(w_packed), kind, b, h, w, cin, cout, C.byref(ep), stream_ptr()), fn_name)
+    check(fn(ptr(x_nhwc_op), ptr(w_packed), kind, b, h, w, cin, cout, op_code(x_nhwc_op.dtype), C.byref(ep), stream_ptr()),
+          fn_name)
 
 
 def _conv_out_hw(kind: int, h: int, w: int):
@@ -165,22 +167,23 @@ def _conv_out_hw(kind: int, h: int, w: int):
     return h, w
 
 
-def conv_igemm(x_nhwc_bf16: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, bias: torch.Tensor, *,
-               film_scale1p=None, film_shift=None, resid=None, want_f32=True, want_bf16=False, want_nchw=False,
+def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, bias: torch.Tensor, *,
+               film_scale1p=None, film_shift=None, resid=None, want_f32=True, want_op=False, want_nchw=False,
                impl: str = "igemm"):
-    """Implicit-GEMM conv on the tensor cores.  Returns a dict of the requested outputs."""
-    b, h, w, _ = x_nhwc_bf16.shape
+    """Implicit-GEMM conv on the tensor cores (x and w_packed in the same 16-bit dtype).  Returns a dict of the
+    requested outputs: "f32" NHWC fp32, "op" NHWC in the operand dtype, "nchw" fp32 NCHW."""
+    b, h, w, _ = x_nhwc_op.shape
     oh, ow = _conv_out_hw(kind, h, w)
-    dev = x_nhwc_bf16.device
+    dev = x_nhwc_op.device
     outs = {}
     if want_f32:
         outs["f32"] = torch.empty((b, oh, ow, cout), dtype=torch.float32, device=dev)
-    if want_bf16:
-        outs["bf16"] = torch.empty((b, oh, ow, cout), dtype=torch.bfloat16, device=dev)
+    if want_op:
+        outs["op"] = torch.empty((b, oh, ow, cout), dtype=x_nhwc_op.dtype, device=dev)
     if want_nchw:
         outs["nchw"] = torch.empty((b, cout, oh, ow), dtype=torch.float32, device=dev)
-    _conv("clpk_conv_igemm" if impl == "igemm" else "clpk_conv_direct", x_nhwc_bf16, w_packed, kind, cout, bias,
-          film_scale1p, film_shift, _f32c(resid) if resid is not None else None, outs.get("f32"), outs.get("bf16"),
+    _conv("clpk_conv_igemm" if impl == "igemm" else "clpk_conv_direct", x_nhwc_op, w_packed, kind, cout, bias,
+          film_scale1p, film_shift, _f32c(resid) if resid is not None else None, outs.get("f32"), outs.get("op"),
           outs.get("nchw"))
     return outs
 

@@ -30,6 +30,12 @@ extern "C" {
 
 #define CLPK_MAX_LEVELS 8
 
+/* 16-bit tensor-core operand formats (both run at the same tcgen05 kind::f16 rate, fp32 accumulation in TMEM).
+ * F16 (10 mantissa bits) is the plan default: with BF16 (7 bits) the per-step epsilon error of narrow UNets
+ * (base=32) exceeds the 1e-2 parity bar (measured 1.6e-2) — see DESIGN.md "Precision". */
+#define CLPK_OP_BF16 0
+#define CLPK_OP_F16 1
+
 const char* clpk_last_error(void);
 int clpk_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
@@ -80,26 +86,29 @@ int clpk_linear(const float* x_dev, const float* w_dev, const float* b_dev, cons
 int clpk_film_apply(const float* x_nchw_dev, const float* scale1p_dev, const float* shift_dev, float* y_nchw_dev,
                     int batch, int ch, int hw, void* stream);
 
-/* GroupNorm(groups, C) over NHWC fp32 input, optional SiLU, bf16 NHWC output (blocks.py:33-36,41,43; unet.py:78,105).
- * ws_dev: scratch of clpk_groupnorm_ws_bytes(batch, hw, c, groups) bytes. */
+/* GroupNorm(groups, C) over NHWC fp32 input, optional SiLU, 16-bit (op_dtype) NHWC output = conv A operand
+ * (blocks.py:33-36,41,43; unet.py:78,105).  ws_dev: scratch of clpk_groupnorm_ws_bytes(batch, hw, c, groups) bytes. */
 int64_t clpk_groupnorm_ws_bytes(int batch, int hw, int c, int groups);
-int clpk_groupnorm_silu(const float* x_nhwc_dev, const float* gamma_dev, const float* beta_dev, void* y_bf16_nhwc_dev,
-                        void* ws_dev, int batch, int hw, int c, int groups, float eps, int silu, void* stream);
+int clpk_groupnorm_silu(const float* x_nhwc_dev, const float* gamma_dev, const float* beta_dev, void* y_op_nhwc_dev,
+                        void* ws_dev, int batch, int hw, int c, int groups, float eps, int silu, int op_dtype,
+                        void* stream);
 
 /* Convolution kinds understood by the implicit-GEMM kernel. */
 #define CLPK_CONV_3X3_S1 0   /* Conv2d 3x3 stride 1 pad 1  (blocks.py:34,36; unet.py:79)   */
 #define CLPK_CONV_3X3_S2 1   /* Conv2d 3x3 stride 2 pad 1  (unet.py:63)                    */
 #define CLPK_CONVT_4X4_S2 2  /* ConvTranspose2d 4x4 stride 2 pad 1 (unet.py:75)            */
 
-/* Repack a reference-layout fp32 weight (Conv2d: [Cout,Cin,kh,kw]; ConvTranspose2d: [Cin,Cout,4,4]) into the bf16
+/* Repack a reference-layout fp32 weight (Conv2d: [Cout,Cin,kh,kw]; ConvTranspose2d: [Cin,Cout,4,4]) into the 16-bit
  * K-major GEMM layout the tcgen05 kernel reads: Conv: [Cout_pad][tap][Cin]; ConvT: [phase(4)][Cout_pad][tap(4)][Cin].
- * Returns the number of bf16 elements written (or needed, when out_dev == NULL) or <0 on error. */
-int64_t clpk_pack_conv_weight(const float* w_dev, void* out_bf16_dev, int kind, int cin, int cout, void* stream);
+ * Returns the number of 16-bit elements written (or needed, when out_dev == NULL) or <0 on error. */
+int64_t clpk_pack_conv_weight(const float* w_dev, void* out_op_dev, int kind, int cin, int cout, int op_dtype,
+                              void* stream);
 
 /* Epilogue description of one implicit-GEMM convolution launch.
  *   y = conv(x) + bias;  if film: y = y * film_scale1p[b,c] + film_shift[b,c]   (blocks.py:22-25, scale1p = 1+s)
  *   if resid: y += resid (same NHWC shape as the output; may alias out_f32)       (blocks.py:44, unet.py:104)
- *   outputs (any subset): out_f32 NHWC fp32, out_bf16 NHWC bf16, out_nchw fp32 NCHW restricted to cout_valid channels. */
+ *   outputs (any subset): out_f32 NHWC fp32, out_op NHWC in the operand format (feeds the next conv), out_nchw fp32
+ *   NCHW restricted to cout_valid channels. */
 typedef struct clpk_conv_epilogue {
   const float* bias;          /* dev [cout]                       */
   const float* film_scale1p;  /* dev, element (b,c) at [b*film_stride + c], or NULL */
@@ -107,21 +116,21 @@ typedef struct clpk_conv_epilogue {
   int64_t film_stride;
   const float* resid;         /* dev NHWC fp32 or NULL            */
   float* out_f32;             /* dev NHWC fp32 or NULL            */
-  void* out_bf16;             /* dev NHWC bf16 or NULL            */
+  void* out_op;               /* dev NHWC 16-bit (op_dtype) or NULL */
   float* out_nchw;            /* dev NCHW fp32 or NULL            */
   int cout_valid;             /* channels really present (<= cout_pad) */
 } clpk_conv_epilogue;
 
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed).
- * x: bf16 NHWC [batch, h_in, w_in, cin]; w_packed from clpk_pack_conv_weight.
+ * x: 16-bit (op_dtype) NHWC [batch, h_in, w_in, cin]; w_packed from clpk_pack_conv_weight with the same op_dtype.
  * Output spatial size: S1: (h_in, w_in); S2: (h_in/2, w_in/2); ConvT: (2*h_in, 2*w_in). */
-int clpk_conv_igemm(const void* x_bf16_nhwc_dev, const void* w_packed_dev, int kind, int batch, int h_in, int w_in,
-                    int cin, int cout, const clpk_conv_epilogue* ep, void* stream);
+int clpk_conv_igemm(const void* x_op_nhwc_dev, const void* w_packed_dev, int kind, int batch, int h_in, int w_in,
+                    int cin, int cout, int op_dtype, const clpk_conv_epilogue* ep, void* stream);
 
 /* Same contract evaluated by a plain CUDA-core kernel (one thread per output element, fp32 accumulation of the same
- * bf16 operands).  On-device cross-check for the tensor-core kernel in tests; never used by the plan. */
-int clpk_conv_direct(const void* x_bf16_nhwc_dev, const void* w_packed_dev, int kind, int batch, int h_in, int w_in,
-                     int cin, int cout, const clpk_conv_epilogue* ep, void* stream);
+ * 16-bit operands).  On-device cross-check for the tensor-core kernel in tests; never used by the plan. */
+int clpk_conv_direct(const void* x_op_nhwc_dev, const void* w_packed_dev, int kind, int batch, int h_in, int w_in,
+                     int cin, int cout, int op_dtype, const clpk_conv_epilogue* ep, void* stream);
 
 /* in_conv (unet.py:55,88): fp32 NCHW [B,cin,H,W] -> fp32 NHWC [B,H,W,cout], 3x3 s1 p1, fp32 arithmetic. */
 int clpk_conv_in(const float* x_nchw_dev, const float* w_dev /*[cout,cin,3,3]*/, const float* b_dev, float* y_nhwc_dev,
@@ -139,6 +148,7 @@ typedef struct clpk_unet_config {
   int time_dim;   /* 256 */
   int img_ch;     /* 3 */
   int groups;     /* 8 */
+  int op_dtype;   /* CLPK_OP_F16 (default) or CLPK_OP_BF16: tensor-core operand format */
 } clpk_unet_config;
 
 typedef struct clpk_plan clpk_plan;
@@ -171,6 +181,14 @@ int clpk_plan_prepare_ddim(clpk_plan* plan, int steps, const int64_t* ts_host, c
  * eps_trace_dev / x_trace_dev: NULL or [steps][...] buffers receiving every step's eps and input x (parity). */
 int clpk_ddim_sample(clpk_plan* plan, const float* z_clip_dev, float* x_dev, const float* noise_dev, uint64_t seed,
                      float* eps_trace_dev, float* x_trace_dev, void* stream);
+
+/* Measurement hooks (bench.py): eager DDIM steps with CUDA events around every launch.  ms_out6 / count_out6 are HOST
+ * arrays of 6 entries, one per kernel class: 0 ResBlock 3x3 convs (tcgen05), 1 other tcgen05 convs, 2 GroupNorm
+ * (stats + apply), 3 stem conv, 4 conditioning, 5 DDIM update.  Needs clpk_plan_prepare_ddim first. */
+int clpk_plan_profile_steps(clpk_plan* plan, int iters, float* ms_out6, int* count_out6, void* stream);
+/* Algorithmic work of one forward at the plan's batch: FLOPs of conv classes 0 and 1, fp32 elements read by GroupNorm. */
+int clpk_plan_work_breakdown(const clpk_plan* plan, double* conv_res_flops, double* conv_other_flops,
+                             double* gn_elements);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Output side: reconstruct_diffusion.py:55-56, PKG/eval/metrics.py:16-29

@@ -135,7 +135,7 @@ def scheduler_tables(timesteps: int = 1000, schedule: str = "cosine") -> Dict[st
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: int = 10000) -> torch.Tensor:
     """PKG/models/unet.py:22-39."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, device=t.device) / half)
     args = t.float().unsqueeze(1) * freqs.unsqueeze(0)
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2 == 1:
@@ -280,15 +280,15 @@ def ddim_sample(eps_fn: Callable, tables: Dict[str, torch.Tensor], z_clip: torch
         trace["x"], trace["eps"] = [], []
     for i in range(steps):
         t = ts[i]
-        t_b = torch.full((x.shape[0],), int(t.item()), dtype=torch.long)
+        t_b = torch.full((x.shape[0],), int(t.item()), dtype=torch.long, device=x.device)
         if teacher is not None:
             x = teacher[i]
         eps = eps_fn(x, z_clip, t_b)
         if trace is not None:
             trace["x"].append(x.clone())
             trace["eps"].append(eps.clone())
-        a_t = tables["alphas_cumprod"][t]
-        a_s = tables["alphas_cumprod_prev"][t] if i < steps - 1 else torch.tensor(1.0)
+        a_t = tables["alphas_cumprod"][t].to(x.device)
+        a_s = (tables["alphas_cumprod_prev"][t] if i < steps - 1 else torch.tensor(1.0)).to(x.device)
         x = ddim_update(x, eps, a_t, a_s, eta, None if noise is None else noise[i])
     if trace is not None:
         trace["x"], trace["eps"] = torch.stack(trace["x"]), torch.stack(trace["eps"])

@@ -1,0 +1,235 @@
+"""GPU parity of every leaf entry point of libclpk.so (called through the C ABI) against the oracle and the golden
+vectors of the unmodified reference.  Integer / byte work: bit exact.  Floating point: tolerance stated per test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from clip_neural_image_conpression_b200 import ops as o
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return o
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------------------ codec (bit exact)
+def test_dequant_bit_exact_and_l2norm(ops, oracle, golden):
+    g = golden("quantizer")
+    z, raw = ops.dequant_l2norm(cu(g["codes"]), cu(g["scale"]), cu(g["zero"]), l2norm=True, return_raw=True)
+    assert np.array_equal(raw.cpu().numpy(), g["decoded"])                     # bit exact (north-star)
+    # L2 normalisation: numpy's pairwise fp32 sum vs a warp-tree fp32 sum -> the norm may differ in the last ulp
+    np.testing.assert_allclose(z.cpu().numpy(), g["z_dec"], rtol=3e-7, atol=1e-9)
+    z2 = ops.dequant_l2norm(cu(g["codes"]), cu(g["scale"]), cu(g["zero"]), l2norm=False)
+    assert np.array_equal(z2.cpu().numpy(), g["decoded"])
+
+
+def test_dequant_edge_cases(ops, oracle):
+    rng = np.random.default_rng(0)
+    for b, d in ((1, 1), (3, 7), (5, 768), (2, 4099)):
+        q = rng.integers(0, 256, (b, d), dtype=np.uint8)
+        q[0, :] = 0
+        scale = rng.random(d, dtype=np.float32) * 1e-2 + 1e-8
+        zero = (rng.standard_normal(d) * 0.1).astype(np.float32)
+        if b > 1:
+            zero_row = np.zeros(d, np.float32)  # a row that dequantises to exactly 0 -> max(norm, 1e-9) guard
+            raw = ops.dequant_l2norm(cu(q[:1]), cu(scale), cu(zero_row), l2norm=True)
+            assert torch.all(raw == 0)
+        raw = ops.dequant_l2norm(cu(q), cu(scale), cu(zero), l2norm=False).cpu().numpy()
+        assert np.array_equal(raw, oracle.dequant(q, scale, zero))
+    empty = ops.dequant_l2norm(torch.zeros((0, 16), dtype=torch.uint8, device="cuda"), cu(np.ones(16, np.float32)),
+                               cu(np.zeros(16, np.float32)))
+    assert empty.shape == (0, 16)
+
+
+def test_quantizer_fit_encode_bit_exact(ops, golden):
+    g = golden("quantizer")
+    scale, zero = ops.quant_fit(cu(g["Z"]))
+    assert np.array_equal(scale.cpu().numpy(), g["scale"]) and np.array_equal(zero.cpu().numpy(), g["zero"])
+    q = ops.quant_encode(cu(g["Z"]), scale, zero)
+    assert np.array_equal(q.cpu().numpy(), g["codes"])
+
+
+def test_quantizer_class_round_trip(golden):
+    from clip_neural_image_conpression_b200.codecs import PerChannelAffineQuantizer
+    g = golden("quantizer")
+    qz = PerChannelAffineQuantizer(8).fit(torch.from_numpy(g["Z"]))
+    codes = qz.encode(torch.from_numpy(g["Z"]))
+    assert codes.dtype == np.uint8 and np.array_equal(codes, g["codes"])
+    assert np.array_equal(qz.decode(codes), g["decoded"])
+    # tie cases: values exactly half way between two codes must round half to even like torch.round
+    qz.scale, qz.zero = torch.full((4,), 2.0), torch.zeros(4)
+    assert qz.encode(torch.tensor([1.0, 3.0, 5.0, 600.0])).tolist() == [0, 2, 2, 255]
+
+
+# ------------------------------------------------------------------------------------------------ DDIM update
+def test_ddim_step_bit_exact(ops, oracle):
+    tabs = oracle.scheduler_tables(1000, "cosine")
+    g = torch.Generator().manual_seed(0)
+    x, eps, nz = (torch.randn(2, 3, 33, 31, generator=g) for _ in range(3))  # odd size: exercises the scalar tail
+    from clip_neural_image_conpression_b200.diffusion.ddim import ddim_coefficients, ddim_timesteps
+    from clip_neural_image_conpression_b200.diffusion import NoiseScheduler
+    sch = NoiseScheduler(1000, "cosine", "cpu")
+    for eta in (0.0, 1e-3, 1.0):
+        ts = ddim_timesteps(1000, 10)
+        coef = ddim_coefficients(sch, ts, eta)
+        for i in (0, 1, 5, 9):
+            a_t = tabs["alphas_cumprod"][ts[i]]
+            a_s = tabs["alphas_cumprod_prev"][ts[i]] if i < 9 else torch.tensor(1.0)
+            ref = oracle.ddim_update(x, eps, a_t, a_s, eta, nz)
+            got = ops.ddim_step(x.cuda(), eps.cuda(), coef[i].tolist(), nz.cuda() if eta > 0 else None).cpu()
+            assert torch.equal(torch.isnan(got), torch.isnan(ref)), (eta, i)      # NaN pattern (eta=1: all NaN early)
+            m = ~torch.isnan(ref)
+            assert torch.equal(got[m], ref[m]), (eta, i)                           # bit exact elsewhere
+
+
+# ------------------------------------------------------------------------------------------------ small fp kernels
+def test_timestep_embedding(ops, golden):
+    g = golden("timestep_embedding")
+    for dim, key in ((256, "emb256"), (64, "emb64")):
+        e = ops.timestep_embedding(cu(g["t"]), dim).cpu().numpy()
+        # fp32 expf / sinf / cosf of CUDA vs the CPU's vectorised libm: a 1-ulp frequency difference is amplified by
+        # t <= 999, hence the absolute tolerance (values are in [-1, 1])
+        np.testing.assert_allclose(e, g[key], rtol=0, atol=2e-4)
+
+
+def test_linear(ops):
+    g = torch.Generator().manual_seed(1)
+    for m, n, k, act in ((1, 256, 512, 1), (8, 1024, 256, 1), (50, 256, 1024, 0), (13, 7680, 256, 0)):
+        x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** 0.5, torch.randn(n, generator=g)
+        ref = F.linear(x.double(), w.double(), b.double())
+        ref = F.silu(ref) if act else ref
+        y = ops.linear(x.cuda(), w.cuda(), b.cuda(), act=act).cpu()
+        np.testing.assert_allclose(y.numpy(), ref.float().numpy(), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_groupnorm_silu(ops, dtype):
+    g = torch.Generator().manual_seed(2)
+    tol = 1.5e-3 if dtype == torch.float16 else 6e-3   # half an ulp of the output format + fast-exp noise
+    for b, h, w, c, silu in ((2, 16, 16, 32, True), (3, 32, 32, 128, True), (1, 8, 8, 512, False), (2, 8, 8, 192, True),
+                             (1, 4, 4, 3072, True), (2, 64, 64, 64, True)):
+        x = (torch.randn(b, h, w, c, generator=g) * 1.7 + 0.4)
+        gamma, beta = 1 + 0.1 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)
+        ref = F.group_norm(x.permute(0, 3, 1, 2).double(), 8, gamma.double(), beta.double(), 1e-5)
+        ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
+        y = ops.groupnorm_silu(x.cuda(), gamma.cuda(), beta.cuda(), 8, 1e-5, silu, dtype=dtype).cpu()
+        assert y.dtype == dtype
+        err = (y.double() - ref).abs()
+        assert float((err / (ref.abs() + 1e-2)).max()) < tol, (b, h, w, c)
+        y2 = ops.groupnorm_silu(x.cuda(), gamma.cuda(), beta.cuda(), 8, 1e-5, silu, dtype=dtype).cpu()
+        assert torch.equal(y, y2)  # deterministic (no float atomics)
+
+
+def test_conv_in(ops):
+    g = torch.Generator().manual_seed(3)
+    for b, h, w, cout in ((2, 40, 24, 128), (1, 16, 16, 32), (1, 8, 8, 192)):
+        x, wt, bias = torch.randn(b, 3, h, w, generator=g), torch.randn(cout, 3, 3, 3, generator=g) / 5, torch.randn(cout, generator=g)
+        ref = F.conv2d(x.double(), wt.double(), bias.double(), padding=1).permute(0, 2, 3, 1).float()
+        y = ops.conv_in(x.cuda(), wt.cuda(), bias.cuda()).cpu()
+        np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core convs
+CONV_CASES = [
+    # kind, B, H, W, Cin, Cout, film, resid
+    (0, 1, 8, 16, 64, 64, False, False),       # one M tile
+    (0, 2, 32, 32, 128, 128, True, False),     # conv1 + FiLM epilogue
+    (0, 2, 32, 32, 128, 128, False, True),     # conv2 + residual epilogue
+    (0, 1, 16, 16, 32, 32, False, False),      # BLOCK_K = 32 (64-byte swizzle)
+    (0, 1, 8, 8, 512, 512, False, True),       # two N tiles, 72 k-blocks, half-filled M tile
+    (0, 1, 4, 256, 128, 128, False, False),    # W > 128
+    (0, 1, 24, 24, 64, 64, False, False),      # ragged boxes
+    (0, 2, 16, 16, 128, 3, False, False),      # `out` conv: N padded to 16, NCHW output
+    (0, 4, 64, 64, 256, 256, True, False),     # several tiles per CTA: smem ring wrap + TMEM double buffering
+    (0, 1, 16, 16, 192, 192, False, True),     # wide config channel count (N = 192)
+    (1, 1, 32, 32, 64, 128, False, False),     # stride 2
+    (1, 2, 16, 16, 128, 256, False, False),
+    (1, 1, 16, 16, 32, 64, False, False),
+    (2, 1, 8, 8, 128, 64, False, True),        # transposed conv + skip add
+    (2, 2, 16, 16, 256, 128, False, True),
+    (2, 1, 8, 8, 64, 32, False, False),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("kind,b,h,w,cin,cout,film,resid", CONV_CASES)
+def test_conv_igemm(ops, kind, b, h, w, cin, cout, film, resid, dtype):
+    g = torch.Generator().manual_seed(kind * 1000 + cin + cout + h)
+    xb = torch.randn(b, h, w, cin, generator=g).to(dtype).cuda()
+    if kind == 2:
+        wt = (torch.randn(cin, cout, 4, 4, generator=g) / (cin * 4) ** 0.5).cuda()
+    else:
+        wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    wp = ops.pack_conv_weight(wt, kind, dtype)
+    xr, wr = xb.float().permute(0, 3, 1, 2).double(), wt.to(dtype).double()
+    if kind == 0:
+        ref = F.conv2d(xr, wr, bias.double(), padding=1)
+    elif kind == 1:
+        ref = F.conv2d(xr, wr, bias.double(), stride=2, padding=1)
+    else:
+        ref = F.conv_transpose2d(xr, wr, bias.double(), stride=2, padding=1)
+    kw = {}
+    if film:
+        sc, sh = (1 + 0.3 * torch.randn(b, cout, generator=g)).cuda(), torch.randn(b, cout, generator=g).cuda()
+        kw.update(film_scale1p=sc, film_shift=sh)
+        ref = ref * sc.double()[:, :, None, None] + sh.double()[:, :, None, None]
+    if resid:
+        r = torch.randn(b, ref.shape[2], ref.shape[3], cout, generator=g).cuda()
+        kw["resid"] = r
+        ref = ref + r.permute(0, 3, 1, 2).double()
+    nchw = cout % 16 != 0
+    o = ops.conv_igemm(xb, wp, kind, cout, bias, want_f32=not nchw, want_op=not nchw, want_nchw=nchw, **kw)
+    d = ops.conv_direct(xb, wp, kind, cout, bias, want_f32=not nchw, want_op=False, want_nchw=nchw, **kw)
+    y = o["nchw"] if nchw else o["f32"].permute(0, 3, 1, 2)
+    yd = d["nchw"] if nchw else d["f32"].permute(0, 3, 1, 2)
+    scale = float(ref.abs().max())
+    # identical 16-bit operands, fp32 accumulation: only the summation order differs from the fp64 reference
+    assert float((y.double() - ref).abs().max()) < 1e-4 * max(scale, 1.0)
+    assert float((y - yd).abs().max()) < 1e-4 * max(scale, 1.0)
+    if not nchw:
+        assert o["op"].dtype == dtype
+        half_ulp = 2.0 ** -11 if dtype == torch.float16 else 2.0 ** -8
+        assert float((o["op"].double().permute(0, 3, 1, 2) - ref).abs().max()) < 1.2 * half_ulp * max(scale, 1.0)
+
+
+# ------------------------------------------------------------------------------------------------ blocks, post-process
+def test_film_and_resblock_match_reference(ops, golden):
+    from clip_neural_image_conpression_b200.models import FiLM, ResBlock
+    g = golden("unet_forward")
+    film = FiLM(16, 32)
+    film.load_state_dict({k[len("film.sd."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("film.sd.")})
+    y = film.cuda()(cu(g["film.x"]), cu(g["film.h"]))
+    assert y.shape == (2, 16, 8, 8)                                        # the reference's own test (shape)
+    np.testing.assert_allclose(y.cpu().numpy(), g["film.y"], rtol=1e-5, atol=1e-5)
+    rb = ResBlock(32, 256)
+    rb.load_state_dict({k[len("rb.sd."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("rb.sd.")})
+    y = rb.cuda()(cu(g["rb.x"]), cu(g["rb.h"])).cpu()
+    ref = torch.from_numpy(g["rb.y"])
+    # fp16 conv operands, fp32 accumulation/stream: relative L2 far under the 1e-2 epsilon bar
+    assert float(torch.linalg.norm(y - ref) / torch.linalg.norm(ref)) < 1e-3
+    rb.operand_dtype = torch.bfloat16
+    yb = rb(cu(g["rb.x"]), cu(g["rb.h"])).cpu()
+    assert float(torch.linalg.norm(yb - ref) / torch.linalg.norm(ref)) < 5e-3
+
+
+def test_to_uint8_and_psnr(ops, oracle, golden):
+    g = golden("metrics")
+    u8 = ops.to_uint8_hwc(cu(g["a"])).cpu().numpy()
+    assert np.array_equal(u8, g["u8"])                                      # bit exact (truncation)
+    from clip_neural_image_conpression_b200.eval.metrics import psnr, psnr_batch
+    got = psnr_batch(cu(g["a"]), cu(g["b"]))
+    # the reference averages squares in float32 (numpy pairwise sum); ours is an exact integer sum -> ~1e-6 dB
+    np.testing.assert_allclose(got, g["psnr"][:3], rtol=0, atol=1e-4)
+    assert psnr(g["a"][0], g["a"][0]) == float("inf")
+    sq = ops.psnr_sqerr_u8(cu(g["a"]), cu(g["b"])).cpu().numpy()
+    ref = ((oracle.metric_uint8(g["a"]).astype(np.int64) - oracle.metric_uint8(g["b"]).astype(np.int64)) ** 2).reshape(3, -1).sum(1)
+    assert np.array_equal(sq, ref)                                           # integer work: exact

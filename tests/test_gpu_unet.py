@@ -1,0 +1,193 @@
+"""GPU parity of the plan-level path (whole CLIPCondUNet forward, DDIM loop, CUDA graph) against the golden outputs of
+the unmodified reference and the oracle.  Tolerances are the north-star's: per-step epsilon <= 1e-2 relative L2
+(teacher forced), final reconstruction >= 40 dB PSNR vs the reference's fp32 output (contractive weights)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(z_dim=512, base=32, ch_mult=(1, 2))
+MID = dict(z_dim=512, base=64, ch_mult=(1, 2))
+EPS_TOL = 1e-2
+PSNR_BAR = 40.0
+
+
+def make_net(oracle, cfg, seed, out_gain=1.0):
+    from clip_neural_image_conpression_b200.models import CLIPCondUNet
+    net = CLIPCondUNet(z_dim=cfg["z_dim"], base=cfg["base"], ch_mult=cfg["ch_mult"])
+    sd = oracle.make_state_dict(cfg["z_dim"], cfg["base"], cfg["ch_mult"], seed=seed, out_gain=out_gain)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().eval(), sd
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def test_reference_shape_test():
+    """Mirror of the reference's tests/test_unet.py:7-13 on the CUDA path."""
+    from clip_neural_image_conpression_b200.models import CLIPCondUNet
+    net = CLIPCondUNet(z_dim=512, base=64, ch_mult=(1, 2), img_ch=3).cuda()
+    x, z, t = torch.randn(2, 3, 64, 64).cuda(), torch.randn(2, 512).cuda(), torch.randint(0, 1000, (2,)).cuda()
+    y = net(x, z, t)
+    assert y.shape == x.shape and torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("name,cfg", [("tiny", TINY), ("mid", MID)])
+def test_unet_forward_vs_reference_golden(oracle, golden, name, cfg):
+    g = golden("unet_forward")
+    net, _ = make_net(oracle, cfg, seed=11)
+    eps = net(cu(g[f"{name}.x"]), cu(g[f"{name}.z"]), cu(g[f"{name}.t"])).cpu()
+    ref = torch.from_numpy(g[f"{name}.eps"])
+    for b in range(ref.shape[0]):  # per sample: t = 999 and t = 37
+        assert oracle.rel_l2(eps[b], ref[b]) < EPS_TOL, (name, b, oracle.rel_l2(eps[b], ref[b]))
+
+
+def test_bf16_operand_variant(oracle, golden):
+    """bf16 operands (selectable) meet the epsilon bar on >= 64-channel networks; fp16 (default) is ~8x tighter."""
+    g = golden("unet_forward")
+    net, _ = make_net(oracle, MID, seed=11)
+    ref = torch.from_numpy(g["mid.eps"])
+    e16 = oracle.rel_l2(net(cu(g["mid.x"]), cu(g["mid.z"]), cu(g["mid.t"])).cpu(), ref)
+    net.operand_dtype = torch.bfloat16
+    eb = oracle.rel_l2(net(cu(g["mid.x"]), cu(g["mid.z"]), cu(g["mid.t"])).cpu(), ref)
+    assert e16 < 2e-3 and eb < EPS_TOL and e16 < eb, (e16, eb)
+
+
+def test_unet_forward_is_deterministic_and_batch_independent(oracle):
+    net, _ = make_net(oracle, TINY, seed=3)
+    g = torch.Generator().manual_seed(1)
+    x, z = torch.randn(4, 3, 32, 32, generator=g).cuda(), torch.randn(4, 512, generator=g).cuda()
+    t = torch.tensor([999, 500, 20, 0]).cuda()
+    a, b = net(x, z, t), net(x, z, t)
+    assert torch.equal(a, b)
+    solo = torch.cat([net(x[i:i + 1], z[i:i + 1], t[i:i + 1]) for i in range(4)])
+    # images never interact (GroupNorm / FiLM are per sample); only the GN partial-sum split depends on the batch
+    assert oracle.rel_l2(solo, a) < 1e-5
+
+
+def test_state_dict_reload_rebuilds_plan(oracle):
+    net, sd = make_net(oracle, TINY, seed=3)
+    g = torch.Generator().manual_seed(1)
+    x, z, t = torch.randn(1, 3, 32, 32, generator=g).cuda(), torch.randn(1, 512, generator=g).cuda(), torch.tensor([7]).cuda()
+    a = net(x, z, t)
+    with torch.no_grad():
+        net.out.weight.mul_(0.5)
+        net.out.bias.mul_(0.5)
+    b = net(x, z, t)
+    assert oracle.rel_l2(b, 0.5 * a) < 1e-5
+
+
+def _sampler(eta):
+    from clip_neural_image_conpression_b200.diffusion import DDIMSampler, NoiseScheduler
+    return DDIMSampler(NoiseScheduler(1000, "cosine", "cuda"), eta=eta)
+
+
+def test_scheduler_tables_on_device_bit_exact(golden):
+    from clip_neural_image_conpression_b200.diffusion import NoiseScheduler
+    g = golden("scheduler")
+    for sch in ("cosine", "linear"):
+        s = NoiseScheduler(1000, sch, "cuda")
+        for k in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "posterior_variance"):
+            assert getattr(s, k).is_cuda and np.array_equal(getattr(s, k).cpu().numpy(), g[f"{sch}.{k}"])
+
+
+def test_ddim_config1_vs_reference_golden(oracle, golden):
+    """BASELINE configs[0]: base=32 ch_mult=(1,2) 64 px, batch 2, DDIM 10 steps — closed loop vs the reference."""
+    g = golden("ddim")
+    z, x_T = cu(g["z"]), cu(g["x_T"])
+    net, _ = make_net(oracle, TINY, seed=0, out_gain=0.1)
+    x = _sampler(0.0).sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T).cpu()
+    assert oracle.psnr_float(x, torch.from_numpy(g["pg.eta0.x"])) >= PSNR_BAR
+    x50 = _sampler(0.0).sample(net, z, (2, 3, 64, 64), steps=50, x_T=x_T).cpu()
+    assert oracle.psnr_float(x50, torch.from_numpy(g["pg.eta0.steps50.x"])) >= PSNR_BAR
+
+
+def test_ddim_stochastic_path_and_nan_pattern(oracle, golden):
+    g = golden("ddim")
+    z, x_T = cu(g["z"]), cu(g["x_T"])
+    net, _ = make_net(oracle, TINY, seed=0, out_gain=0.1)
+    torch.manual_seed(7)
+    noise = torch.stack([torch.randn(2, 3, 64, 64) for _ in range(10)]).cuda()  # the reference's global-RNG draws
+    x = _sampler(1e-3).sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T, noise=noise).cpu()
+    assert oracle.psnr_float(x, torch.from_numpy(g["pg.eta1e-3.x"])) >= PSNR_BAR
+    # eta = 1.0: the reference's sqrt(a_s - sigma^2) is NaN from step 0 on -> all-NaN output
+    xn = _sampler(1.0).sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T, noise=noise)
+    assert float(torch.isnan(xn).float().mean()) == float(g["pg.eta1.nan_fraction"]) == 1.0
+    # in-kernel Philox noise: finite, seed-reproducible, seed-sensitive
+    s = _sampler(1e-3)
+    a = s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T)
+    b = s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T)
+    s.seed = 1
+    c = s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T)
+    assert torch.isfinite(a).all() and torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_ddim_teacher_forced_epsilon(oracle, golden):
+    """Open-loop per-step epsilon parity on plain (undamped) random weights: the oracle's own x_t trajectory is fed to
+    the CUDA UNet at every sampled step; relative L2 of eps must stay under 1e-2 (north-star)."""
+    g = golden("ddim")
+    z, x_T = torch.from_numpy(g["z"]), torch.from_numpy(g["x_T"])
+    net, sd = make_net(oracle, TINY, seed=0)
+    tabs = oracle.scheduler_tables(1000, "cosine")
+    tr = {}
+    with torch.no_grad():
+        oracle.ddim_sample(lambda x, zc, t: oracle.unet_forward(sd, (1, 2), x, zc, t), tabs, z, x_T, steps=10, trace=tr)
+    ts = oracle.ddim_timesteps(1000, 10)
+    worst = 0.0
+    for i in range(10):
+        t_b = torch.full((2,), int(ts[i]), dtype=torch.long).cuda()
+        eps = net(tr["x"][i].cuda(), z.cuda(), t_b).cpu()
+        worst = max(worst, oracle.rel_l2(eps, tr["eps"][i]))
+    assert worst < EPS_TOL, worst
+
+
+def test_graph_replay_equals_eager_launches_and_trace(oracle, golden):
+    g = golden("ddim")
+    z, x_T = cu(g["z"]), cu(g["x_T"])
+    net, _ = make_net(oracle, TINY, seed=0, out_gain=0.1)
+    s = _sampler(0.0)
+    tr = {}
+    a = s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T, trace=tr)
+    s.use_graph = False
+    b = s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T)
+    assert torch.equal(a, b)                                   # same kernels, same order -> bitwise identical
+    assert tr["x"].shape == (10, 2, 3, 64, 64) and torch.equal(tr["x"][0], x_T)
+    # the traced eps of step 0 is what forward() returns for x_T at t = 999
+    e0 = net(x_T, z, torch.full((2,), 999, device="cuda"))
+    assert oracle.rel_l2(tr["eps"][0], e0) < 1e-5
+    # generic-callable path (any eps model) walks the same trajectory
+    c = s.sample(lambda x, zc, t: net(x, zc, t), z, (2, 3, 64, 64), steps=10, x_T=x_T)
+    assert oracle.psnr_float(c.cpu(), a.cpu()) > 60.0
+
+
+def test_default_architecture_full_size_properties(oracle):
+    """BASELINE configs[1] shape (base=128, ch_mult=(1,2,2), 256 px, batch 8): too slow for the CPU oracle, so the
+    full-size run is checked through size-independent properties + the SAME oracle code executed on the GPU in fp32."""
+    cfg = dict(z_dim=512, base=128, ch_mult=(1, 2, 2))
+    net, sd = make_net(oracle, cfg, seed=21, out_gain=0.1)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(8, 3, 256, 256, generator=g).cuda()
+    z = torch.nn.functional.normalize(torch.randn(8, 512, generator=g), dim=-1).cuda()
+    t = torch.tensor([999, 978, 795, 489, 250, 40, 20, 0]).cuda()
+    eps = net(x, z, t)
+    assert torch.isfinite(eps).all()
+    assert torch.equal(eps, net(x, z, t))                                             # idempotent / deterministic
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4]).cuda()
+    assert oracle.rel_l2(net(x[perm], z[perm], t[perm]), eps[perm]) < 1e-5            # equivariant to batch order
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd_cu = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = oracle.unet_forward(sd_cu, cfg["ch_mult"], x, z, t)                     # oracle code, fp32, on the GPU
+    for b in range(8):
+        assert oracle.rel_l2(eps[b], ref[b]) < EPS_TOL, (b, oracle.rel_l2(eps[b], ref[b]))
+    # 10-step closed loop at full size against the same oracle loop on the GPU
+    s = _sampler(0.0)
+    x_T = torch.randn(8, 3, 256, 256, generator=g).cuda()
+    out = s.sample(net, z, (8, 3, 256, 256), steps=10, x_T=x_T)
+    tabs = oracle.scheduler_tables(1000, "cosine")
+    with torch.no_grad():
+        ref = oracle.ddim_sample(lambda xx, zc, tt: oracle.unet_forward(sd_cu, cfg["ch_mult"], xx, zc, tt), tabs, z, x_T, steps=10)
+    assert oracle.psnr_float(out, ref) >= PSNR_BAR

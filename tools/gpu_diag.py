@@ -55,18 +55,18 @@ def bf16r(x):
 
 
 @guarded
-def conv_case(kind, b, h, w, cin, cout, film=False, resid=False, seed=0):
+def conv_case(kind, b, h, w, cin, cout, film=False, resid=False, seed=0, dtype=torch.float16):
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = torch.randn(b, h, w, cin, generator=g).to(dev)
-    xb = x.to(torch.bfloat16).contiguous()
+    xb = x.to(dtype).contiguous()
     if kind == ops.CONVT_4X4_S2:
         wt = (torch.randn(cin, cout, 4, 4, generator=g) / (cin * 4) ** 0.5).to(dev)
     else:
         wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev)
     bias = torch.randn(cout, generator=g).to(dev)
-    wp = ops.pack_conv_weight(wt, kind)
+    wp = ops.pack_conv_weight(wt, kind, dtype)
     xr = xb.float().permute(0, 3, 1, 2).double()
-    wr = bf16r(wt).double()
+    wr = wt.to(dtype).double()
     if kind == ops.CONV_3X3_S1:
         ref = F.conv2d(xr, wr, bias.double(), padding=1)
     elif kind == ops.CONV_3X3_S2:
@@ -87,7 +87,7 @@ def conv_case(kind, b, h, w, cin, cout, film=False, resid=False, seed=0):
     nchw = cout % 16 != 0
     outs = {}
     for impl in ("direct", "igemm"):
-        o = ops.conv_igemm(xb, wp, kind, cout, bias, want_f32=not nchw, want_bf16=not nchw, want_nchw=nchw, impl=impl, **kw)
+        o = ops.conv_igemm(xb, wp, kind, cout, bias, want_f32=not nchw, want_op=not nchw, want_nchw=nchw, impl=impl, **kw)
         torch.cuda.synchronize()
         outs[impl] = o
         y = o["nchw"].permute(0, 2, 3, 1) if nchw else o["f32"]
@@ -96,7 +96,7 @@ def conv_case(kind, b, h, w, cin, cout, film=False, resid=False, seed=0):
         ok = err <= 2e-3 * max(scale, 1.0)
         extra = ""
         if not nchw:
-            eb = (o["bf16"].float() - ref_nhwc).abs().max().item()
+            eb = (o["op"].float() - ref_nhwc).abs().max().item()
             extra = f" bf16copy_err={eb:.3e}"
             ok = ok and eb <= 1.6e-2 * max(scale, 1.0)
         if not ok and impl == "igemm":
