@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
 
 namespace clpk {
 
@@ -32,6 +33,7 @@ struct __align__(8) PipeBarriers {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full[4];  // residual chunk landed in staging slot s
   uint32_t tmem_base;
 };
 
@@ -55,9 +57,18 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
   return c;
 }
 
+// per-tile epilogue vectors: y = acc * mul[n] + add[n]   (mul = 1 + FiLM scale or 1, add = bias * mul + FiLM shift)
+struct EpiVectors {
+  float mul[256];
+  float add[256];
+};
+
+constexpr int kStagingBytes = kTileM * 128;  // one staging buffer: 128 rows x 32 fp32 columns, 128B-swizzled
+
 template <int BLOCK_K>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ OutMaps maps_out, const __grid_constant__ OutMaps maps_res,
                   const __grid_constant__ IgemmParams p) {
   constexpr int kSwizzle = BLOCK_K * 2;           // bytes per smem row
   constexpr int kABytes = kTileM * BLOCK_K * 2;   // one A stage
@@ -69,7 +80,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int b_bytes = p.block_n * BLOCK_K * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.stages * kABytes;
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem_b + (size_t)p.stages * b_bytes);
+  uint8_t* smem_s = smem_b + (size_t)p.stages * b_bytes;  // staging buffers (1024-aligned: all sizes are multiples)
+  EpiVectors* vec = reinterpret_cast<EpiVectors*>(smem_s + (size_t)p.n_staging * kStagingBytes);
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(vec + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,6 +99,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(&bars->tmem_full[s], 1);
       mbar_init(&bars->tmem_empty[s], 4);  // one arrive per epilogue warp
     }
+    for (int s = 0; s < 4; ++s) mbar_init(&bars->res_full[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -107,14 +121,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         const int w_row = tc.phase * p.cout_pad + tc.n0;
+        if (p.ep.resid && p.n_staging > 0) {
+          // the epilogue will add this residual tile: pull it into L2 while the MMAs run
+          for (int c = 0; c < p.block_n; c += 32)
+            tma_prefetch_5d(&maps_res.m[tc.phase], tc.n0 + c, tc.w0, 0, tc.h0, tc.b);
+        }
         int tap = 0, kc = 0;
         for (int kb = 0; kb < k_blocks; ++kb) {
           const int ti = tc.phase * p.taps + tap;
           mbar_wait(&bars->empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
-          tma_load_5d(smem_a + (size_t)stage * kABytes, &map_a, &bars->full[stage], p.tap_x[ti] + kc * BLOCK_K,
-                      tc.w0 + p.tap_dw[ti], p.tap_p[ti], tc.h0 + p.tap_dh[ti], tc.b);
-          tma_load_2d(smem_b + (size_t)stage * b_bytes, &map_w, &bars->full[stage], kb * BLOCK_K, w_row);
+          uint32_t tx = tx_bytes;
+          if (p.dbg & 4) tx -= rows * BLOCK_K * 2;
+          if (p.dbg & 8) tx -= (uint32_t)b_bytes;
+          mbar_arrive_expect_tx(&bars->full[stage], tx);
+          if (!(p.dbg & 4))
+            tma_load_5d(smem_a + (size_t)stage * kABytes, &map_a, &bars->full[stage], p.tap_x[ti] + kc * BLOCK_K,
+                        tc.w0 + p.tap_dw[ti], p.tap_p[ti], tc.h0 + p.tap_dh[ti], tc.b);
+          if (!(p.dbg & 8))
+            tma_load_2d(smem_b + (size_t)stage * b_bytes, &map_w, &bars->full[stage], kb * BLOCK_K, w_row);
           if (++kc == p.kpt) { kc = 0; ++tap; }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -140,7 +164,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const uint64_t bdesc = make_kmajor_desc<kSwizzle>(smem_u32(smem_b + (size_t)stage * b_bytes));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
+            if (p.dbg & 2) break;
+            // advance 16 elements = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
             umma_f16kind(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
           }
           umma_commit(&bars->empty[stage]);  // smem slot reusable once these MMAs retire
@@ -157,7 +182,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int wl = row - hl * p.wbox;
     const clpk_conv_epilogue& ep = p.ep;
     const int ldc = ep.cout_valid;
+    const int etid = threadIdx.x - 64;       // 0..127 among the epilogue threads
+    const bool leader = (etid == 0);
+    const bool f16 = p.op_f16 != 0;
     int it = 0;
+    uint32_t gchunk = 0;                     // running chunk counter (selects the staging buffer)
+    int cached_key = -1;
+    // Residual chunks are TMA-loaded straight into the staging slot that will later be stored from (read-modify-write in
+    // place).  The leader keeps `res_ahead` chunks in flight; (ld_tile, ld_c, ld_g) is its load cursor.
+    const bool res_tma = (p.n_staging > 0) && (ep.resid != nullptr);
+    const uint32_t res_bytes = (uint32_t)(p.wbox * p.hbox) * 128u;
+    int ld_tile = blockIdx.x, ld_c = 0;
+    uint32_t ld_g = 0;
+    auto issue_res_load = [&]() {
+      if (ld_tile >= p.num_tiles) return;
+      const TileCoord lc = decode_tile(p, ld_tile);
+      const uint32_t slot = ld_g % (uint32_t)p.n_staging;
+      mbar_arrive_expect_tx(&bars->res_full[slot], res_bytes);
+      tma_load_5d(smem_s + (size_t)slot * kStagingBytes, &maps_res.m[lc.phase], &bars->res_full[slot], lc.n0 + ld_c, lc.w0, 0,
+                  lc.h0, lc.b);
+      ++ld_g;
+      ld_c += 32;
+      if (ld_c >= p.block_n) { ld_c = 0; ld_tile += gridDim.x; }
+    };
+    if (res_tma && leader && !(p.dbg & 1))
+      for (int i = 0; i < p.res_ahead; ++i) issue_res_load();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -166,72 +215,104 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const bool valid = (hl < p.hbox) && (h < p.grid_h) && (w < p.grid_w);
       const int oh = h * p.out_scale + (tc.phase >> 1), ow = w * p.out_scale + (tc.phase & 1);
       const long long opix = ((long long)tc.b * p.out_h + oh) * p.out_w + ow;
-      mbar_wait(&bars->tmem_full[as], aphase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.block_n);
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t r[16];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores of the last chunk
-        tmem_ld16(taddr + (uint32_t)c, r);
-        tmem_ld_wait();
-        const int n = tc.n0 + c;
-        if (valid && n < ldc) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (ldc - n >= 16) {
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n) + j4);
-              v[4 * j4 + 0] += bv.x; v[4 * j4 + 1] += bv.y; v[4 * j4 + 2] += bv.z; v[4 * j4 + 3] += bv.w;
-            }
+
+      if (p.n_staging > 0) {
+        // ------------------------------------------------ staged path: TMEM -> regs -> swizzled smem -> TMA store
+        const int key = tc.b * 4096 + tc.n0;
+        if (key != cached_key) {  // (image, channel-tile) changed: refresh the folded bias / FiLM vectors
+          named_bar_sync(1, 128);
+          for (int n = etid; n < p.block_n; n += 128) {
+            float mul = 1.0f, add = __ldg(ep.bias + tc.n0 + n);
             if (ep.film_scale1p) {
-              const float* fs = ep.film_scale1p + (long long)tc.b * ep.film_stride + n;
-              const float* fb = ep.film_shift + (long long)tc.b * ep.film_stride + n;
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 s = __ldg(reinterpret_cast<const float4*>(fs) + j4);
-                const float4 t = __ldg(reinterpret_cast<const float4*>(fb) + j4);
-                v[4 * j4 + 0] = fmaf(v[4 * j4 + 0], s.x, t.x); v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], s.y, t.y);
-                v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], s.z, t.z); v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], s.w, t.w);
-              }
+              mul = __ldg(ep.film_scale1p + (long long)tc.b * ep.film_stride + tc.n0 + n);
+              add = fmaf(add, mul, __ldg(ep.film_shift + (long long)tc.b * ep.film_stride + tc.n0 + n));
             }
-            if (ep.resid) {
-              const float4* rp = reinterpret_cast<const float4*>(ep.resid + opix * ldc + n);
+            vec->mul[n] = mul;
+            vec->add[n] = add;
+          }
+          named_bar_sync(1, 128);
+          cached_key = key;
+        }
+        mbar_wait(&bars->tmem_full[as], aphase);
+        tc_fence_after();
+        for (int c = 0; c < p.block_n; c += 32, ++gchunk) {
+          const uint32_t slot = gchunk % (uint32_t)p.n_staging;
+          uint8_t* sbuf = smem_s + (size_t)slot * kStagingBytes;
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+          tmem_ld16(taddr + (uint32_t)c + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+          tmem_ld_wait();
+          if (!(p.dbg & 1)) {
+            float v[32];
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 q = rp[j4];
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 m4 = *reinterpret_cast<const float4*>(&vec->mul[c + 4 * j4]);  // smem broadcast
+              const float4 a4 = *reinterpret_cast<const float4*>(&vec->add[c + 4 * j4]);
+              v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), m4.x, a4.x);
+              v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), m4.y, a4.y);
+              v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), m4.z, a4.z);
+              v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), m4.w, a4.w);
+            }
+            // staging row = tile row; 16-byte chunk j4 lives at chunk (j4 ^ (row & 7)) — the 128B TMA swizzle
+            uint8_t* srow = sbuf + row * 128;
+            if (res_tma) {
+              mbar_wait(&bars->res_full[slot], (gchunk / (uint32_t)p.n_staging) & 1u);  // residual chunk has landed
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 q = *reinterpret_cast<const float4*>(srow + ((j4 ^ (row & 7)) << 4));
                 v[4 * j4 + 0] += q.x; v[4 * j4 + 1] += q.y; v[4 * j4 + 2] += q.z; v[4 * j4 + 3] += q.w;
               }
             }
-            if (ep.out_f32) {
-              float4* op = reinterpret_cast<float4*>(ep.out_f32 + opix * ldc + n);
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4)
-                op[j4] = make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-            }
-            if (ep.out_op) {
-              const bool f16 = p.op_f16 != 0;
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out_op) + opix * ldc + n);
-              op[0] = make_uint4(pack_op2(v[0], v[1], f16), pack_op2(v[2], v[3], f16), pack_op2(v[4], v[5], f16),
-                                 pack_op2(v[6], v[7], f16));
-              op[1] = make_uint4(pack_op2(v[8], v[9], f16), pack_op2(v[10], v[11], f16), pack_op2(v[12], v[13], f16),
-                                 pack_op2(v[14], v[15], f16));
-            }
-            if (ep.out_nchw) {
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<float4*>(srow + ((j4 ^ (row & 7)) << 4)) =
+                  make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+            if (ep.out_op && valid) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out_op) + opix * ldc + tc.n0 + c);
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                ep.out_nchw[(((long long)tc.b * ldc + n + j) * p.out_h + oh) * p.out_w + ow] = v[j];
+              for (int j8 = 0; j8 < 4; ++j8)
+                op[j8] = make_uint4(pack_op2(v[8 * j8 + 0], v[8 * j8 + 1], f16), pack_op2(v[8 * j8 + 2], v[8 * j8 + 3], f16),
+                                    pack_op2(v[8 * j8 + 4], v[8 * j8 + 5], f16), pack_op2(v[8 * j8 + 6], v[8 * j8 + 7], f16));
             }
-          } else {
-            // ragged tail (e.g. the 3-channel `out` conv padded to N = 16): scalar path, NCHW output only
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          if (leader) {
+            // Slot reuse.  Before the barrier of chunk g the stores of chunks <= g-1 are committed.  The slot that is
+            // touched next — by the generic writes of chunk g+1 (no residual) or by the residual load of chunk g+A —
+            // was last stored from by chunk g+1-S resp. g+A-S, so at most S-2 resp. S-A-1 groups may stay pending.
+            const int pending_ok = res_tma ? (p.n_staging - p.res_ahead - 1) : (p.n_staging - 2);
+            if (pending_ok >= 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+            if (res_tma && !(p.dbg & 1)) issue_res_load();
+          }
+          named_bar_sync(1, 128);
+          if (leader && !(p.dbg & 1)) {
+            tma_store_5d(&maps_out.m[tc.phase], sbuf, tc.n0 + c, tc.w0, 0, tc.h0, tc.b);
+            bulk_commit_group();
+          }
+        }
+      } else {
+        // ------------------------------------------------ direct path (narrow N: the 3-channel `out` conv, NCHW store)
+        mbar_wait(&bars->tmem_full[as], aphase);
+        tc_fence_after();
+        for (int c = 0; c < p.block_n; c += 16) {
+          uint32_t r[16];
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores of the last chunk
+          tmem_ld16(taddr + (uint32_t)c, r);
+          tmem_ld_wait();
+          const int n = tc.n0 + c;
+          if (valid && n < ldc && !(p.dbg & 1)) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               if (n + j < ldc) {
-                float y = v[j] + __ldg(ep.bias + n + j);
+                float y = __uint_as_float(r[j]) + __ldg(ep.bias + n + j);
                 if (ep.film_scale1p)
                   y = fmaf(y, __ldg(ep.film_scale1p + (long long)tc.b * ep.film_stride + n + j),
                            __ldg(ep.film_shift + (long long)tc.b * ep.film_stride + n + j));
+                if (ep.resid) y += ep.resid[opix * ldc + n + j];
+                if (ep.out_f32) ep.out_f32[opix * ldc + n + j] = y;
+                if (ep.out_op) reinterpret_cast<uint16_t*>(ep.out_op)[opix * ldc + n + j] = to_op(y, f16);
                 if (ep.out_nchw) ep.out_nchw[(((long long)tc.b * ldc + n + j) * p.out_h + oh) * p.out_w + ow] = y;
               }
             }
@@ -242,6 +323,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
     }
+    if (leader && p.n_staging > 0) bulk_wait_group_all();  // all stores retired before smem goes away
   }
 
   tc_fence_before();
@@ -350,14 +432,14 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                      const cuuint32_t* box, int swizzle_bytes, bool f16) {
+                      const cuuint32_t* box, int swizzle_bytes, CUtensorMapDataType dtype) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return CLPK_ERR_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -381,6 +463,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   if (kind == CLPK_CONV_3X3_S2) CLPK_REQUIRE(h_in % 2 == 0 && w_in % 2 == 0, "stride-2 conv needs even H, W");
   IgemmParams& p = out->p;
   memset(&p, 0, sizeof(p));
+  { const char* e = getenv("CLPK_IGEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.batch = batch;
   p.op_f16 = (op_dtype == CLPK_OP_F16) ? 1 : 0;
   p.cin = cin;
@@ -449,19 +532,56 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
   const int stage_bytes = kTileM * p.block_k * 2 + p.block_n * p.block_k * 2;
-  p.stages = std::min(kMaxStages, (kSmemBudget - 2048) / stage_bytes);
+  // staged (TMA-store) epilogue whenever there is an fp32 NHWC output of >= 32 channels per tile
+  const bool staged = p.ep.out_f32 != nullptr && p.block_n % 32 == 0 && cout % 32 == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.ep.out_f32) & 15) == 0;
+  const int fixed = 1024 /*alignment slack*/ + (int)sizeof(EpiVectors) + (int)sizeof(PipeBarriers) + 64;
+  p.n_staging = 0;
+  if (staged) {
+    p.n_staging = ((kSmemBudget - fixed - 3 * kStagingBytes) / stage_bytes >= 4) ? 3 : 2;
+    if ((kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes < 2) p.n_staging = 0;
+  }
+  // residual chunks kept in flight by the epilogue leader: slots - 2 (one slot is being processed, one being stored)
+  p.res_ahead = (p.n_staging > 0 && p.ep.resid) ? std::max(1, p.n_staging - 2) : 0;
+  if (p.n_staging == 2 && p.ep.resid) p.res_ahead = 1;
+  p.stages = std::min(kMaxStages, (kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes);
   CLPK_REQUIRE(p.stages >= 2, "tile does not fit shared memory");
-  out->smem_bytes = p.stages * stage_bytes + 2048;
+  out->smem_bytes = p.stages * stage_bytes + p.n_staging * kStagingBytes + fixed;
   out->grid = std::min(p.num_tiles, num_sms());
 
   const int swz = p.block_k * 2;
   cuuint32_t box_a[5] = {(cuuint32_t)p.block_k, (cuuint32_t)p.wbox, 1, (cuuint32_t)p.hbox, 1};
-  int rc = encode_map(&out->map_a, x_bf16, 5, dims, strides, box_a, swz, p.op_f16 != 0);
+  const CUtensorMapDataType op_dt = p.op_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  int rc = encode_map(&out->map_a, x_bf16, 5, dims, strides, box_a, swz, op_dt);
   if (rc) return rc;
   cuuint64_t wdims[2] = {(cuuint64_t)p.taps * cin, (cuuint64_t)p.phases * p.cout_pad};
   cuuint64_t wstr[1] = {(cuuint64_t)p.taps * cin * 2};
   cuuint32_t box_w[2] = {(cuuint32_t)p.block_k, (cuuint32_t)p.block_n};
-  rc = encode_map(&out->map_w, w_packed, 2, wdims, wstr, box_w, swz, p.op_f16 != 0);
+  rc = encode_map(&out->map_w, w_packed, 2, wdims, wstr, box_w, swz, op_dt);
+  if (rc) return rc;
+  // fp32 NHWC output maps for the TMA-store epilogue: [C, Wgrid, 1, Hgrid, B] per phase (transposed conv: the phase
+  // (ph,pw) owns output pixels (2h+ph, 2w+pw) -> base offset + doubled w/h strides)
+  memset(&out->maps_out, 0, sizeof(out->maps_out));
+  if (p.n_staging > 0) {
+    const long long CO = cout, OW = p.out_w, OH = p.out_h, sc = p.out_scale;
+    cuuint64_t odims[5] = {(cuuint64_t)CO, (cuuint64_t)p.grid_w, 1, (cuuint64_t)p.grid_h, (cuuint64_t)batch};
+    cuuint64_t ostr[4] = {(cuuint64_t)(sc * CO * 4), (cuuint64_t)(sc * OW * CO * 4), (cuuint64_t)(sc * OW * CO * 4),
+                          (cuuint64_t)(OH * OW * CO * 4)};
+    cuuint32_t obox[5] = {32, (cuuint32_t)p.wbox, 1, (cuuint32_t)p.hbox, 1};
+    memset(&out->maps_res, 0, sizeof(out->maps_res));
+    for (int phase = 0; phase < p.phases; ++phase) {
+      const long long off = ((long long)(phase >> 1) * OW + (phase & 1)) * CO;
+      rc = encode_map(&out->maps_out.m[phase], p.ep.out_f32 + off, 5, odims, ostr, obox, 128,
+                      CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+      if (rc) return rc;
+      if (p.ep.resid) {
+        CLPK_REQUIRE((reinterpret_cast<uintptr_t>(p.ep.resid) & 15) == 0, "residual tensor must be 16-byte aligned");
+        rc = encode_map(&out->maps_res.m[phase], const_cast<float*>(p.ep.resid) + off, 5, odims, ostr, obox, 128,
+                        CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+        if (rc) return rc;
+      }
+    }
+  }
   return rc;
 }
 
@@ -481,9 +601,9 @@ int igemm_launch(const IgemmLaunch& L, cudaStream_t stream) {
   int irc = igemm_init();
   if (irc) return irc;
   if (L.p.block_k == 64)
-    conv_igemm_kernel<64><<<L.grid, kNumThreads, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.p);
+    conv_igemm_kernel<64><<<L.grid, kNumThreads, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
   else
-    conv_igemm_kernel<32><<<L.grid, kNumThreads, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.p);
+    conv_igemm_kernel<32><<<L.grid, kNumThreads, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }

@@ -18,6 +18,9 @@ struct IgemmParams {
   int phases, taps, kpt;    // kpt = k-blocks per tap = cin / block_k
   int num_tiles, stages, tmem_cols;
   int op_f16;               // operand format: 1 = fp16, 0 = bf16
+  int n_staging;            // epilogue staging buffers (128 rows x 128 B each) for the TMA-store path, 0 = direct stores
+  int res_ahead;            // residual chunks the epilogue leader keeps in flight ahead of the one being processed
+  int dbg;                  // perf-debug switches (env CLPK_IGEMM_DBG): 1 no epilogue memory ops, 2 no MMA, 4 no A loads, 8 no B loads
   // A-operand coordinates (5-D view of the NHWC input, see make_a_map): per (phase*taps + tap)
   int tap_x[kMaxTapEntries], tap_dw[kMaxTapEntries], tap_p[kMaxTapEntries], tap_dh[kMaxTapEntries];
   // element strides of that 5-D view (used by the CUDA-core cross-check kernel only)
@@ -28,10 +31,16 @@ struct IgemmParams {
   clpk_conv_epilogue ep;
 };
 
+struct alignas(64) OutMaps {
+  CUtensorMap m[4];  // fp32 NHWC output viewed per transposed-conv phase (entry 0 for ordinary convs)
+};
+
 struct IgemmLaunch {
   IgemmParams p;
   CUtensorMap map_a;
   CUtensorMap map_w;
+  OutMaps maps_out;
+  OutMaps maps_res;  // same geometry over the residual tensor (== maps_out when the conv updates in place)
   int grid;
   int smem_bytes;
 };

@@ -107,18 +107,27 @@ gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float
   __syncthreads();
   if (is_last) {
     __threadfence();
-    if (tid < groups) {
+    // warp w folds the partials of groups w, w+nwarps, ...: lanes stride over the chunks (independent loads in
+    // flight), then a fixed-order fp64 shuffle tree -> deterministic and latency-parallel
+    for (int g = warp; g < groups; g += nwarps) {
       double S = 0.0, SS = 0.0;
-      const float2* pp = partial + (long long)b * chunks * groups + tid;
-      for (int k = 0; k < chunks; ++k) {
+      const float2* pp = partial + (long long)b * chunks * groups + g;
+      for (int k = lane; k < chunks; k += 32) {
         const float2 v = __ldcg(pp + (long long)k * groups);
         S += (double)v.x; SS += (double)v.y;
       }
-      const double n = (double)hw * (double)cpg;
-      const double mean = S / n;
-      double var = SS / n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      stats[(long long)b * groups + tid] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        SS += __shfl_xor_sync(0xffffffffu, SS, o);
+      }
+      if (lane == 0) {
+        const double n = (double)hw * (double)cpg;
+        const double mean = S / n;
+        double var = SS / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[(long long)b * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+      }
     }
     if (tid == 0) counter[b] = 0;  // ready for the next launch / graph replay
   }
