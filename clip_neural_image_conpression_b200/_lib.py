@@ -36,6 +36,8 @@ class ConvEpilogue(C.Structure):
         ("out_op", C.c_void_p),
         ("out_nchw", C.c_void_p),
         ("cout_valid", C.c_int),
+        ("gn_partial", C.c_void_p),
+        ("gn_cpg", C.c_int),
     ]
 
 
@@ -68,6 +70,9 @@ SIGNATURES = {
     "clpk_film_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "clpk_groupnorm_ws_bytes": (_i64, [_i, _i, _i, _i]),
     "clpk_groupnorm_silu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "clpk_groupnorm_finalize": (_i, [_vp, _vp, _i, _i, _i, C.c_double, _f, _vp]),
+    "clpk_groupnorm_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "clpk_conv_gn_slots": (_i, [_i, _i, _i, _i, _i]),
     "clpk_pack_conv_weight": (_i64, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "clpk_conv_igemm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
     "clpk_conv_direct": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),

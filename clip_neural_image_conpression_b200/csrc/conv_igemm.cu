@@ -61,9 +61,81 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
 struct EpiVectors {
   float mul[256];
   float add[256];
+  float2 red[2][4][8];  // fused GN statistics: [chunk parity][epilogue warp][group pair] partial (sum, sumsq)
 };
 
-constexpr int kStagingBytes = kTileM * 128;  // one staging buffer: 128 rows x 32 fp32 columns, 128B-swizzled
+constexpr int kStagingBytes = kTileM * 128;
+
+// Fused GroupNorm statistics helpers.  A thread holds 32 consecutive output channels of one pixel; P = number of
+// consumer-GroupNorm groups those 32 channels span (1, 2, 4 or 8).  row_sums: per-thread (sum, sumsq) per group —
+// 32 FADD + 32 FFMA, all indices static.  warp_reduce_scatter: folds NV values over the 32 lanes with a halving butterfly
+// (NV/2 + NV/4 + ... shuffles instead of 5*NV); afterwards lane L holds the total of value index
+// bitreverse-ordered by the lane bits consumed, see `owner` below.  Fixed tree -> deterministic.
+template <int P>
+__device__ __forceinline__ void row_sums(const float (&v)[32], bool valid, float (&out)[2 * P]) {
+  constexpr int per = 32 / P;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < per; ++j) {
+      const float x = v[i * per + j];
+      s1 += x;
+      s2 = fmaf(x, x, s2);
+    }
+    out[2 * i] = valid ? s1 : 0.f;
+    out[2 * i + 1] = valid ? s2 : 0.f;
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ float warp_reduce_scatter(float (&vals)[NV], int lane) {
+  // halving steps: after the step with offset `off`, each lane keeps NV/2 values (those of its half)
+  int off = 16;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1) {
+    const int h = n >> 1;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float keep = upper ? vals[h + i] : vals[i];
+      const float send = upper ? vals[i] : vals[h + i];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+  float r = vals[0];
+  for (; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  return r;
+}
+
+// value index owned by `lane` after warp_reduce_scatter<NV>: the halving steps consumed lane bits 4,3,... (MSB first)
+template <int NV>
+__device__ __forceinline__ int scatter_owner_index(int lane) {
+  int idx = 0, off = 16;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1) {
+    idx = idx * 2 + ((lane & off) ? 1 : 0);  // NOTE: upper half at each step = +h in the ORIGINAL numbering
+    off >>= 1;
+  }
+  return idx;
+}
+
+template <int P>
+__device__ __forceinline__ void gn_chunk_partials(const float (&v)[32], bool valid, int lane, float2* redw) {
+  float vals[2 * P];
+  row_sums<P>(v, valid, vals);
+  const float r = warp_reduce_scatter<2 * P>(vals, lane);
+  // Which original value does this lane hold?  At the first step the kept half is [h, 2h) for `upper` lanes, i.e. the
+  // top bit of the original index = lane bit 4; the next step decides the next bit, and so on.
+  constexpr int kSteps = (P == 1) ? 1 : (P == 2) ? 2 : (P == 4) ? 3 : 4;
+  const int idx = scatter_owner_index<2 * P>(lane);
+  const int low_mask = (32 >> kSteps) - 1;  // lanes differing only in the untouched low bits hold duplicates
+  if ((lane & low_mask) == 0) {
+    float* f = reinterpret_cast<float*>(redw);
+    f[idx] = r;  // redw[i] = (sum_i, sumsq_i)  <->  flat index 2*i (+1)
+  }
+}  // one staging buffer: 128 rows x 32 fp32 columns, 128B-swizzled
 
 template <int BLOCK_K>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -265,6 +337,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 v[4 * j4 + 0] += q.x; v[4 * j4 + 1] += q.y; v[4 * j4 + 2] += q.z; v[4 * j4 + 3] += q.w;
               }
             }
+            if (ep.gn_partial) {
+              // per-thread (sum, sumsq) of this row's 32 values split by consumer-GroupNorm group, folded over the warp's
+              // 32 rows; the owning lanes park the warp's partials for the fixed-order 4-warp fold after the barrier
+              float2* redw = vec->red[gchunk & 1u][quarter];
+              const int cpg = ep.gn_cpg;
+              if (cpg >= 32) gn_chunk_partials<1>(v, valid, lane, redw);
+              else if (cpg == 16) gn_chunk_partials<2>(v, valid, lane, redw);
+              else if (cpg == 8) gn_chunk_partials<4>(v, valid, lane, redw);
+              else gn_chunk_partials<8>(v, valid, lane, redw);
+            }
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
               *reinterpret_cast<float4*>(srow + ((j4 ^ (row & 7)) << 4)) =
@@ -290,6 +372,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (leader && !(p.dbg & 1)) {
             tma_store_5d(&maps_out.m[tc.phase], sbuf, tc.n0 + c, tc.w0, 0, tc.h0, tc.b);
             bulk_commit_group();
+          }
+          if (ep.gn_partial && !(p.dbg & 1)) {
+            const int cpg = ep.gn_cpg;
+            const int npairs = cpg >= 32 ? 1 : 32 / cpg;
+            if (etid < npairs) {
+              const float2* rr = &vec->red[gchunk & 1u][0][etid];
+              float2 acc = rr[0];
+#pragma unroll
+              for (int wq = 1; wq < 4; ++wq) { acc.x += rr[wq * 8].x; acc.y += rr[wq * 8].y; }  // fixed order
+              const int ch = tc.n0 + c;
+              const int g = (cpg >= 32) ? ch / cpg : ch / cpg + etid;
+              const int mtile = (tc.phase * p.tiles_h + tc.h0 / p.hbox) * p.tiles_w + tc.w0 / p.wbox;
+              const int slot = mtile * p.gn_sub + ((cpg >= 32) ? (ch % cpg) / 32 : 0);
+              reinterpret_cast<float2*>(ep.gn_partial)[((long long)tc.b * p.gn_slots + slot) * p.gn_groups + g] = acc;
+            }
           }
         }
       } else {
@@ -406,6 +503,25 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __rest
 }
 
 int igemm_cout_pad(int cout) { return (cout + 15) / 16 * 16; }
+
+// geometry of the M tiling (shared by igemm_setup and the GN-slot computation)
+static void tile_geometry(int kind, int h_in, int w_in, int* grid_h, int* grid_w, int* wbox, int* hbox, int* phases) {
+  *grid_h = (kind == CLPK_CONV_3X3_S2) ? h_in / 2 : h_in;
+  *grid_w = (kind == CLPK_CONV_3X3_S2) ? w_in / 2 : w_in;
+  *phases = (kind == CLPK_CONVT_4X4_S2) ? 4 : 1;
+  *wbox = std::min(*grid_w, kTileM);
+  *hbox = std::max(1, std::min(*grid_h, kTileM / *wbox));
+}
+
+int igemm_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg) {
+  if (gn_cpg <= 0 || cout % gn_cpg != 0 || cout % 32 != 0) return 0;
+  if (!(gn_cpg == 4 || gn_cpg == 8 || gn_cpg == 16 || gn_cpg % 32 == 0)) return 0;
+  if (cout / gn_cpg > 32) return 0;
+  int gh, gw, wbox, hbox, phases;
+  tile_geometry(kind, h_in, w_in, &gh, &gw, &wbox, &hbox, &phases);
+  const int sub = gn_cpg >= 32 ? gn_cpg / 32 : 1;
+  return phases * ((gh + hbox - 1) / hbox) * ((gw + wbox - 1) / wbox) * sub;
+}
 int igemm_block_n(int cout_pad) {
   int best = 16;
   for (int n = 16; n <= 256 && n <= cout_pad; n += 16)
@@ -541,6 +657,15 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     p.n_staging = ((kSmemBudget - fixed - 3 * kStagingBytes) / stage_bytes >= 4) ? 3 : 2;
     if ((kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes < 2) p.n_staging = 0;
   }
+  p.gn_groups = p.gn_slots = 0;
+  p.gn_sub = 1;
+  if (p.ep.gn_partial) {
+    p.gn_slots = igemm_gn_slots(kind, h_in, w_in, cout, p.ep.gn_cpg);
+    CLPK_REQUIRE(p.gn_slots > 0 && p.n_staging > 0,
+                 "fused GroupNorm statistics unsupported for this conv (cout=%d cpg=%d)", cout, p.ep.gn_cpg);
+    p.gn_groups = cout / p.ep.gn_cpg;
+    p.gn_sub = p.ep.gn_cpg >= 32 ? p.ep.gn_cpg / 32 : 1;
+  }
   // residual chunks kept in flight by the epilogue leader: slots - 2 (one slot is being processed, one being stored)
   p.res_ahead = (p.n_staging > 0 && p.ep.resid) ? std::max(1, p.n_staging - 2) : 0;
   if (p.n_staging == 2 && p.ep.resid) p.res_ahead = 1;
@@ -641,6 +766,11 @@ extern "C" int64_t clpk_pack_conv_weight(const float* w_dev, void* out_bf16_dev,
   }
   count_launch();
   return total;
+}
+
+extern "C" int clpk_conv_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg) {
+  if (kind < 0 || kind > 2 || h_in <= 0 || w_in <= 0 || cout <= 0) return 0;
+  return igemm_gn_slots(kind, h_in, w_in, cout, gn_cpg);
 }
 
 extern "C" int clpk_conv_igemm(const void* x, const void* w, int kind, int batch, int h_in, int w_in, int cin, int cout,

@@ -20,6 +20,7 @@ struct IgemmParams {
   int op_f16;               // operand format: 1 = fp16, 0 = bf16
   int n_staging;            // epilogue staging buffers (128 rows x 128 B each) for the TMA-store path, 0 = direct stores
   int res_ahead;            // residual chunks the epilogue leader keeps in flight ahead of the one being processed
+  int gn_groups, gn_slots, gn_sub;  // fused GroupNorm statistics: groups, partial slots per image, chunks per group slot
   int dbg;                  // perf-debug switches (env CLPK_IGEMM_DBG): 1 no epilogue memory ops, 2 no MMA, 4 no A loads, 8 no B loads
   // A-operand coordinates (5-D view of the NHWC input, see make_a_map): per (phase*taps + tap)
   int tap_x[kMaxTapEntries], tap_dw[kMaxTapEntries], tap_p[kMaxTapEntries], tap_dh[kMaxTapEntries];
@@ -53,6 +54,7 @@ int igemm_launch(const IgemmLaunch& L, cudaStream_t stream);
 int direct_launch(const IgemmLaunch& L, const void* x_bf16, const void* w_packed, cudaStream_t stream);
 
 // padded GEMM-N of a conv with `cout` output channels, and the UMMA N tile chosen for it
+int igemm_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg);  // <= 0: unsupported
 int igemm_cout_pad(int cout);
 int igemm_block_n(int cout_pad);
 

@@ -167,8 +167,68 @@ gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
   }
 }
 
+// Folds per-tile partial sums produced by a conv epilogue: partial[b][slots][groups] (sum, sum of squares) ->
+// stats[b][g] = (mean, rstd).  One warp per (image, group); lanes stride over the slots, fp64 shuffle tree: deterministic.
+__global__ void gn_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stats, int slots, int groups,
+                                   double n_per_group, float eps) {
+  const int b = blockIdx.x;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (g >= groups) return;
+  const float2* pp = partial + (long long)b * slots * groups + g;
+  double S = 0.0, SS = 0.0;
+  for (int k = lane; k < slots; k += 32) {
+    const float2 v = __ldg(pp + (long long)k * groups);
+    S += (double)v.x; SS += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    S += __shfl_xor_sync(0xffffffffu, S, o);
+    SS += __shfl_xor_sync(0xffffffffu, SS, o);
+  }
+  if (lane == 0) {
+    const double mean = S / n_per_group;
+    double var = SS / n_per_group - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(long long)b * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  }
+}
+
+int launch_gn_finalize(const float2* partial, float2* stats, int batch, int slots, int groups, double n_per_group,
+                       float eps, cudaStream_t stream) {
+  CLPK_REQUIRE(groups <= 32, "GroupNorm finalize supports <= 32 groups");
+  gn_finalize_kernel<<<batch, 32 * groups, 0, stream>>>(partial, stats, slots, groups, n_per_group, eps);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+int launch_gn_apply(const float* x, const float* gamma, const float* beta, const float2* stats, void* y_op,
+                    const GnShape& s, int silu, int op_dtype, cudaStream_t stream) {
+  const long long octs = (long long)s.hw * (s.c / 8);
+  CLPK_REQUIRE(s.c % 8 == 0 && s.c % s.groups == 0 && (s.c / s.groups) % 4 == 0,
+               "GroupNorm needs C %% 8 == 0 and (C/groups) %% 4 == 0 (C=%d groups=%d)", s.c, s.groups);
+  CLPK_REQUIRE(octs < (1ll << 31), "image too large for GroupNorm indexing");
+  const int per_img_blocks = (int)std::min<long long>((octs + kGnThreads - 1) / kGnThreads,
+                                                      std::max(1, num_sms() * 8 / s.batch));
+  dim3 agrid(std::max(per_img_blocks, 1), s.batch);
+  gn_apply_kernel<<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, reinterpret_cast<uint16_t*>(y_op), s.hw, s.c,
+                                                   s.groups, silu, op_dtype == CLPK_OP_F16);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+// statistics pass only: leaves (mean, rstd) in the stats area of ws (see layout above) and returns its address
+int launch_gn_stats(const float* x, void* ws, const GnShape& s, float eps, const float2** stats_out, cudaStream_t stream);
+
 int launch_groupnorm(const float* x, const float* gamma, const float* beta, void* y_bf16, void* ws, const GnShape& s,
                      float eps, int silu, int op_dtype, cudaStream_t stream) {
+  const float2* stats = nullptr;
+  int rc = launch_gn_stats(x, ws, s, eps, &stats, stream);
+  if (rc) return rc;
+  return launch_gn_apply(x, gamma, beta, stats, y_bf16, s, silu, op_dtype, stream);
+}
+
+int launch_gn_stats(const float* x, void* ws, const GnShape& s, float eps, const float2** stats_out,
+                    cudaStream_t stream) {
   CLPK_REQUIRE(s.c % 8 == 0 && s.c % s.groups == 0 && (s.c / s.groups) % 4 == 0,
                "GroupNorm needs C %% 8 == 0 and (C/groups) %% 4 == 0 (C=%d groups=%d)", s.c, s.groups);
   CLPK_REQUIRE(s.c <= 4 * kGnMaxJ * kGnThreads, "GroupNorm supports C <= %d", 4 * kGnMaxJ * kGnThreads);
@@ -195,14 +255,7 @@ int launch_groupnorm(const float* x, const float* gamma, const float* beta, void
                                                           pix_per_chunk, eps);
   }
   CLPK_CHECK_LAUNCH();
-  const long long octs = (long long)s.hw * (s.c / 8);
-  CLPK_REQUIRE(octs < (1ll << 31), "image too large for GroupNorm indexing");
-  const int per_img_blocks = (int)std::min<long long>((octs + kGnThreads - 1) / kGnThreads,
-                                                      std::max(1, num_sms() * 8 / s.batch));
-  dim3 agrid(std::max(per_img_blocks, 1), s.batch);
-  gn_apply_kernel<<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, reinterpret_cast<uint16_t*>(y_bf16), s.hw,
-                                                   s.c, s.groups, silu, op_dtype == CLPK_OP_F16);
-  CLPK_CHECK_LAUNCH();
+  *stats_out = stats;
   return CLPK_OK;
 }
 
@@ -224,4 +277,21 @@ extern "C" int clpk_groupnorm_silu(const float* x, const float* gamma, const flo
   // the leaf entry point cannot assume the counters (start of ws) are zero
   CLPK_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)batch * 4, (cudaStream_t)stream));
   return launch_groupnorm(x, gamma, beta, y, ws, s, eps, silu, op_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int clpk_groupnorm_finalize(const void* partial, void* stats, int batch, int slots, int groups,
+                                       double n_per_group, float eps, void* stream) {
+  CLPK_REQUIRE(partial && stats && batch > 0 && slots > 0 && groups > 0 && n_per_group > 0,
+               "clpk_groupnorm_finalize: bad arguments");
+  return launch_gn_finalize(reinterpret_cast<const float2*>(partial), reinterpret_cast<float2*>(stats), batch, slots,
+                            groups, n_per_group, eps, (cudaStream_t)stream);
+}
+
+extern "C" int clpk_groupnorm_apply(const float* x, const float* gamma, const float* beta, const void* stats, void* y,
+                                    int batch, int hw, int c, int groups, int silu, int op_dtype, void* stream) {
+  CLPK_REQUIRE(x && gamma && beta && stats && y && batch > 0 && hw > 0 && c > 0 && groups > 0,
+               "clpk_groupnorm_apply: bad arguments");
+  CLPK_REQUIRE(op_dtype == CLPK_OP_BF16 || op_dtype == CLPK_OP_F16, "clpk_groupnorm_apply: operand dtype %d unknown", op_dtype);
+  return launch_gn_apply(x, gamma, beta, reinterpret_cast<const float2*>(stats), y, gn_shape(batch, hw, c, groups), silu,
+                         op_dtype, (cudaStream_t)stream);
 }

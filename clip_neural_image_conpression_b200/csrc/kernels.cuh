@@ -35,6 +35,11 @@ GnShape gn_shape(int batch, int hw, int c, int groups);
 long long gn_ws_bytes(const GnShape& s);
 int launch_groupnorm(const float* x, const float* gamma, const float* beta, void* y_op, void* ws, const GnShape& s,
                      float eps, int silu, int op_dtype, cudaStream_t stream);
+int launch_gn_stats(const float* x, void* ws, const GnShape& s, float eps, const float2** stats_out, cudaStream_t stream);
+int launch_gn_finalize(const float2* partial, float2* stats, int batch, int slots, int groups, double n_per_group,
+                       float eps, cudaStream_t stream);
+int launch_gn_apply(const float* x, const float* gamma, const float* beta, const float2* stats, void* y_op,
+                    const GnShape& s, int silu, int op_dtype, cudaStream_t stream);
 
 // conv_in.cu
 int launch_conv_in(const float* x_nchw, const float* w, const float* b, float* y_nhwc, int batch, int cin, int h, int w_,

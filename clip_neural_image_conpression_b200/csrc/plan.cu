@@ -25,9 +25,20 @@ struct ConvPlan {
   double flops = 0;
 };
 
+// One GroupNorm instance.  When its input is produced by a tcgen05 conv whose epilogue can emit per-tile partial sums
+// (`fused`), the statistics pass over the tensor disappears: finalize(partial) -> stats -> apply.
+struct GnPlan {
+  int level = 0, silu = 1;
+  float *gamma = nullptr, *beta = nullptr;
+  float2* stats = nullptr;    // [B][groups] (mean, rstd)
+  float2* partial = nullptr;  // [B][slots][groups] (sum, sumsq) written by the producer conv
+  int slots = 0;
+  bool fused = false;
+};
+
 struct ResBlockPlan {
   int c = 0, h = 0, w = 0, level = 0;
-  float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+  GnPlan gn1, gn2;
   ConvPlan conv1, conv2;
   int film_off = 0;      // scale1p at [film_off, film_off+c), shift at [film_off+c, film_off+2c)
   bool emit_bf16 = false;  // conv2 also writes a bf16 copy of x into D (feeds the next resampling conv)
@@ -46,7 +57,8 @@ struct clpk_plan {
   long long bytes = 0;
   // parameters
   float *tp0_w = nullptr, *tp0_b = nullptr, *tp2_w = nullptr, *tp2_b = nullptr, *zp_w = nullptr, *zp_b = nullptr;
-  float *in_w = nullptr, *in_b = nullptr, *on_g = nullptr, *on_b = nullptr;
+  float *in_w = nullptr, *in_b = nullptr;
+  GnPlan out_gn;
   float *film_w = nullptr, *film_b = nullptr;
   int film_n = 0;  // 2 * sum of ResBlock channels
   std::vector<ResBlockPlan> rbs;     // execution order
@@ -174,10 +186,11 @@ int make_conv(clpk_plan* P, const ParamTable& tab, const std::string& prefix, in
 int make_resblock(clpk_plan* P, const ParamTable& tab, const std::string& prefix, int level, ResBlockPlan* rb) {
   const int c = P->lv_c[level], h = P->lv_h[level], w = P->lv_w[level], td = P->cfg.time_dim;
   rb->c = c; rb->h = h; rb->w = w; rb->level = level;
-  CLPK_TRY(copy_param(P, tab, prefix + ".norm1.weight", c, &rb->g1));
-  CLPK_TRY(copy_param(P, tab, prefix + ".norm1.bias", c, &rb->b1));
-  CLPK_TRY(copy_param(P, tab, prefix + ".norm2.weight", c, &rb->g2));
-  CLPK_TRY(copy_param(P, tab, prefix + ".norm2.bias", c, &rb->b2));
+  rb->gn1.level = rb->gn2.level = level;
+  CLPK_TRY(copy_param(P, tab, prefix + ".norm1.weight", c, &rb->gn1.gamma));
+  CLPK_TRY(copy_param(P, tab, prefix + ".norm1.bias", c, &rb->gn1.beta));
+  CLPK_TRY(copy_param(P, tab, prefix + ".norm2.weight", c, &rb->gn2.gamma));
+  CLPK_TRY(copy_param(P, tab, prefix + ".norm2.bias", c, &rb->gn2.beta));
   CLPK_TRY(make_conv(P, tab, prefix + ".conv1", CLPK_CONV_3X3_S1, c, c, h, w, &rb->conv1));
   CLPK_TRY(make_conv(P, tab, prefix + ".conv2", CLPK_CONV_3X3_S1, c, c, h, w, &rb->conv2));
   // FiLM rows into the concatenated matrix: [scale rows | shift rows]; "+1" folded into the scale bias
@@ -200,17 +213,40 @@ int bind_conv(clpk_plan* P, ConvPlan* cv, const void* a, const clpk_conv_epilogu
   return igemm_setup(a, cv->w, cv->kind, P->B, cv->h_in, cv->w_in, cv->cin, cv->cout, P->cfg.op_dtype, &ep, &cv->L);
 }
 
-int run_groupnorm(clpk_plan* P, const float* x, const float* g, const float* b, int level, int silu, cudaStream_t s) {
-  const GnShape shp = gn_shape(P->B, P->lv_h[level] * P->lv_w[level], P->lv_c[level], std::min(P->cfg.groups, P->lv_c[level]));
-  CLPK_TIMED(P, kProfGroupNorm, s, launch_groupnorm(x, g, b, P->T, P->gn_ws, shp, 1e-5f, silu, P->cfg.op_dtype, s));
+int gn_groups_of(const clpk_plan* P, int level) { return std::min(P->cfg.groups, P->lv_c[level]); }
+
+// allocate the statistics buffers of a GroupNorm whose input comes from a conv of (kind, h_in, w_in) -> cout channels
+int setup_gn(clpk_plan* P, GnPlan* gn, int producer_kind, int prod_h_in, int prod_w_in) {
+  const int c = P->lv_c[gn->level], groups = gn_groups_of(P, gn->level);
+  CLPK_TRY(P->alloc(&gn->stats, (long long)P->B * groups));
+  gn->slots = (producer_kind >= 0) ? igemm_gn_slots(producer_kind, prod_h_in, prod_w_in, c, c / groups) : 0;
+  gn->fused = gn->slots > 0;
+  if (gn->fused) CLPK_TRY(P->alloc(&gn->partial, (long long)P->B * gn->slots * groups));
   return CLPK_OK;
+}
+
+int run_groupnorm(clpk_plan* P, const float* x, const GnPlan& gn, cudaStream_t s) {
+  const int level = gn.level, groups = gn_groups_of(P, level);
+  const int hw = P->lv_h[level] * P->lv_w[level], c = P->lv_c[level];
+  const GnShape shp = gn_shape(P->B, hw, c, groups);
+  const float2* stats = gn.stats;
+  P->prof_mark(kProfGroupNorm, s);
+  int rc;
+  if (gn.fused) {
+    rc = launch_gn_finalize(gn.partial, gn.stats, P->B, gn.slots, groups, (double)hw * (c / groups), 1e-5f, s);
+  } else {
+    rc = launch_gn_stats(x, P->gn_ws, shp, 1e-5f, &stats, s);
+  }
+  if (rc == CLPK_OK) rc = launch_gn_apply(x, gn.gamma, gn.beta, stats, P->T, shp, gn.silu, P->cfg.op_dtype, s);
+  P->prof_mark(-1, s);
+  return rc;
 }
 
 int run_resblock(clpk_plan* P, ResBlockPlan& rb, cudaStream_t s) {
   float* X = P->X[rb.level];
-  CLPK_TRY(run_groupnorm(P, X, rb.g1, rb.b1, rb.level, 1, s));     // blocks.py:41 act(norm1(x))
+  CLPK_TRY(run_groupnorm(P, X, rb.gn1, s));                        // blocks.py:41 act(norm1(x))
   CLPK_TIMED(P, kProfConvRes, s, igemm_launch(rb.conv1.L, s));     // conv1 + FiLM -> Y   (blocks.py:41-42)
-  CLPK_TRY(run_groupnorm(P, P->Y, rb.g2, rb.b2, rb.level, 1, s));  // blocks.py:43 act(norm2(y))
+  CLPK_TRY(run_groupnorm(P, P->Y, rb.gn2, s));                     // blocks.py:43 act(norm2(y))
   CLPK_TIMED(P, kProfConvRes, s, igemm_launch(rb.conv2.L, s));     // conv2 + x -> X      (blocks.py:43-44)
   return CLPK_OK;
 }
@@ -232,7 +268,7 @@ int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s) {
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
     CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->ups[l].L, s));  // D (bf16 of X[l+1]) -> X[l] += convT (unet.py:102-104)
   }
-  CLPK_TRY(run_groupnorm(P, P->X[0], P->on_g, P->on_b, 0, 0, s));  // out_norm, no activation (unet.py:105)
+  CLPK_TRY(run_groupnorm(P, P->X[0], P->out_gn, s));               // out_norm, no activation (unet.py:105)
   CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->out_conv.L, s));  // -> eps_buf (NCHW)
   return CLPK_OK;
 }
@@ -300,8 +336,10 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   CLPK_TRY(copy_param(P, tab, "z_proj.0.bias", td, &P->zp_b));
   CLPK_TRY(copy_param(P, tab, "in_conv.weight", (int64_t)cfg->base * cfg->img_ch * 9, &P->in_w));
   CLPK_TRY(copy_param(P, tab, "in_conv.bias", cfg->base, &P->in_b));
-  CLPK_TRY(copy_param(P, tab, "out_norm.weight", cfg->base, &P->on_g));
-  CLPK_TRY(copy_param(P, tab, "out_norm.bias", cfg->base, &P->on_b));
+  P->out_gn.level = 0;
+  P->out_gn.silu = 0;
+  CLPK_TRY(copy_param(P, tab, "out_norm.weight", cfg->base, &P->out_gn.gamma));
+  CLPK_TRY(copy_param(P, tab, "out_norm.bias", cfg->base, &P->out_gn.beta));
 
   // ---- ResBlock list in execution order + FiLM offsets
   struct RbSpec { std::string prefix; int level; bool emit; };
@@ -358,7 +396,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   CLPK_TRY(P->alloc(&P->run_dev, 1));
   CLPK_CHECK_CUDA(cudaMemset(P->run_dev, 0, sizeof(DdimRun)));
 
-  // ---- ResBlocks
+  // ---- ResBlocks: parameters first, then the GroupNorm statistics wiring (who produces each GN's input)
   P->rbs.resize(specs.size());
   int off = 0;
   for (size_t i = 0; i < specs.size(); ++i) {
@@ -367,6 +405,35 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     rb.emit_bf16 = specs[i].emit;
     CLPK_TRY(make_resblock(P, tab, specs[i].prefix, specs[i].level, &rb));
     off += 2 * rb.c;
+  }
+  std::vector<GnPlan*> gn_after_conv2(specs.size(), nullptr), gn_after_down(L, nullptr), gn_after_up(L, nullptr);
+  for (size_t i = 0; i < specs.size(); ++i) {
+    ResBlockPlan& rb = P->rbs[i];
+    const int l = rb.level;
+    CLPK_TRY(setup_gn(P, &rb.gn2, CLPK_CONV_3X3_S1, rb.h, rb.w));  // input = this block's conv1 output
+    if (i == 0) {
+      CLPK_TRY(setup_gn(P, &rb.gn1, -1, 0, 0));                    // input = stem conv (CUDA-core kernel): own stats pass
+    } else if (specs[i - 1].level == l) {
+      CLPK_TRY(setup_gn(P, &rb.gn1, CLPK_CONV_3X3_S1, rb.h, rb.w));
+      gn_after_conv2[i - 1] = &rb.gn1;
+    } else if (specs[i - 1].level < l) {                            // came down: stride-2 conv from level l-1
+      CLPK_TRY(setup_gn(P, &rb.gn1, CLPK_CONV_3X3_S2, P->lv_h[l - 1], P->lv_w[l - 1]));
+      gn_after_down[l - 1] = &rb.gn1;
+    } else {                                                        // came up: transposed conv from level l+1
+      CLPK_TRY(setup_gn(P, &rb.gn1, CLPK_CONVT_4X4_S2, P->lv_h[l + 1], P->lv_w[l + 1]));
+      gn_after_up[l] = &rb.gn1;
+    }
+  }
+  CLPK_TRY(setup_gn(P, &P->out_gn, CLPK_CONVT_4X4_S2, P->lv_h[1], P->lv_w[1]));
+  gn_after_up[0] = &P->out_gn;
+  auto wire_gn = [&](clpk_conv_epilogue* e, const GnPlan* gn) {
+    if (gn && gn->fused) {
+      e->gn_partial = gn->partial;
+      e->gn_cpg = P->lv_c[gn->level] / gn_groups_of(P, gn->level);
+    }
+  };
+  for (size_t i = 0; i < specs.size(); ++i) {
+    ResBlockPlan& rb = P->rbs[i];
     clpk_conv_epilogue e1{};
     e1.bias = rb.conv1.bias;
     e1.film_scale1p = P->film + rb.film_off;
@@ -374,6 +441,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     e1.film_stride = film_n;
     e1.out_f32 = P->Y;
     e1.cout_valid = rb.c;
+    wire_gn(&e1, &rb.gn2);
     CLPK_TRY(bind_conv(P, &rb.conv1, P->T, e1));
     clpk_conv_epilogue e2{};
     e2.bias = rb.conv2.bias;
@@ -381,6 +449,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     e2.out_f32 = P->X[rb.level];
     e2.out_op = rb.emit_bf16 ? P->D : nullptr;
     e2.cout_valid = rb.c;
+    wire_gn(&e2, gn_after_conv2[i]);
     CLPK_TRY(bind_conv(P, &rb.conv2, P->T, e2));
     P->flops_fwd += rb.conv1.flops + rb.conv2.flops;
   }
@@ -395,6 +464,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     ed.bias = dn.bias;
     ed.out_f32 = P->X[l + 1];
     ed.cout_valid = P->lv_c[l + 1];
+    wire_gn(&ed, gn_after_down[l]);
     CLPK_TRY(bind_conv(P, &dn, P->D, ed));
     P->flops_fwd += dn.flops;
     // up stage i = L-1-l maps level l+1 -> l: module up.(3*i+2), ConvTranspose2d(C[l+1] -> C[l])
@@ -407,6 +477,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     eu.resid = P->X[l];  // skip connection, added in place
     eu.out_f32 = P->X[l];
     eu.cout_valid = P->lv_c[l];
+    wire_gn(&eu, gn_after_up[l]);
     CLPK_TRY(bind_conv(P, &up, P->D, eu));
     P->flops_fwd += up.flops;
   }

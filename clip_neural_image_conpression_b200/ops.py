@@ -138,7 +138,7 @@ def pack_conv_weight(w: torch.Tensor, kind: int, dtype: torch.dtype = torch.floa
 
 
 def _conv(fn_name: str, x_nhwc_op, w_packed, kind, cout, bias, film_scale1p, film_shift, resid, out_f32, out_op,
-          out_nchw):
+          out_nchw, gn_partial=None, gn_cpg=0):
     require_cuda(x_nhwc_op, w_packed, bias)
     assert x_nhwc_op.is_contiguous() and x_nhwc_op.dtype == w_packed.dtype, "operands must share one 16-bit dtype"
     b, h, w, cin = x_nhwc_op.shape
@@ -154,6 +154,8 @@ def _conv(fn_name: str, x_nhwc_op, w_packed, kind, cout, bias, film_scale1p, fil
     ep.out_op = ptr(out_op)
     ep.out_nchw = ptr(out_nchw)
     ep.cout_valid = cout
+    ep.gn_partial = ptr(gn_partial)
+    ep.gn_cpg = int(gn_cpg)
     fn = getattr(_lib.load(), fn_name)
     check(fn(ptr(x_nhwc_op), ptr(w_packed), kind, b, h, w, cin, cout, op_code(x_nhwc_op.dtype), C.byref(ep), stream_ptr()),
           fn_name)
@@ -169,9 +171,11 @@ def _conv_out_hw(kind: int, h: int, w: int):
 
 def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, bias: torch.Tensor, *,
                film_scale1p=None, film_shift=None, resid=None, want_f32=True, want_op=False, want_nchw=False,
-               impl: str = "igemm"):
+               gn_groups: int = 0, impl: str = "igemm"):
     """Implicit-GEMM conv on the tensor cores (x and w_packed in the same 16-bit dtype).  Returns a dict of the
-    requested outputs: "f32" NHWC fp32, "op" NHWC in the operand dtype, "nchw" fp32 NCHW."""
+    requested outputs: "f32" NHWC fp32, "op" NHWC in the operand dtype, "nchw" fp32 NCHW.  gn_groups > 0 additionally
+    returns "gn_stats" [B, gn_groups, 2] = (mean, rstd) of a GroupNorm(gn_groups) over the output, accumulated by the
+    conv epilogue (no extra pass over the tensor)."""
     b, h, w, _ = x_nhwc_op.shape
     oh, ow = _conv_out_hw(kind, h, w)
     dev = x_nhwc_op.device
@@ -182,10 +186,35 @@ def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout:
         outs["op"] = torch.empty((b, oh, ow, cout), dtype=x_nhwc_op.dtype, device=dev)
     if want_nchw:
         outs["nchw"] = torch.empty((b, cout, oh, ow), dtype=torch.float32, device=dev)
+    partial, slots, cpg = None, 0, 0
+    if gn_groups > 0:
+        cpg = cout // gn_groups
+        slots = int(_lib.load().clpk_conv_gn_slots(kind, h, w, cout, cpg))
+        if slots <= 0:
+            raise ValueError(f"fused GroupNorm statistics unsupported for cout={cout}, groups={gn_groups}")
+        partial = torch.zeros((b, slots, gn_groups, 2), dtype=torch.float32, device=dev)
     _conv("clpk_conv_igemm" if impl == "igemm" else "clpk_conv_direct", x_nhwc_op, w_packed, kind, cout, bias,
           film_scale1p, film_shift, _f32c(resid) if resid is not None else None, outs.get("f32"), outs.get("op"),
-          outs.get("nchw"))
+          outs.get("nchw"), partial, cpg)
+    if gn_groups > 0:
+        stats = torch.empty((b, gn_groups, 2), dtype=torch.float32, device=dev)
+        check(_lib.load().clpk_groupnorm_finalize(ptr(partial), ptr(stats), b, slots, gn_groups, float(oh * ow * cpg), 1e-5,
+                                                  stream_ptr()), "clpk_groupnorm_finalize")
+        outs["gn_stats"] = stats
     return outs
+
+
+def groupnorm_apply(x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, stats: torch.Tensor, groups: int,
+                    silu: bool = True, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """Second half of GroupNorm(+SiLU) given (mean, rstd) [B, groups, 2] (e.g. from conv_igemm(gn_groups=...))."""
+    require_cuda(x_nhwc, gamma, beta, stats)
+    x = _f32c(x_nhwc)
+    b, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (b * c)
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    check(_lib.load().clpk_groupnorm_apply(ptr(x), ptr(_f32c(gamma)), ptr(_f32c(beta)), ptr(_f32c(stats)), ptr(y), b, hw, c,
+                                           groups, int(silu), op_code(dtype), stream_ptr()), "clpk_groupnorm_apply")
+    return y
 
 
 def conv_direct(*args, **kwargs):

@@ -93,6 +93,14 @@ int clpk_groupnorm_silu(const float* x_nhwc_dev, const float* gamma_dev, const f
                         void* ws_dev, int batch, int hw, int c, int groups, float eps, int silu, int op_dtype,
                         void* stream);
 
+/* The two halves of clpk_groupnorm_silu for producers that already emitted partial sums (conv epilogue):
+ * finalize: partial[b][slots][groups] float2 (sum, sumsq) -> stats[b][groups] float2 (mean, rstd), biased variance over
+ * n_per_group elements; apply: y = (x - mean) * rstd * gamma + beta [SiLU] in the 16-bit operand format. */
+int clpk_groupnorm_finalize(const void* partial_dev, void* stats_dev, int batch, int slots, int groups,
+                            double n_per_group, float eps, void* stream);
+int clpk_groupnorm_apply(const float* x_nhwc_dev, const float* gamma_dev, const float* beta_dev, const void* stats_dev,
+                         void* y_op_nhwc_dev, int batch, int hw, int c, int groups, int silu, int op_dtype, void* stream);
+
 /* Convolution kinds understood by the implicit-GEMM kernel. */
 #define CLPK_CONV_3X3_S1 0   /* Conv2d 3x3 stride 1 pad 1  (blocks.py:34,36; unet.py:79)   */
 #define CLPK_CONV_3X3_S2 1   /* Conv2d 3x3 stride 2 pad 1  (unet.py:63)                    */
@@ -119,7 +127,16 @@ typedef struct clpk_conv_epilogue {
   void* out_op;               /* dev NHWC 16-bit (op_dtype) or NULL */
   float* out_nchw;            /* dev NCHW fp32 or NULL            */
   int cout_valid;             /* channels really present (<= cout_pad) */
+  /* Fused GroupNorm statistics of the FINAL output values (after bias / FiLM / residual): per-tile partial sums
+   * gn_partial[b][slot][g] = (sum, sum of squares) as float2, slots = clpk_conv_gn_slots(...), g < cout / gn_cpg.
+   * Fold them with clpk_groupnorm_finalize.  NULL = off.  Needs out_f32 and gn_cpg in {4, 8, 16} or a multiple of 32. */
+  void* gn_partial;
+  int gn_cpg;
 } clpk_conv_epilogue;
+
+/* Number of partial-sum slots per image a conv of this geometry writes for a consumer GroupNorm with gn_cpg channels
+ * per group (<= 0: the fused statistics are not available for this shape). */
+int clpk_conv_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg);
 
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed).
  * x: 16-bit (op_dtype) NHWC [batch, h_in, w_in, cin]; w_packed from clpk_pack_conv_weight with the same op_dtype.

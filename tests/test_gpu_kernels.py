@@ -201,6 +201,39 @@ def test_conv_igemm(ops, kind, b, h, w, cin, cout, film, resid, dtype):
         assert float((o["op"].double().permute(0, 3, 1, 2) - ref).abs().max()) < 1.2 * half_ulp * max(scale, 1.0)
 
 
+@pytest.mark.parametrize("kind,b,h,w,cin,cout,resid", [
+    (0, 2, 32, 32, 128, 128, True),      # cpg 16: two groups per 32-column chunk
+    (0, 3, 16, 16, 32, 32, False),       # cpg 4
+    (0, 2, 16, 16, 64, 64, True),        # cpg 8
+    (0, 2, 16, 16, 256, 256, False),     # cpg 32: one group per chunk, two N... one N tile
+    (0, 2, 8, 8, 512, 512, True),        # cpg 64: two chunks per group, two N tiles, half-filled M tile
+    (1, 2, 32, 32, 128, 256, False),     # stride-2 producer
+    (2, 2, 16, 16, 256, 128, True),      # transposed-conv producer (4 phases)
+    (0, 1, 24, 24, 64, 64, False),       # ragged tiles: masked rows must not contribute
+])
+def test_conv_fused_groupnorm_statistics(ops, kind, b, h, w, cin, cout, resid):
+    """The conv epilogue's fused (mean, rstd) equal a GroupNorm statistics pass over its own fp32 output."""
+    g = torch.Generator().manual_seed(7 + cout + h)
+    xb = torch.randn(b, h, w, cin, generator=g).to(torch.float16).cuda()
+    wt = ((torch.randn(cin, cout, 4, 4, generator=g) if kind == 2 else torch.randn(cout, cin, 3, 3, generator=g)) * 0.05).cuda()
+    bias = (torch.randn(cout, generator=g) + 0.5).cuda()
+    oh, ow = (h // 2, w // 2) if kind == 1 else ((2 * h, 2 * w) if kind == 2 else (h, w))
+    kw = {"resid": torch.randn(b, oh, ow, cout, generator=g).cuda()} if resid else {}
+    o = ops.conv_igemm(xb, ops.pack_conv_weight(wt, kind), kind, cout, bias, gn_groups=8, **kw)
+    y = o["f32"].double().reshape(b, oh * ow, 8, cout // 8)
+    mean = y.mean(dim=(1, 3))
+    rstd = 1.0 / torch.sqrt(y.var(dim=(1, 3), unbiased=False) + 1e-5)
+    np.testing.assert_allclose(o["gn_stats"][..., 0].cpu().numpy(), mean.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(o["gn_stats"][..., 1].cpu().numpy(), rstd.cpu().numpy(), rtol=1e-4)
+    o2 = ops.conv_igemm(xb, ops.pack_conv_weight(wt, kind), kind, cout, bias, gn_groups=8, **kw)
+    assert torch.equal(o["gn_stats"], o2["gn_stats"]) and torch.equal(o["f32"], o2["f32"])   # deterministic
+    # finalize + apply == the standalone GroupNorm kernel on the same tensor
+    gamma, beta = (1 + 0.1 * torch.randn(cout, generator=g)).cuda(), (0.1 * torch.randn(cout, generator=g)).cuda()
+    a = ops.groupnorm_apply(o["f32"], gamma, beta, o["gn_stats"], 8, silu=True)
+    ref = ops.groupnorm_silu(o["f32"], gamma, beta, 8, 1e-5, True)
+    assert float((a.float() - ref.float()).abs().max()) <= 4e-3 * max(1.0, float(ref.float().abs().max()))
+
+
 # ------------------------------------------------------------------------------------------------ blocks, post-process
 def test_film_and_resblock_match_reference(ops, golden):
     from clip_neural_image_conpression_b200.models import FiLM, ResBlock
