@@ -39,18 +39,22 @@ struct __align__(8) PipeBarriers {
 
 struct TileCoord {
   int phase, b, h0, w0, n0;
+  bool ok;  // false: the odd CTA of a pair past the last spatial tile (loads hit TMA out-of-bounds zeros, nothing stored)
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+// Work item -> tile.  Order (fastest first): channel tile, transposed-conv phase, spatial tile (pair).  Keeping the 4
+// phases of one spatial tile adjacent in time lets their interleaved output rows meet in L2 before they reach HBM.
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int item, int rank) {
   TileCoord c;
-  int nt = tile % p.n_tiles_n;
-  int r = tile / p.n_tiles_n;
-  int tw = r % p.tiles_w;
-  r /= p.tiles_w;
-  int th = r % p.tiles_h;
-  r /= p.tiles_h;
-  c.b = r % p.batch;
-  c.phase = r / p.batch;
+  const int nt = item % p.n_tiles_n;
+  int r = item / p.n_tiles_n;
+  c.phase = r % p.phases;
+  const int msp = (r / p.phases) * p.ncta + rank;
+  c.ok = msp < p.spatial_tiles;
+  const int tw = msp % p.tiles_w;
+  r = msp / p.tiles_w;
+  const int th = r % p.tiles_h;
+  c.b = r / p.tiles_h;
   c.h0 = th * p.hbox;
   c.w0 = tw * p.wbox;
   c.n0 = nt * p.block_n;
@@ -58,11 +62,13 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
 }
 
 // per-tile epilogue vectors: y = acc * mul[n] + add[n]   (mul = 1 + FiLM scale or 1, add = bias * mul + FiLM shift)
-struct EpiVectors {
-  float mul[256];
-  float add[256];
-  float2 red[2][4][8];  // fused GN statistics: [chunk parity][epilogue warp][group pair] partial (sum, sumsq)
+struct EpiVectors {       // laid out in smem as: float mul[block_n] | float add[block_n] | float2 red[2][4][8]
+  float* mul;
+  float* add;
+  float2 (*red)[4][8];    // fused GN statistics: [chunk parity][epilogue warp][group pair] partial (sum, sumsq)
 };
+constexpr int kRedBytes = 2 * 4 * 8 * (int)sizeof(float2);
+static inline int epi_vector_bytes(int block_n) { return 2 * 4 * block_n + kRedBytes; }
 
 constexpr int kStagingBytes = kTileM * 128;
 
@@ -137,24 +143,37 @@ __device__ __forceinline__ void gn_chunk_partials(const float (&v)[32], bool val
   }
 }  // one staging buffer: 128 rows x 32 fp32 columns, 128B-swizzled
 
-template <int BLOCK_K>
+template <int BLOCK_K, int NCTA>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ OutMaps maps_out, const __grid_constant__ OutMaps maps_res,
                   const __grid_constant__ IgemmParams p) {
-  constexpr int kSwizzle = BLOCK_K * 2;           // bytes per smem row
-  constexpr int kABytes = kTileM * BLOCK_K * 2;   // one A stage
+  // BLOCK_K elements of K per pipeline stage.  A smem row holds one swizzle atom of kAtomK elements (<= 128 bytes);
+  // BLOCK_K = 128 stages two atoms side by side (two TMA boxes per operand, 8 MMAs per barrier handshake).
+  constexpr int kAtomK = BLOCK_K > 64 ? 64 : BLOCK_K;
+  constexpr int kAtoms = BLOCK_K / kAtomK;
+  constexpr int kSwizzle = kAtomK * 2;            // bytes per smem row
+  constexpr int kAAtomBytes = kTileM * kAtomK * 2;
+  constexpr int kABytes = kAAtomBytes * kAtoms;   // one A stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
   uint8_t* smem = smem_raw + pad;  // 1024-byte aligned (swizzle atoms)
 
-  const int b_bytes = p.block_n * BLOCK_K * 2;
+  const int b_rows = p.block_n / NCTA;            // each CTA of a pair stages half of the B (weight) tile
+  const int b_atom_bytes = b_rows * kAtomK * 2;
+  const int b_bytes = b_atom_bytes * kAtoms;
+  const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / NCTA, num_clusters = gridDim.x / NCTA;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.stages * kABytes;
   uint8_t* smem_s = smem_b + (size_t)p.stages * b_bytes;  // staging buffers (1024-aligned: all sizes are multiples)
-  EpiVectors* vec = reinterpret_cast<EpiVectors*>(smem_s + (size_t)p.n_staging * kStagingBytes);
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(vec + 1);
+  EpiVectors vec_s;
+  vec_s.mul = reinterpret_cast<float*>(smem_s + (size_t)p.n_staging * kStagingBytes);
+  vec_s.add = vec_s.mul + p.block_n;
+  vec_s.red = reinterpret_cast<float2(*)[4][8]>(vec_s.add + p.block_n);
+  const EpiVectors* vec = &vec_s;
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(reinterpret_cast<uint8_t*>(vec_s.red) + kRedBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,81 +188,123 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
-      mbar_init(&bars->tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&bars->tmem_empty[s], 4 * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int s = 0; s < 4; ++s) mbar_init(&bars->res_full[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
-    tmem_relinquish();
+    if (NCTA == 2) { tmem_alloc_pair(&bars->tmem_base, (uint32_t)p.tmem_cols); tmem_relinquish_pair(); }
+    else { tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();  // barriers of BOTH CTAs initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    // The whole warp walks the loop converged (every lane waits on the barrier); only the issue of the uniform-datapath
+    // TMA instructions sits under elect.sync.  Issuing them from a divergent `if (lane == 0)` region makes the compiler
+    // wrap each one in an ELECT/BRA.U.ANY serialisation loop, which throttles the pipeline.
+    {
       const uint32_t rows = (uint32_t)(p.wbox * p.hbox);
       const uint32_t tx_bytes = rows * BLOCK_K * 2 + (uint32_t)b_bytes;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
-        const int w_row = tc.phase * p.cout_pad + tc.n0;
-        if (p.ep.resid && p.n_staging > 0) {
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        const TileCoord tc = decode_tile(p, tile, (int)rank);
+        const int w_row = tc.phase * p.cout_pad + tc.n0 + (int)rank * b_rows;
+        if (p.ep.resid && p.n_staging > 0 && tc.ok && elect_one()) {
           // the epilogue will add this residual tile: pull it into L2 while the MMAs run
           for (int c = 0; c < p.block_n; c += 32)
             tma_prefetch_5d(&maps_res.m[tc.phase], tc.n0 + c, tc.w0, 0, tc.h0, tc.b);
         }
+        __syncwarp();
         int tap = 0, kc = 0;
         for (int kb = 0; kb < k_blocks; ++kb) {
           const int ti = tc.phase * p.taps + tap;
           mbar_wait(&bars->empty[stage], phase ^ 1u);
-          uint32_t tx = tx_bytes;
-          if (p.dbg & 4) tx -= rows * BLOCK_K * 2;
-          if (p.dbg & 8) tx -= (uint32_t)b_bytes;
-          mbar_arrive_expect_tx(&bars->full[stage], tx);
-          if (!(p.dbg & 4))
-            tma_load_5d(smem_a + (size_t)stage * kABytes, &map_a, &bars->full[stage], p.tap_x[ti] + kc * BLOCK_K,
-                        tc.w0 + p.tap_dw[ti], p.tap_p[ti], tc.h0 + p.tap_dh[ti], tc.b);
-          if (!(p.dbg & 8))
-            tma_load_2d(smem_b + (size_t)stage * b_bytes, &map_w, &bars->full[stage], kb * BLOCK_K, w_row);
+          if (elect_one()) {
+            uint32_t tx = tx_bytes;
+            if (p.dbg & 4) tx -= rows * BLOCK_K * 2;
+            if (p.dbg & 8) tx -= (uint32_t)b_bytes;
+            uint8_t* a_dst = smem_a + (size_t)stage * kABytes;
+            uint8_t* b_dst = smem_b + (size_t)stage * b_bytes;
+            if (NCTA == 2) {
+              // both CTAs' bytes are accounted on the LEADER's full barrier (the MMA issuer lives there)
+              if (rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * tx);
+              const uint32_t lead_full = mapa_u32(smem_u32(&bars->full[stage]), 0u);
+#pragma unroll
+              for (int at = 0; at < kAtoms; ++at) {
+                if (!(p.dbg & 4))
+                  tma_load_5d_pair(a_dst + at * kAAtomBytes, &map_a, lead_full, p.tap_x[ti] + kc * BLOCK_K + at * kAtomK,
+                                   tc.w0 + p.tap_dw[ti], p.tap_p[ti], tc.h0 + p.tap_dh[ti], tc.b);
+                if (!(p.dbg & 8))
+                  tma_load_2d_pair(b_dst + at * b_atom_bytes, &map_w, lead_full, kb * BLOCK_K + at * kAtomK, w_row);
+              }
+            } else {
+              mbar_arrive_expect_tx(&bars->full[stage], tx);
+#pragma unroll
+              for (int at = 0; at < kAtoms; ++at) {
+                if (!(p.dbg & 4))
+                  tma_load_5d(a_dst + at * kAAtomBytes, &map_a, &bars->full[stage], p.tap_x[ti] + kc * BLOCK_K + at * kAtomK,
+                              tc.w0 + p.tap_dw[ti], p.tap_p[ti], tc.h0 + p.tap_dh[ti], tc.b);
+                if (!(p.dbg & 8))
+                  tma_load_2d(b_dst + at * b_atom_bytes, &map_w, &bars->full[stage], kb * BLOCK_K + at * kAtomK, w_row);
+              }
+            }
+          }
+          __syncwarp();
           if (++kc == p.kpt) { kc = 0; ++tap; }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_16bit(kTileM, p.block_n, p.op_f16 != 0);
+    // ===================================================== MMA issuer (warp converged, one elected lane issues)
+    if (rank == 0) {  // in a CTA pair only the leader issues (for both CTAs)
+      const uint32_t idesc = make_idesc_16bit(kTileM * NCTA, p.block_n, p.op_f16 != 0);
+      const uint64_t adesc0 = make_kmajor_desc<kSwizzle>(smem_u32(smem_a));
+      const uint64_t bdesc0 = make_kmajor_desc<kSwizzle>(smem_u32(smem_b));
+      const uint64_t a_step = (uint64_t)(kABytes >> 4), b_step = (uint64_t)(b_bytes >> 4);  // per stage, in 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);  // epilogue has drained this accumulator
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);  // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&bars->full[stage], phase);  // TMA bytes have landed
+          mbar_wait(&bars->full[stage], phase);  // TMA bytes (of both CTAs) have landed
           tc_fence_after();
-          const uint64_t adesc = make_kmajor_desc<kSwizzle>(smem_u32(smem_a + (size_t)stage * kABytes));
-          const uint64_t bdesc = make_kmajor_desc<kSwizzle>(smem_u32(smem_b + (size_t)stage * b_bytes));
+          if (elect_one()) {
+            const uint64_t adesc = adesc0 + a_step * (uint64_t)stage;
+            const uint64_t bdesc = bdesc0 + b_step * (uint64_t)stage;
+            if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            if (p.dbg & 2) break;
-            // advance 16 elements = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
-            umma_f16kind(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+              for (int k = 0; k < BLOCK_K / 16; ++k) {
+                // K advance: 16 elements = 32 bytes inside the swizzled row (+2 in the addr>>4 field); next atom = next
+                // 128-row block of the stage
+                const int at = k / (kAtomK / 16), kk = k % (kAtomK / 16);
+                const uint64_t ao = (uint64_t)(at * (kAAtomBytes >> 4) + 2 * kk);
+                const uint64_t bo = (uint64_t)(at * (b_atom_bytes >> 4) + 2 * kk);
+                const uint32_t acc = (k == 0) ? (uint32_t)(kb != 0) : 1u;
+                if (NCTA == 2) umma_f16kind_pair(tmem_d, adesc + ao, bdesc + bo, idesc, acc);
+                else umma_f16kind(tmem_d, adesc + ao, bdesc + bo, idesc, acc);
+              }
+            }
+            // smem slot reusable (in both CTAs) once these MMAs retire; last k-block: accumulator complete
+            if (NCTA == 2) umma_commit_pair(&bars->empty[stage]); else umma_commit(&bars->empty[stage]);
+            if (kb == k_blocks - 1) {
+              if (NCTA == 2) umma_commit_pair(&bars->tmem_full[as]); else umma_commit(&bars->tmem_full[as]);
+            }
           }
-          umma_commit(&bars->empty[stage]);  // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&bars->tmem_full[as]);  // accumulator complete
       }
     }
   } else {
@@ -264,41 +325,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // place).  The leader keeps `res_ahead` chunks in flight; (ld_tile, ld_c, ld_g) is its load cursor.
     const bool res_tma = (p.n_staging > 0) && (ep.resid != nullptr);
     const uint32_t res_bytes = (uint32_t)(p.wbox * p.hbox) * 128u;
-    int ld_tile = blockIdx.x, ld_c = 0;
+    int ld_tile = cluster_id, ld_c = 0;
     uint32_t ld_g = 0;
     auto issue_res_load = [&]() {
       if (ld_tile >= p.num_tiles) return;
-      const TileCoord lc = decode_tile(p, ld_tile);
+      const TileCoord lc = decode_tile(p, ld_tile, (int)rank);
       const uint32_t slot = ld_g % (uint32_t)p.n_staging;
       mbar_arrive_expect_tx(&bars->res_full[slot], res_bytes);
       tma_load_5d(smem_s + (size_t)slot * kStagingBytes, &maps_res.m[lc.phase], &bars->res_full[slot], lc.n0 + ld_c, lc.w0, 0,
                   lc.h0, lc.b);
       ++ld_g;
       ld_c += 32;
-      if (ld_c >= p.block_n) { ld_c = 0; ld_tile += gridDim.x; }
+      if (ld_c >= p.block_n) { ld_c = 0; ld_tile += num_clusters; }
     };
     if (res_tma && leader && !(p.dbg & 1))
       for (int i = 0; i < p.res_ahead; ++i) issue_res_load();
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t lead_tmem_empty0 = (NCTA == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[0]), 0u) : 0u;
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      const TileCoord tc = decode_tile(p, tile);
+      const TileCoord tc = decode_tile(p, tile, (int)rank);
       const int h = tc.h0 + hl, w = tc.w0 + wl;
-      const bool valid = (hl < p.hbox) && (h < p.grid_h) && (w < p.grid_w);
+      const bool valid = tc.ok && (hl < p.hbox) && (h < p.grid_h) && (w < p.grid_w);
       const int oh = h * p.out_scale + (tc.phase >> 1), ow = w * p.out_scale + (tc.phase & 1);
       const long long opix = ((long long)tc.b * p.out_h + oh) * p.out_w + ow;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.block_n);
 
       if (p.n_staging > 0) {
         // ------------------------------------------------ staged path: TMEM -> regs -> swizzled smem -> TMA store
-        const int key = tc.b * 4096 + tc.n0;
+        const int vb = tc.ok ? tc.b : 0;  // a masked tile still runs the (uniform) protocol, on image 0's vectors
+        const int key = vb * 4096 + tc.n0;
         if (key != cached_key) {  // (image, channel-tile) changed: refresh the folded bias / FiLM vectors
           named_bar_sync(1, 128);
           for (int n = etid; n < p.block_n; n += 128) {
             float mul = 1.0f, add = __ldg(ep.bias + tc.n0 + n);
             if (ep.film_scale1p) {
-              mul = __ldg(ep.film_scale1p + (long long)tc.b * ep.film_stride + tc.n0 + n);
-              add = fmaf(add, mul, __ldg(ep.film_shift + (long long)tc.b * ep.film_stride + tc.n0 + n));
+              mul = __ldg(ep.film_scale1p + (long long)vb * ep.film_stride + tc.n0 + n);
+              add = fmaf(add, mul, __ldg(ep.film_shift + (long long)vb * ep.film_stride + tc.n0 + n));
             }
             vec->mul[n] = mul;
             vec->add[n] = add;
@@ -376,7 +439,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (ep.gn_partial && !(p.dbg & 1)) {
             const int cpg = ep.gn_cpg;
             const int npairs = cpg >= 32 ? 1 : 32 / cpg;
-            if (etid < npairs) {
+            if (etid < npairs && tc.ok) {
               const float2* rr = &vec->red[gchunk & 1u][0][etid];
               float2 acc = rr[0];
 #pragma unroll
@@ -418,15 +481,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(lead_tmem_empty0 + (uint32_t)as * 8u);  // the issuer waits in the leader CTA
+        else mbar_arrive(&bars->tmem_empty[as]);
+      }
     }
     if (leader && p.n_staging > 0) bulk_wait_group_all();  // all stores retired before smem goes away
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();  // no remote arrive / multicast commit may still target a peer
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (NCTA == 2) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ cross-check kernel
@@ -584,8 +652,17 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   p.op_f16 = (op_dtype == CLPK_OP_F16) ? 1 : 0;
   p.cin = cin;
   p.cout_pad = igemm_cout_pad(cout);
-  p.block_k = (cin % 64 == 0) ? 64 : 32;
   p.block_n = igemm_block_n(p.cout_pad);
+  // Tile configuration (measured on B200, tools/bench_conv.py): N >= 256 tiles run as CTA pairs (cta_group::2, the B
+  // tile split over the pair) with 64-wide k-blocks; N <= 128 tiles run single-CTA with 128-wide k-blocks (8 MMAs per
+  // barrier handshake) — the handshake, not the MMA, bounds a 128x128 k-block of 64.
+  p.ncta = (p.block_n >= 256) ? 2 : 1;
+  { const char* e = getenv("CLPK_IGEMM_NCTA"); if (e && (atoi(e) == 1 || atoi(e) == 2)) p.ncta = atoi(e); }
+  if (p.block_n % 32 != 0) p.ncta = 1;  // a CTA pair splits N in two halves that must stay multiples of 16
+  p.block_k = (cin % 128 == 0 && p.ncta == 1) ? 128 : (cin % 64 == 0) ? 64 : 32;
+  { const char* e = getenv("CLPK_IGEMM_BK");
+    if (e && atoi(e) == 64 && p.block_k == 128) p.block_k = 64;
+    if (e && atoi(e) == 128 && cin % 128 == 0) p.block_k = 128; }
   p.n_tiles_n = p.cout_pad / p.block_n;
   p.kpt = cin / p.block_k;
   p.ep = *ep;
@@ -642,19 +719,22 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   p.hbox = std::max(1, std::min(p.grid_h, kTileM / p.wbox));
   p.tiles_w = (p.grid_w + p.wbox - 1) / p.wbox;
   p.tiles_h = (p.grid_h + p.hbox - 1) / p.hbox;
-  const long long nt = (long long)p.phases * batch * p.tiles_h * p.tiles_w * p.n_tiles_n;
+  p.spatial_tiles = batch * p.tiles_h * p.tiles_w;
+  const long long nt = (long long)((p.spatial_tiles + p.ncta - 1) / p.ncta) * p.phases * p.n_tiles_n;
   CLPK_REQUIRE(nt < (1ll << 30), "too many tiles");
   p.num_tiles = (int)nt;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
-  const int stage_bytes = kTileM * p.block_k * 2 + p.block_n * p.block_k * 2;
+  const int stage_bytes = kTileM * p.block_k * 2 + (p.block_n / p.ncta) * p.block_k * 2;
   // staged (TMA-store) epilogue whenever there is an fp32 NHWC output of >= 32 channels per tile
   const bool staged = p.ep.out_f32 != nullptr && p.block_n % 32 == 0 && cout % 32 == 0 &&
                       (reinterpret_cast<uintptr_t>(p.ep.out_f32) & 15) == 0;
-  const int fixed = 1024 /*alignment slack*/ + (int)sizeof(EpiVectors) + (int)sizeof(PipeBarriers) + 64;
+  const int fixed = 1024 /*alignment slack*/ + epi_vector_bytes(p.block_n) + (int)sizeof(PipeBarriers) + 16;
   p.n_staging = 0;
   if (staged) {
-    p.n_staging = ((kSmemBudget - fixed - 3 * kStagingBytes) / stage_bytes >= 4) ? 3 : 2;
+    p.n_staging = ((kSmemBudget - fixed - 3 * kStagingBytes) / stage_bytes >= 4 ||
+                   (kSmemBudget - fixed - 3 * kStagingBytes) / stage_bytes == (kSmemBudget - fixed - 2 * kStagingBytes) / stage_bytes)
+                      ? 3 : 2;
     if ((kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes < 2) p.n_staging = 0;
   }
   p.gn_groups = p.gn_slots = 0;
@@ -672,16 +752,17 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   p.stages = std::min(kMaxStages, (kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes);
   CLPK_REQUIRE(p.stages >= 2, "tile does not fit shared memory");
   out->smem_bytes = p.stages * stage_bytes + p.n_staging * kStagingBytes + fixed;
-  out->grid = std::min(p.num_tiles, num_sms());
+  out->grid = p.ncta * std::min(p.num_tiles, num_sms() / p.ncta);
 
-  const int swz = p.block_k * 2;
-  cuuint32_t box_a[5] = {(cuuint32_t)p.block_k, (cuuint32_t)p.wbox, 1, (cuuint32_t)p.hbox, 1};
+  const int atom_k = std::min(p.block_k, 64);  // one TMA box = one swizzle atom (<= 128 bytes of K per row)
+  const int swz = atom_k * 2;
+  cuuint32_t box_a[5] = {(cuuint32_t)atom_k, (cuuint32_t)p.wbox, 1, (cuuint32_t)p.hbox, 1};
   const CUtensorMapDataType op_dt = p.op_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   int rc = encode_map(&out->map_a, x_bf16, 5, dims, strides, box_a, swz, op_dt);
   if (rc) return rc;
   cuuint64_t wdims[2] = {(cuuint64_t)p.taps * cin, (cuuint64_t)p.phases * p.cout_pad};
   cuuint64_t wstr[1] = {(cuuint64_t)p.taps * cin * 2};
-  cuuint32_t box_w[2] = {(cuuint32_t)p.block_k, (cuuint32_t)p.block_n};
+  cuuint32_t box_w[2] = {(cuuint32_t)atom_k, (cuuint32_t)(p.block_n / p.ncta)};
   rc = encode_map(&out->map_w, w_packed, 2, wdims, wstr, box_w, swz, op_dt);
   if (rc) return rc;
   // fp32 NHWC output maps for the TMA-store epilogue: [C, Wgrid, 1, Hgrid, B] per phase (transposed conv: the phase
@@ -710,25 +791,51 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   return rc;
 }
 
+template <int BK, int NC>
+static cudaError_t set_smem_attr() {
+  return cudaFuncSetAttribute(conv_igemm_kernel<BK, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+}
+
 int igemm_init() {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    attr_err = set_smem_attr<64, 1>();
+    if (attr_err == cudaSuccess) attr_err = set_smem_attr<32, 1>();
+    if (attr_err == cudaSuccess) attr_err = set_smem_attr<128, 1>();
+    if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2>();
+    if (attr_err == cudaSuccess) attr_err = set_smem_attr<32, 2>();
+    if (attr_err == cudaSuccess) attr_err = set_smem_attr<128, 2>();
   });
   CLPK_CHECK_CUDA(attr_err);
   return CLPK_OK;
 }
 
+template <int BK, int NC>
+static cudaError_t launch_variant(const IgemmLaunch& L, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)L.grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = (size_t)L.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (NC > 1) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BK, NC>, L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
+}
+
 int igemm_launch(const IgemmLaunch& L, cudaStream_t stream) {
   int irc = igemm_init();
   if (irc) return irc;
-  if (L.p.block_k == 64)
-    conv_igemm_kernel<64><<<L.grid, kNumThreads, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
-  else
-    conv_igemm_kernel<32><<<L.grid, kNumThreads, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
+  cudaError_t e;
+  if (L.p.block_k == 128) e = (L.p.ncta == 2) ? launch_variant<128, 2>(L, stream) : launch_variant<128, 1>(L, stream);
+  else if (L.p.block_k == 64) e = (L.p.ncta == 2) ? launch_variant<64, 2>(L, stream) : launch_variant<64, 1>(L, stream);
+  else e = (L.p.ncta == 2) ? launch_variant<32, 2>(L, stream) : launch_variant<32, 1>(L, stream);
+  CLPK_CHECK_CUDA(e);
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }

@@ -16,7 +16,9 @@ struct IgemmParams {
   int wbox, hbox;           // an M tile is a wbox x hbox patch of one image (wbox*hbox <= 128 rows)
   int tiles_w, tiles_h;
   int phases, taps, kpt;    // kpt = k-blocks per tap = cin / block_k
-  int num_tiles, stages, tmem_cols;
+  int num_tiles, stages, tmem_cols;   // num_tiles = work items: ceil(spatial tiles / ncta) * phases * n_tiles_n
+  int ncta;                 // 1, or 2 = CTA pairs (tcgen05 cta_group::2): two M tiles share one B tile split over the pair
+  int spatial_tiles;        // batch * tiles_h * tiles_w
   int op_f16;               // operand format: 1 = fp16, 0 = bf16
   int n_staging;            // epilogue staging buffers (128 rows x 128 B each) for the TMA-store path, 0 = direct stores
   int res_ahead;            // residual chunks the epilogue leader keeps in flight ahead of the one being processed
