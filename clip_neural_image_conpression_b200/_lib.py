@@ -16,6 +16,7 @@ MAX_LEVELS = 8
 CONV_3X3_S1 = 0
 CONV_3X3_S2 = 1
 CONVT_4X4_S2 = 2
+CONV_1X1 = 3
 
 OP_BF16 = 0
 OP_F16 = 1
@@ -76,6 +77,7 @@ SIGNATURES = {
     "clpk_pack_conv_weight": (_i64, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "clpk_conv_igemm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
     "clpk_conv_direct": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
+    "clpk_stem_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "clpk_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "clpk_plan_create": (_i, [C.POINTER(UnetConfig), _i, _i, _i, _i, C.POINTER(C.c_char_p), C.POINTER(_vp),
                               C.POINTER(_i64), C.POINTER(_vp)]),

@@ -543,7 +543,7 @@ __global__ void conv_direct_kernel(const uint16_t* __restrict__ x, const uint16_
 // Conv2d [Cout,Cin,3,3] -> [cout_pad][tap][Cin];  ConvTranspose2d [Cin,Cout,4,4] -> [phase][cout_pad][tap][Cin]
 __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int kind, int cin,
                                    int cout, int cout_pad, int op_f16) {
-  const int taps = (kind == CLPK_CONVT_4X4_S2) ? 4 : 9;
+  const int taps = (kind == CLPK_CONVT_4X4_S2) ? 4 : (kind == CLPK_CONV_1X1) ? 1 : 9;
   const int phases = (kind == CLPK_CONVT_4X4_S2) ? 4 : 1;
   const long long total = (long long)phases * cout_pad * taps * cin;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -563,7 +563,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __rest
         const int kh = ph + 1 - 2 * dh, kw = pw + 1 - 2 * dw;
         v = w[(((long long)c * cout + n) * 4 + kh) * 4 + kw];
       } else {
-        v = w[((long long)n * cin + c) * 9 + t];
+        v = w[((long long)n * cin + c) * taps + t];  // Conv2d [Cout,Cin,kh,kw] (3x3: taps 9; 1x1: taps 1)
       }
     }
     out[idx] = to_op(v, op_f16 != 0);
@@ -637,7 +637,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 
 int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, int h_in, int w_in, int cin, int cout,
                 int op_dtype, const clpk_conv_epilogue* ep, IgemmLaunch* out) {
-  CLPK_REQUIRE(kind >= 0 && kind <= 2, "conv kind %d unknown", kind);
+  CLPK_REQUIRE(kind >= 0 && kind <= 3, "conv kind %d unknown", kind);
   CLPK_REQUIRE(op_dtype == CLPK_OP_BF16 || op_dtype == CLPK_OP_F16, "operand dtype %d unknown", op_dtype);
   CLPK_REQUIRE(batch > 0 && h_in > 0 && w_in > 0, "bad conv geometry");
   CLPK_REQUIRE(cin % 32 == 0, "implicit-GEMM conv needs Cin %% 32 == 0 (got %d)", cin);
@@ -691,7 +691,11 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     p.a_dim_w = w_in / 2; p.a_dim_p = 2; p.a_dim_h = h_in / 2;
   } else {
     p.grid_h = h_in; p.grid_w = w_in;
-    if (kind == CLPK_CONV_3X3_S1) {
+    if (kind == CLPK_CONV_1X1) {
+      p.phases = 1; p.taps = 1;
+      p.out_h = h_in; p.out_w = w_in; p.out_scale = 1;
+      p.tap_dh[0] = 0; p.tap_dw[0] = 0;
+    } else if (kind == CLPK_CONV_3X3_S1) {
       p.phases = 1; p.taps = 9;
       p.out_h = h_in; p.out_w = w_in; p.out_scale = 1;
       for (int r = 0; r < 3; ++r)
@@ -855,12 +859,13 @@ using namespace clpk;
 
 extern "C" int64_t clpk_pack_conv_weight(const float* w_dev, void* out_bf16_dev, int kind, int cin, int cout,
                                          int op_dtype, void* stream) {
-  if (kind < 0 || kind > 2 || cin <= 0 || cout <= 0 || (op_dtype != CLPK_OP_BF16 && op_dtype != CLPK_OP_F16)) {
+  if (kind < 0 || kind > 3 || cin <= 0 || cout <= 0 || (op_dtype != CLPK_OP_BF16 && op_dtype != CLPK_OP_F16)) {
     set_error("clpk_pack_conv_weight: bad arguments");
     return -1;
   }
   const int cout_pad = igemm_cout_pad(cout);
-  const int taps = (kind == CLPK_CONVT_4X4_S2) ? 4 : 9, phases = (kind == CLPK_CONVT_4X4_S2) ? 4 : 1;
+  const int taps = (kind == CLPK_CONVT_4X4_S2) ? 4 : (kind == CLPK_CONV_1X1) ? 1 : 9;
+  const int phases = (kind == CLPK_CONVT_4X4_S2) ? 4 : 1;
   const long long total = (long long)phases * cout_pad * taps * cin;
   if (!out_bf16_dev) return total;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 65535);
@@ -876,7 +881,7 @@ extern "C" int64_t clpk_pack_conv_weight(const float* w_dev, void* out_bf16_dev,
 }
 
 extern "C" int clpk_conv_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg) {
-  if (kind < 0 || kind > 2 || h_in <= 0 || w_in <= 0 || cout <= 0) return 0;
+  if (kind < 0 || kind > 3 || h_in <= 0 || w_in <= 0 || cout <= 0) return 0;
   return igemm_gn_slots(kind, h_in, w_in, cout, gn_cpg);
 }
 

@@ -86,7 +86,74 @@ int launch_conv_in(const float* x, const float* w, const float* b, float* y, int
   return CLPK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ stem im2col
+// One thread per pixel: 27 (cin*9) neighbourhood values -> 32 16-bit columns = 64 contiguous bytes (4 x 16-byte stores).
+// Reads are coalesced along W within each (channel, row).
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ cols, int batch, int cin, int h, int wd, int f16) {
+  const long long npix = (long long)batch * h * wd;
+  const long long plane = (long long)h * wd;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(pix / plane);
+    const int rem = (int)(pix - (long long)b * plane);
+    const int yy = rem / wd, xx = rem - yy * wd;
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c < cin) {
+        const float* xp = x + ((long long)b * cin + c) * plane;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int iy = yy + r - 1;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int ix = xx + s - 1;
+            v[c * 9 + r * 3 + s] = (iy >= 0 && iy < h && ix >= 0 && ix < wd) ? __ldg(xp + (long long)iy * wd + ix) : 0.f;
+          }
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(cols + pix * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      dst[j] = make_uint4(pack_op2(v[8 * j + 0], v[8 * j + 1], f16 != 0), pack_op2(v[8 * j + 2], v[8 * j + 3], f16 != 0),
+                          pack_op2(v[8 * j + 4], v[8 * j + 5], f16 != 0), pack_op2(v[8 * j + 6], v[8 * j + 7], f16 != 0));
+  }
+}
+
+int launch_stem_im2col(const float* x, void* cols, int batch, int cin, int h, int wd, int op_dtype, cudaStream_t stream) {
+  CLPK_REQUIRE(cin >= 1 && cin * 9 <= 27, "stem im2col supports cin <= 3 (got %d)", cin);
+  const long long npix = (long long)batch * h * wd;
+  const int blocks = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 16);
+  stem_im2col_kernel<<<blocks, 256, 0, stream>>>(x, reinterpret_cast<uint16_t*>(cols), batch, cin, h, wd,
+                                                 op_dtype == CLPK_OP_F16);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+// [rows][k_src] fp32 -> [rows][k_dst] fp32, zero padded (stem weight [cout][cin*9] -> [cout][32])
+__global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int k_src, int k_dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * k_dst) return;
+  const int r = i / k_dst, k = i - r * k_dst;
+  dst[i] = (k < k_src) ? src[r * k_src + k] : 0.f;
+}
+int launch_pad_rows(const float* src, float* dst, int rows, int k_src, int k_dst, cudaStream_t stream) {
+  pad_rows_kernel<<<(rows * k_dst + 255) / 256, 256, 0, stream>>>(src, dst, rows, k_src, k_dst);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
 }  // namespace clpk
+
+extern "C" int clpk_stem_im2col(const float* x, void* cols, int batch, int cin, int h, int wd, int op_dtype,
+                                void* stream) {
+  CLPK_REQUIRE(x && cols && batch > 0 && h > 0 && wd > 0, "clpk_stem_im2col: bad arguments");
+  CLPK_REQUIRE(op_dtype == CLPK_OP_BF16 || op_dtype == CLPK_OP_F16, "clpk_stem_im2col: operand dtype %d unknown", op_dtype);
+  return clpk::launch_stem_im2col(x, cols, batch, cin, h, wd, op_dtype, (cudaStream_t)stream);
+}
 
 extern "C" int clpk_conv_in(const float* x, const float* w, const float* b, float* y, int batch, int cin, int h, int wd,
                             int cout, void* stream) {

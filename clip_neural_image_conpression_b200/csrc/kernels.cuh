@@ -45,4 +45,7 @@ int launch_gn_apply(const float* x, const float* gamma, const float* beta, const
 int launch_conv_in(const float* x_nchw, const float* w, const float* b, float* y_nhwc, int batch, int cin, int h, int w_,
                    int cout, cudaStream_t stream);
 
+int launch_stem_im2col(const float* x, void* cols, int batch, int cin, int h, int wd, int op_dtype, cudaStream_t stream);
+int launch_pad_rows(const float* src, float* dst, int rows, int k_src, int k_dst, cudaStream_t stream);
+
 }  // namespace clpk

@@ -57,7 +57,8 @@ struct clpk_plan {
   long long bytes = 0;
   // parameters
   float *tp0_w = nullptr, *tp0_b = nullptr, *tp2_w = nullptr, *tp2_b = nullptr, *zp_w = nullptr, *zp_b = nullptr;
-  float *in_w = nullptr, *in_b = nullptr;
+  ConvPlan stem;             // in_conv as im2col (K = 27 -> 32) + pointwise tcgen05 GEMM
+  uint16_t* stem_cols = nullptr;  // [B,H,W,32] 16-bit im2col columns
   GnPlan out_gn;
   float *film_w = nullptr, *film_b = nullptr;
   int film_n = 0;  // 2 * sum of ResBlock channels
@@ -254,7 +255,11 @@ int run_resblock(clpk_plan* P, ResBlockPlan& rb, cudaStream_t s) {
 // everything after the conditioning vector: in_conv ... out   (unet.py:88-105).  film = [B, film_n].
 int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s) {
   const clpk_unet_config& c = P->cfg;
-  CLPK_TIMED(P, kProfConvIn, s, launch_conv_in(x_nchw, P->in_w, P->in_b, P->X[0], P->B, c.img_ch, P->H, P->W, c.base, s));
+  P->prof_mark(kProfConvIn, s);  // stem (unet.py:88): im2col columns + pointwise GEMM on the tensor cores
+  int src = launch_stem_im2col(x_nchw, P->stem_cols, P->B, c.img_ch, P->H, P->W, c.op_dtype, s);
+  if (src == CLPK_OK) src = igemm_launch(P->stem.L, s);
+  P->prof_mark(-1, s);
+  if (src != CLPK_OK) return src;
   size_t r = 0;
   for (int l = 0; l < P->n_levels; ++l) {
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
@@ -334,8 +339,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   CLPK_TRY(copy_param(P, tab, "time_proj.2.bias", td, &P->tp2_b));
   CLPK_TRY(copy_param(P, tab, "z_proj.0.weight", (int64_t)td * cfg->z_dim, &P->zp_w));
   CLPK_TRY(copy_param(P, tab, "z_proj.0.bias", td, &P->zp_b));
-  CLPK_TRY(copy_param(P, tab, "in_conv.weight", (int64_t)cfg->base * cfg->img_ch * 9, &P->in_w));
-  CLPK_TRY(copy_param(P, tab, "in_conv.bias", cfg->base, &P->in_b));
+  CLPK_REQUIRE(cfg->img_ch * 9 <= 27, "img_ch > 3 is not supported by the stem im2col");
   P->out_gn.level = 0;
   P->out_gn.silu = 0;
   CLPK_TRY(copy_param(P, tab, "out_norm.weight", cfg->base, &P->out_gn.gamma));
@@ -412,7 +416,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     const int l = rb.level;
     CLPK_TRY(setup_gn(P, &rb.gn2, CLPK_CONV_3X3_S1, rb.h, rb.w));  // input = this block's conv1 output
     if (i == 0) {
-      CLPK_TRY(setup_gn(P, &rb.gn1, -1, 0, 0));                    // input = stem conv (CUDA-core kernel): own stats pass
+      CLPK_TRY(setup_gn(P, &rb.gn1, CLPK_CONV_1X1, rb.h, rb.w));   // input = stem conv (pointwise tcgen05 GEMM)
     } else if (specs[i - 1].level == l) {
       CLPK_TRY(setup_gn(P, &rb.gn1, CLPK_CONV_3X3_S1, rb.h, rb.w));
       gn_after_conv2[i - 1] = &rb.gn1;
@@ -481,6 +485,31 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     CLPK_TRY(bind_conv(P, &up, P->D, eu));
     P->flops_fwd += up.flops;
   }
+  // ---- stem: in_conv.weight [base, img_ch, 3, 3] = [base][27] -> zero-padded [base][32] -> packed pointwise weight
+  {
+    ConvPlan& st = P->stem;
+    st.kind = CLPK_CONV_1X1; st.cin = 32; st.cout = cfg->base; st.h_in = height; st.w_in = width;
+    const int k_src = cfg->img_ch * 9;
+    const float *w = nullptr, *b = nullptr;
+    CLPK_TRY(tab.get("in_conv.weight", (int64_t)cfg->base * k_src, &w));
+    CLPK_TRY(tab.get("in_conv.bias", cfg->base, &b));
+    float* wpad = nullptr;
+    CLPK_TRY(P->alloc(&wpad, (long long)cfg->base * 32));
+    CLPK_TRY(launch_pad_rows(w, wpad, cfg->base, k_src, 32, nullptr));
+    const int64_t n = clpk_pack_conv_weight(nullptr, nullptr, CLPK_CONV_1X1, 32, cfg->base, cfg->op_dtype, nullptr);
+    CLPK_TRY(P->alloc(&st.w, n));
+    if (clpk_pack_conv_weight(wpad, st.w, CLPK_CONV_1X1, 32, cfg->base, cfg->op_dtype, nullptr) < 0) return CLPK_ERR_CUDA;
+    CLPK_TRY(P->alloc(&st.bias, igemm_cout_pad(cfg->base)));
+    CLPK_CHECK_CUDA(cudaMemset(st.bias, 0, (size_t)igemm_cout_pad(cfg->base) * sizeof(float)));
+    CLPK_CHECK_CUDA(cudaMemcpy(st.bias, b, (size_t)cfg->base * sizeof(float), cudaMemcpyDeviceToDevice));
+    CLPK_TRY(P->alloc(&P->stem_cols, (long long)batch * height * width * 32));
+    clpk_conv_epilogue es{};
+    es.bias = st.bias;
+    es.out_f32 = P->X[0];
+    es.cout_valid = cfg->base;
+    wire_gn(&es, &P->rbs[0].gn1);
+    CLPK_TRY(bind_conv(P, &st, P->stem_cols, es));
+  }
   // ---- head
   CLPK_TRY(make_conv(P, tab, "out", CLPK_CONV_3X3_S1, cfg->base, cfg->img_ch, height, width, &P->out_conv));
   {
@@ -493,8 +522,8 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   }
   P->flops_fwd += 2.0 * batch * (double)height * width * cfg->base * cfg->img_ch * 9;  // in_conv
   P->flops_fwd += 2.0 * batch * ((double)td * 4 * td * 2 + (double)cfg->z_dim * td + (double)film_n * td);
-  // launches per forward: conditioning (5) + in_conv + per ResBlock (2 GN x 2 + 2 conv) + resamplers + out_norm(2) + out
-  P->launches_fwd = 5 + 1 + (int)P->rbs.size() * 6 + 2 * L + 2 + 1;
+  // launches per forward: conditioning (5) + stem (2) + per ResBlock (2 GN x 2 + 2 conv) + resamplers + out_norm(2) + out
+  P->launches_fwd = 5 + 2 + (int)P->rbs.size() * 6 + 2 * L + 2 + 1;
   CLPK_CHECK_CUDA(cudaDeviceSynchronize());
   guard.p = nullptr;
   *out_plan = P;

@@ -105,6 +105,8 @@ int clpk_groupnorm_apply(const float* x_nhwc_dev, const float* gamma_dev, const 
 #define CLPK_CONV_3X3_S1 0   /* Conv2d 3x3 stride 1 pad 1  (blocks.py:34,36; unet.py:79)   */
 #define CLPK_CONV_3X3_S2 1   /* Conv2d 3x3 stride 2 pad 1  (unet.py:63)                    */
 #define CLPK_CONVT_4X4_S2 2  /* ConvTranspose2d 4x4 stride 2 pad 1 (unet.py:75)            */
+#define CLPK_CONV_1X1 3      /* pointwise conv / plain GEMM over NHWC pixels: the stem conv (unet.py:55) runs as this
+                                over 32-wide im2col columns written by clpk_stem_im2col                          */
 
 /* Repack a reference-layout fp32 weight (Conv2d: [Cout,Cin,kh,kw]; ConvTranspose2d: [Cin,Cout,4,4]) into the 16-bit
  * K-major GEMM layout the tcgen05 kernel reads: Conv: [Cout_pad][tap][Cin]; ConvT: [phase(4)][Cout_pad][tap(4)][Cin].
@@ -149,7 +151,13 @@ int clpk_conv_igemm(const void* x_op_nhwc_dev, const void* w_packed_dev, int kin
 int clpk_conv_direct(const void* x_op_nhwc_dev, const void* w_packed_dev, int kind, int batch, int h_in, int w_in,
                      int cin, int cout, int op_dtype, const clpk_conv_epilogue* ep, void* stream);
 
-/* in_conv (unet.py:55,88): fp32 NCHW [B,cin,H,W] -> fp32 NHWC [B,H,W,cout], 3x3 s1 p1, fp32 arithmetic. */
+/* Stem im2col: fp32 NCHW [B,cin,H,W] (cin*9 <= 32) -> 16-bit NHWC [B,H,W,32] with column k = c*9 + r*3 + s holding
+ * x[b,c,h+r-1,w+s-1] (zero padded), columns >= cin*9 zero.  Feeds clpk_conv_igemm(kind = CLPK_CONV_1X1, cin = 32). */
+int clpk_stem_im2col(const float* x_nchw_dev, void* cols_op_dev, int batch, int cin, int h, int w, int op_dtype,
+                     void* stream);
+
+/* in_conv (unet.py:55,88) on the CUDA cores: fp32 NCHW [B,cin,H,W] -> fp32 NHWC [B,H,W,cout], 3x3 s1 p1, fp32
+ * arithmetic.  Kept as an exact-fp32 leaf op; the plan runs the stem on the tensor cores (im2col + CLPK_CONV_1X1). */
 int clpk_conv_in(const float* x_nchw_dev, const float* w_dev /*[cout,cin,3,3]*/, const float* b_dev, float* y_nhwc_dev,
                  int batch, int cin, int h, int w, int cout, void* stream);
 

@@ -137,6 +137,28 @@ def test_conv_in(ops):
         np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
 
 
+def test_stem_im2col_and_pointwise_conv(ops):
+    """The stem (unet.py:55) as the plan runs it: im2col (27 -> 32 columns, 16-bit) + CLPK_CONV_1X1 on the tensor cores."""
+    import ctypes as C
+    from clip_neural_image_conpression_b200 import _lib
+    g = torch.Generator().manual_seed(4)
+    b, h, w, cout = 2, 24, 40, 128
+    x = torch.randn(b, 3, h, w, generator=g).cuda()
+    wt = (torch.randn(cout, 3, 3, 3, generator=g) / 5).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    cols = torch.empty((b, h, w, 32), dtype=torch.float16, device="cuda")
+    _lib.check(_lib.load().clpk_stem_im2col(x.data_ptr(), cols.data_ptr(), b, 3, h, w, _lib.OP_F16, _lib.stream_ptr()), "im2col")
+    ref_cols = F.unfold(x, 3, padding=1).reshape(b, 27, h, w).permute(0, 2, 3, 1)          # k = c*9 + r*3 + s
+    assert torch.equal(cols[..., :27], ref_cols.to(torch.float16)) and torch.all(cols[..., 27:] == 0)
+    wpad = torch.zeros(cout, 32, 1, 1, device="cuda")
+    wpad[:, :27, 0, 0] = wt.reshape(cout, 27)
+    o = ops.conv_igemm(cols, ops.pack_conv_weight(wpad, _lib.CONV_1X1), _lib.CONV_1X1, cout, bias, gn_groups=8)
+    ref = F.conv2d(x.to(torch.float16).double(), wt.to(torch.float16).double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    assert float((o["f32"].double() - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+    exact = F.conv2d(x.double(), wt.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    assert float(torch.linalg.norm(o["f32"].double() - exact) / torch.linalg.norm(exact)) < 1e-3   # fp16 operand rounding
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core convs
 CONV_CASES = [
     # kind, B, H, W, Cin, Cout, film, resid
