@@ -195,21 +195,38 @@ def run_b200_arm(args):
     x_T_host = torch.randn(B, 3, S, S, generator=g).pin_memory()
     codes_host = codes_dev.cpu().pin_memory()
     out_host = torch.empty((B, S, S, 3), dtype=torch.uint8).pin_memory()
+    metric_host = torch.empty(2, dtype=torch.float64).pin_memory()
     x_T_dev = x_T_host.to(dev)
     sampler = DDIMSampler(NoiseScheduler(1000, "cosine", dev), eta=args.eta)
     sampler.use_graph = not args.no_graph
     stream = torch.cuda.current_stream()
 
+    # eval-style tail of every step (north-star: NCCL only AFTER the loop): PSNR vs a synthetic "original" on the device,
+    # then one gather of the uint8 reconstructions and one fp64 all-reduce of the metric sums
+    target = torch.tanh(torch.randn(B, 3, S, S, generator=g)).to(dev)
+    gathered = torch.empty((world * B, S, S, 3), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def finish(x):
+        u8 = ops.to_uint8_hwc(x)
+        sq = ops.psnr_sqerr_u8(x, target)
+        sums = torch.stack([sq.sum().double(), torch.tensor(float(B), dtype=torch.float64, device=dev)])
+        if world > 1:
+            torch.distributed.all_gather_into_tensor(gathered, u8)
+            torch.distributed.all_reduce(sums)
+        return u8, sums
+
     def step_resident():
         z = ops.dequant_l2norm(codes_dev, scale, zero)
         x = sampler.sample(net, z, (B, 3, S, S), steps=T, x_T=x_T_dev)
-        return ops.to_uint8_hwc(x)
+        return finish(x)[0]
 
     def step_e2e():
         x = decode_codes(net, sampler, codes_host.numpy(), scale, zero, S, steps=T, batch=B,
                          x_T=x_T_host.to(dev, non_blocking=True))
-        out_host.copy_(ops.to_uint8_hwc(x), non_blocking=True)
-        stream.synchronize()  # the user holds the images on the host when the call returns
+        u8, sums = finish(x)
+        out_host.copy_(u8, non_blocking=True)
+        metric_host.copy_(sums, non_blocking=True)
+        stream.synchronize()  # the user holds the images and the metric sums on the host when the call returns
 
     def timed(fn, k):
         parallel.barrier()
@@ -289,7 +306,7 @@ def run_b200_arm(args):
                        "l2": "per-step working set (>= 270 MB per activation tensor at batch 8) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(codes_host.numel() + x_T_host.numel() * 4),
-                    "d2h_bytes_per_step": int(out_host.numel())},
+                    "d2h_bytes_per_step": int(out_host.numel() + metric_host.numel() * 8)},
             "gpu_launches": launches,
             "unet_fwd_ms": sum(per_step_ms[c] for c in cls[:5]),
             "roofline": roofline, "roofline_hbm": roofline_hbm,
