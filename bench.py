@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--operand", choices=["f16", "bf16"], default="f16", help="tensor-core operand format")
+    ap.add_argument("--arch", choices=["default", "wide"], default="default",
+                    help="default: base=128 ch_mult=(1,2,2) z=512 (BASELINE configs[1-3]); wide: base=192 ch_mult=(1,2,2,4) z=768 (configs[4], use --size 512 --batch 16)")
     return ap.parse_args()
 
 
@@ -298,7 +300,7 @@ def run_b200_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.operand, "data": "synthetic",
-            "config": {"workload": f"DDIM-{T} {S}px default CLIPCondUNet base=128 ch_mult=(1,2,2), eta={args.eta}, "
+            "config": {"workload": f"DDIM-{T} {S}px {args.arch} CLIPCondUNet base={ARCH['base']} ch_mult={ARCH['ch_mult']}, eta={args.eta}, "
                                    f"batch {B} per GPU, {'CUDA-graph' if sampler.use_graph else 'eager'} step loop",
                        "batch_per_gpu": B, "global_batch": B * world, "ddim_steps": T, "z_dim": ARCH["z_dim"],
                        "weights": "random init (seed 0), out.* x0.1",
@@ -322,6 +324,8 @@ def run_b200_arm(args):
 
 def main():
     args = parse_args()
+    if args.arch == "wide":
+        ARCH.update(z_dim=768, base=192, ch_mult=(1, 2, 2, 4))
     if args.impl == "reference":
         run_reference_arm(args)
     else:

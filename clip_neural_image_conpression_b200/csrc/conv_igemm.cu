@@ -215,7 +215,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
         const TileCoord tc = decode_tile(p, tile, (int)rank);
         const int w_row = tc.phase * p.cout_pad + tc.n0 + (int)rank * b_rows;
-        if (p.ep.resid && p.n_staging > 0 && tc.ok && elect_one()) {
+        if (p.ep.resid && p.chunked && tc.ok && elect_one()) {
           // the epilogue will add this residual tile: pull it into L2 while the MMAs run
           for (int c = 0; c < p.block_n; c += 32)
             tma_prefetch_5d(&maps_res.m[tc.phase], tc.n0 + c, tc.w0, 0, tc.h0, tc.b);
@@ -323,7 +323,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     int cached_key = -1;
     // Residual chunks are TMA-loaded straight into the staging slot that will later be stored from (read-modify-write in
     // place).  The leader keeps `res_ahead` chunks in flight; (ld_tile, ld_c, ld_g) is its load cursor.
-    const bool res_tma = (p.n_staging > 0) && (ep.resid != nullptr);
+    const bool res_tma = p.chunked && (ep.resid != nullptr);
+    const bool st_f32 = p.chunked && (ep.out_f32 != nullptr);  // fp32 output goes through the staging slots + TMA store
     const uint32_t res_bytes = (uint32_t)(p.wbox * p.hbox) * 128u;
     int ld_tile = cluster_id, ld_c = 0;
     uint32_t ld_g = 0;
@@ -351,8 +352,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const long long opix = ((long long)tc.b * p.out_h + oh) * p.out_w + ow;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.block_n);
 
-      if (p.n_staging > 0) {
-        // ------------------------------------------------ staged path: TMEM -> regs -> swizzled smem -> TMA store
+      if (p.chunked) {
+        // ------------------------------------------------ chunked path: TMEM -> regs -> swizzled smem -> TMA store
         const int vb = tc.ok ? tc.b : 0;  // a masked tile still runs the (uniform) protocol, on image 0's vectors
         const int key = vb * 4096 + tc.n0;
         if (key != cached_key) {  // (image, channel-tile) changed: refresh the folded bias / FiLM vectors
@@ -372,7 +373,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         mbar_wait(&bars->tmem_full[as], aphase);
         tc_fence_after();
         for (int c = 0; c < p.block_n; c += 32, ++gchunk) {
-          const uint32_t slot = gchunk % (uint32_t)p.n_staging;
+          const uint32_t slot = p.n_staging > 0 ? gchunk % (uint32_t)p.n_staging : 0u;
           uint8_t* sbuf = smem_s + (size_t)slot * kStagingBytes;
           uint32_t r[32];
           __syncwarp();
@@ -410,10 +411,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               else if (cpg == 8) gn_chunk_partials<4>(v, valid, lane, redw);
               else gn_chunk_partials<8>(v, valid, lane, redw);
             }
+            if (st_f32) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4)
-              *reinterpret_cast<float4*>(srow + ((j4 ^ (row & 7)) << 4)) =
-                  make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+              for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4*>(srow + ((j4 ^ (row & 7)) << 4)) =
+                    make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+            }
             if (ep.out_op && valid) {
               uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out_op) + opix * ldc + tc.n0 + c);
 #pragma unroll
@@ -422,8 +425,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                     pack_op2(v[8 * j8 + 4], v[8 * j8 + 5], f16), pack_op2(v[8 * j8 + 6], v[8 * j8 + 7], f16));
             }
           }
-          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-          if (leader) {
+          if (st_f32) fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          if (leader && p.n_staging > 0) {
             // Slot reuse.  Before the barrier of chunk g the stores of chunks <= g-1 are committed.  The slot that is
             // touched next — by the generic writes of chunk g+1 (no residual) or by the residual load of chunk g+A —
             // was last stored from by chunk g+1-S resp. g+A-S, so at most S-2 resp. S-A-1 groups may stay pending.
@@ -432,7 +435,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (res_tma && !(p.dbg & 1)) issue_res_load();
           }
           named_bar_sync(1, 128);
-          if (leader && !(p.dbg & 1)) {
+          if (leader && st_f32 && !(p.dbg & 1)) {
             tma_store_5d(&maps_out.m[tc.phase], sbuf, tc.n0 + c, tc.w0, 0, tc.h0, tc.b);
             bulk_commit_group();
           }
@@ -486,7 +489,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         else mbar_arrive(&bars->tmem_empty[as]);
       }
     }
-    if (leader && p.n_staging > 0) bulk_wait_group_all();  // all stores retired before smem goes away
+    if (leader && st_f32) bulk_wait_group_all();  // all stores retired before smem goes away
   }
 
   tc_fence_before();
@@ -730,22 +733,24 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
   const int stage_bytes = kTileM * p.block_k * 2 + (p.block_n / p.ncta) * p.block_k * 2;
-  // staged (TMA-store) epilogue whenever there is an fp32 NHWC output of >= 32 channels per tile
-  const bool staged = p.ep.out_f32 != nullptr && p.block_n % 32 == 0 && cout % 32 == 0 &&
-                      (reinterpret_cast<uintptr_t>(p.ep.out_f32) & 15) == 0;
+  // chunked epilogue whenever the tile has >= 32 channels and an NHWC output; its fp32 output (if any) is staged
+  // through smem and written by TMA, a 16-bit output is stored directly from registers
+  const bool f32_ok = p.ep.out_f32 != nullptr && (reinterpret_cast<uintptr_t>(p.ep.out_f32) & 15) == 0;
+  p.chunked = (p.block_n % 32 == 0 && cout % 32 == 0 && (f32_ok || (p.ep.out_op && !p.ep.out_f32)) && !p.ep.out_nchw) ? 1 : 0;
   const int fixed = 1024 /*alignment slack*/ + epi_vector_bytes(p.block_n) + (int)sizeof(PipeBarriers) + 16;
   p.n_staging = 0;
-  if (staged) {
+  if (p.chunked && (p.ep.out_f32 || p.ep.resid)) {
+    CLPK_REQUIRE(p.ep.out_f32 != nullptr, "a residual input needs the fp32 output");
     p.n_staging = ((kSmemBudget - fixed - 3 * kStagingBytes) / stage_bytes >= 4 ||
                    (kSmemBudget - fixed - 3 * kStagingBytes) / stage_bytes == (kSmemBudget - fixed - 2 * kStagingBytes) / stage_bytes)
                       ? 3 : 2;
-    if ((kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes < 2) p.n_staging = 0;
+    if ((kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes < 2) { p.n_staging = 0; p.chunked = 0; }
   }
   p.gn_groups = p.gn_slots = 0;
   p.gn_sub = 1;
   if (p.ep.gn_partial) {
     p.gn_slots = igemm_gn_slots(kind, h_in, w_in, cout, p.ep.gn_cpg);
-    CLPK_REQUIRE(p.gn_slots > 0 && p.n_staging > 0,
+    CLPK_REQUIRE(p.gn_slots > 0 && p.chunked,
                  "fused GroupNorm statistics unsupported for this conv (cout=%d cpg=%d)", cout, p.ep.gn_cpg);
     p.gn_groups = cout / p.ep.gn_cpg;
     p.gn_sub = p.ep.gn_cpg >= 32 ? p.ep.gn_cpg / 32 : 1;
@@ -772,7 +777,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   // fp32 NHWC output maps for the TMA-store epilogue: [C, Wgrid, 1, Hgrid, B] per phase (transposed conv: the phase
   // (ph,pw) owns output pixels (2h+ph, 2w+pw) -> base offset + doubled w/h strides)
   memset(&out->maps_out, 0, sizeof(out->maps_out));
-  if (p.n_staging > 0) {
+  if (p.chunked && p.ep.out_f32) {
     const long long CO = cout, OW = p.out_w, OH = p.out_h, sc = p.out_scale;
     cuuint64_t odims[5] = {(cuuint64_t)CO, (cuuint64_t)p.grid_w, 1, (cuuint64_t)p.grid_h, (cuuint64_t)batch};
     cuuint64_t ostr[4] = {(cuuint64_t)(sc * CO * 4), (cuuint64_t)(sc * OW * CO * 4), (cuuint64_t)(sc * OW * CO * 4),

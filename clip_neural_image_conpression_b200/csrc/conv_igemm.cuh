@@ -20,6 +20,8 @@ struct IgemmParams {
   int ncta;                 // 1, or 2 = CTA pairs (tcgen05 cta_group::2): two M tiles share one B tile split over the pair
   int spatial_tiles;        // batch * tiles_h * tiles_w
   int op_f16;               // operand format: 1 = fp16, 0 = bf16
+  int chunked;              // 1: chunked epilogue (32 columns at a time: folded vectors, fused GN stats, staged TMA store of
+                            // the fp32 output if there is one); 0: narrow direct path (the 3-channel `out` conv)
   int n_staging;            // epilogue staging buffers (128 rows x 128 B each) for the TMA-store path, 0 = direct stores
   int res_ahead;            // residual chunks the epilogue leader keeps in flight ahead of the one being processed
   int gn_groups, gn_slots, gn_sub;  // fused GroupNorm statistics: groups, partial slots per image, chunks per group slot

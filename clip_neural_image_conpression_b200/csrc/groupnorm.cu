@@ -133,31 +133,72 @@ gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float
   }
 }
 
-// y = (x - mean) * rstd * gamma + beta, optional SiLU, 8 channels (32 B in, 16 B out) per thread iteration.
+// y = (x - mean) * rstd * gamma + beta, optional SiLU, 8 channels per thread iteration (32 B fp32 or 16 B 16-bit in,
+// 16 B out).  Statistics come either from `stats` (mean, rstd) or — when `partial` is given — are folded in-kernel from
+// the per-tile partial sums a conv epilogue wrote (same fixed-order fp64 fold as gn_finalize_kernel, one warp per
+// group, redundantly per block: a few KB of L2 reads instead of a separate launch).
+template <bool kIn16>
 __global__ void __launch_bounds__(kGnThreads)
-gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float2* __restrict__ stats, uint16_t* __restrict__ y, int hw, int c, int groups, int silu,
-                int op_f16) {
+gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float2* __restrict__ stats, const float2* __restrict__ partial, int slots, double n_per_group,
+                float eps, uint16_t* __restrict__ y, int hw, int c, int groups, int silu, int op_f16) {
+  __shared__ float2 st_s[32];
   const bool f16 = op_f16 != 0;
   const int b = blockIdx.y;
+  if (partial) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < groups; g += kGnThreads / 32) {
+      const float2* pp = partial + (long long)b * slots * groups + g;
+      double S = 0.0, SS = 0.0;
+      for (int k = lane; k < slots; k += 32) {
+        const float2 v = __ldg(pp + (long long)k * groups);
+        S += (double)v.x; SS += (double)v.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        SS += __shfl_xor_sync(0xffffffffu, SS, o);
+      }
+      if (lane == 0) {
+        const double mean = S / n_per_group;
+        double var = SS / n_per_group - mean * mean;
+        if (var < 0.0) var = 0.0;
+        st_s[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+      }
+    }
+  } else {
+    if (threadIdx.x < groups) st_s[threadIdx.x] = stats[(long long)b * groups + threadIdx.x];
+  }
+  __syncthreads();
   const unsigned oc = (unsigned)c >> 3;  // 8-channel octets per pixel
   const int cpg = c / groups;
   const unsigned total = (unsigned)hw * oc;
-  const float4* xb = reinterpret_cast<const float4*>(x) + (long long)b * total * 2;
   uint4* yb = reinterpret_cast<uint4*>(y) + (long long)b * total;
-  const float2* st = stats + (long long)b * groups;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const unsigned o = i % oc;
     const int ch = (int)o * 8;
-    const float4 v0 = __ldcs(xb + 2ll * i), v1 = __ldcs(xb + 2ll * i + 1);
+    float v[8];
+    if (kIn16) {
+      const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(xin) + (long long)b * total + i);
+      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[2 * k] = from_op((uint16_t)(w4[k] & 0xffffu), f16);
+        v[2 * k + 1] = from_op((uint16_t)(w4[k] >> 16), f16);
+      }
+    } else {
+      const float4* xb = reinterpret_cast<const float4*>(xin) + (long long)b * total * 2;
+      const float4 v0 = __ldcs(xb + 2ll * i), v1 = __ldcs(xb + 2ll * i + 1);
+      v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+    }
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch) + 1);
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch) + 1);
-    const float2 s0 = __ldg(st + ch / cpg), s1 = __ldg(st + (ch + 4) / cpg);
+    const float2 s0 = st_s[ch / cpg], s1 = st_s[(ch + 4) / cpg];
     float r[8];
-    r[0] = (v0.x - s0.x) * s0.y * g0.x + b0.x; r[1] = (v0.y - s0.x) * s0.y * g0.y + b0.y;
-    r[2] = (v0.z - s0.x) * s0.y * g0.z + b0.z; r[3] = (v0.w - s0.x) * s0.y * g0.w + b0.w;
-    r[4] = (v1.x - s1.x) * s1.y * g1.x + b1.x; r[5] = (v1.y - s1.x) * s1.y * g1.y + b1.y;
-    r[6] = (v1.z - s1.x) * s1.y * g1.z + b1.z; r[7] = (v1.w - s1.x) * s1.y * g1.w + b1.w;
+    r[0] = (v[0] - s0.x) * s0.y * g0.x + b0.x; r[1] = (v[1] - s0.x) * s0.y * g0.y + b0.y;
+    r[2] = (v[2] - s0.x) * s0.y * g0.z + b0.z; r[3] = (v[3] - s0.x) * s0.y * g0.w + b0.w;
+    r[4] = (v[4] - s1.x) * s1.y * g1.x + b1.x; r[5] = (v[5] - s1.x) * s1.y * g1.y + b1.y;
+    r[6] = (v[6] - s1.x) * s1.y * g1.z + b1.z; r[7] = (v[7] - s1.x) * s1.y * g1.w + b1.w;
     if (silu) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) r[k] = silu_f(r[k]);
@@ -201,19 +242,31 @@ int launch_gn_finalize(const float2* partial, float2* stats, int batch, int slot
   return CLPK_OK;
 }
 
-int launch_gn_apply(const float* x, const float* gamma, const float* beta, const float2* stats, void* y_op,
-                    const GnShape& s, int silu, int op_dtype, cudaStream_t stream) {
+// x: fp32 NHWC (x_is_16 == 0) or 16-bit NHWC in the operand format.  Exactly one of stats / partial is used.
+int launch_gn_apply_ex(const void* x, int x_is_16, const float* gamma, const float* beta, const float2* stats,
+                       const float2* partial, int slots, double n_per_group, float eps, void* y_op, const GnShape& s,
+                       int silu, int op_dtype, cudaStream_t stream) {
   const long long octs = (long long)s.hw * (s.c / 8);
   CLPK_REQUIRE(s.c % 8 == 0 && s.c % s.groups == 0 && (s.c / s.groups) % 4 == 0,
                "GroupNorm needs C %% 8 == 0 and (C/groups) %% 4 == 0 (C=%d groups=%d)", s.c, s.groups);
-  CLPK_REQUIRE(octs < (1ll << 31), "image too large for GroupNorm indexing");
+  CLPK_REQUIRE(octs < (1ll << 31) && s.groups <= 32, "GroupNorm: image too large or too many groups");
   const int per_img_blocks = (int)std::min<long long>((octs + kGnThreads - 1) / kGnThreads,
                                                       std::max(1, num_sms() * 8 / s.batch));
   dim3 agrid(std::max(per_img_blocks, 1), s.batch);
-  gn_apply_kernel<<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, reinterpret_cast<uint16_t*>(y_op), s.hw, s.c,
-                                                   s.groups, silu, op_dtype == CLPK_OP_F16);
+  uint16_t* y = reinterpret_cast<uint16_t*>(y_op);
+  if (x_is_16)
+    gn_apply_kernel<true><<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, partial, slots, n_per_group, eps, y, s.hw,
+                                                            s.c, s.groups, silu, op_dtype == CLPK_OP_F16);
+  else
+    gn_apply_kernel<false><<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, partial, slots, n_per_group, eps, y,
+                                                             s.hw, s.c, s.groups, silu, op_dtype == CLPK_OP_F16);
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
+}
+
+int launch_gn_apply(const float* x, const float* gamma, const float* beta, const float2* stats, void* y_op,
+                    const GnShape& s, int silu, int op_dtype, cudaStream_t stream) {
+  return launch_gn_apply_ex(x, 0, gamma, beta, stats, nullptr, 0, 1.0, 0.f, y_op, s, silu, op_dtype, stream);
 }
 
 // statistics pass only: leaves (mean, rstd) in the stats area of ws (see layout above) and returns its address

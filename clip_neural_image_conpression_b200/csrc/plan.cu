@@ -3,7 +3,8 @@
 //
 // HBM layout (all plan-owned, sized for the plan's fixed batch B and image size):
 //   X[l]  fp32 NHWC  residual stream of resolution level l (l = 0 .. n_levels); X[l] doubles as the skip tensor
-//   Y     fp32 NHWC  conv1 output of the current ResBlock (max size over levels)
+//   Y     16-bit NHWC conv1 output of the current ResBlock (max size over levels); its GroupNorm statistics are taken
+//         from the fp32 accumulators in the conv1 epilogue, only the stored copy is rounded
 //   T     bf16 NHWC  GroupNorm+SiLU output = A operand of the ResBlock convs (max size)
 //   D     bf16 NHWC  bf16 copy of x feeding the stride-2 / transposed convs (max size)
 //   packed bf16 weights [Cout][tap][Cin] per conv, fp32 bias / gamma / beta / Linear weights, FiLM weights of all
@@ -12,6 +13,7 @@
 #include "kernels.cuh"
 
 #include <map>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -42,6 +44,7 @@ struct ResBlockPlan {
   ConvPlan conv1, conv2;
   int film_off = 0;      // scale1p at [film_off, film_off+c), shift at [film_off+c, film_off+2c)
   bool emit_bf16 = false;  // conv2 also writes a bf16 copy of x into D (feeds the next resampling conv)
+  bool y16 = false;        // conv1 output kept in the 16-bit operand format (needs fused GroupNorm statistics)
 };
 
 }  // namespace clpk
@@ -67,8 +70,9 @@ struct clpk_plan {
   ConvPlan out_conv;
   // workspace
   std::vector<float*> X;
-  float* Y = nullptr;
+  uint16_t* Y = nullptr;     // conv1 output of the current ResBlock, stored in the 16-bit operand format
   uint16_t *T = nullptr, *D = nullptr;  // 16-bit operand buffers (fp16 or bf16, cfg.op_dtype)
+  float* Yf = nullptr;       // fp32 conv1 output, only for ResBlocks whose GroupNorm statistics cannot be fused
   void* gn_ws = nullptr;
   float *temb = nullptr, *h1 = nullptr, *ht = nullptr, *hcond = nullptr, *film = nullptr, *zemb = nullptr;
   int64_t* t_buf = nullptr;
@@ -226,28 +230,31 @@ int setup_gn(clpk_plan* P, GnPlan* gn, int producer_kind, int prod_h_in, int pro
   return CLPK_OK;
 }
 
-int run_groupnorm(clpk_plan* P, const float* x, const GnPlan& gn, cudaStream_t s) {
+int run_groupnorm(clpk_plan* P, const void* x, int x_is_16, const GnPlan& gn, cudaStream_t s) {
   const int level = gn.level, groups = gn_groups_of(P, level);
   const int hw = P->lv_h[level] * P->lv_w[level], c = P->lv_c[level];
   const GnShape shp = gn_shape(P->B, hw, c, groups);
-  const float2* stats = gn.stats;
   P->prof_mark(kProfGroupNorm, s);
   int rc;
   if (gn.fused) {
-    rc = launch_gn_finalize(gn.partial, gn.stats, P->B, gn.slots, groups, (double)hw * (c / groups), 1e-5f, s);
+    // statistics come from the producing conv's epilogue partials and are folded inside the apply kernel
+    rc = launch_gn_apply_ex(x, x_is_16, gn.gamma, gn.beta, nullptr, gn.partial, gn.slots, (double)hw * (c / groups), 1e-5f,
+                            P->T, shp, gn.silu, P->cfg.op_dtype, s);
   } else {
-    rc = launch_gn_stats(x, P->gn_ws, shp, 1e-5f, &stats, s);
+    const float2* stats = nullptr;
+    rc = x_is_16 ? CLPK_ERR_STATE : launch_gn_stats(reinterpret_cast<const float*>(x), P->gn_ws, shp, 1e-5f, &stats, s);
+    if (rc == CLPK_OK)
+      rc = launch_gn_apply_ex(x, 0, gn.gamma, gn.beta, stats, nullptr, 0, 1.0, 0.f, P->T, shp, gn.silu, P->cfg.op_dtype, s);
   }
-  if (rc == CLPK_OK) rc = launch_gn_apply(x, gn.gamma, gn.beta, stats, P->T, shp, gn.silu, P->cfg.op_dtype, s);
   P->prof_mark(-1, s);
   return rc;
 }
 
 int run_resblock(clpk_plan* P, ResBlockPlan& rb, cudaStream_t s) {
   float* X = P->X[rb.level];
-  CLPK_TRY(run_groupnorm(P, X, rb.gn1, s));                        // blocks.py:41 act(norm1(x))
+  CLPK_TRY(run_groupnorm(P, X, 0, rb.gn1, s));                     // blocks.py:41 act(norm1(x))
   CLPK_TIMED(P, kProfConvRes, s, igemm_launch(rb.conv1.L, s));     // conv1 + FiLM -> Y   (blocks.py:41-42)
-  CLPK_TRY(run_groupnorm(P, P->Y, rb.gn2, s));                     // blocks.py:43 act(norm2(y))
+  CLPK_TRY(run_groupnorm(P, rb.y16 ? (const void*)P->Y : (const void*)P->Yf, rb.y16 ? 1 : 0, rb.gn2, s));  // blocks.py:43
   CLPK_TIMED(P, kProfConvRes, s, igemm_launch(rb.conv2.L, s));     // conv2 + x -> X      (blocks.py:43-44)
   return CLPK_OK;
 }
@@ -273,7 +280,7 @@ int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s) {
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
     CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->ups[l].L, s));  // D (bf16 of X[l+1]) -> X[l] += convT (unet.py:102-104)
   }
-  CLPK_TRY(run_groupnorm(P, P->X[0], P->out_gn, s));               // out_norm, no activation (unet.py:105)
+  CLPK_TRY(run_groupnorm(P, P->X[0], 0, P->out_gn, s));            // out_norm, no activation (unet.py:105)
   CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->out_conv.L, s));  // -> eps_buf (NCHW)
   return CLPK_OK;
 }
@@ -375,6 +382,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     P->X.push_back(x);
   }
   CLPK_TRY(P->alloc(&P->Y, max_act));
+  CLPK_TRY(P->alloc(&P->Yf, max_act));
   CLPK_TRY(P->alloc(&P->T, max_act));
   CLPK_TRY(P->alloc(&P->D, max_act));
   long long gn_bytes = 0;
@@ -443,7 +451,8 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     e1.film_scale1p = P->film + rb.film_off;
     e1.film_shift = P->film + rb.film_off + rb.c;
     e1.film_stride = film_n;
-    e1.out_f32 = P->Y;
+    rb.y16 = rb.gn2.fused && !getenv("CLPK_Y_FP32");
+    if (rb.y16) e1.out_op = P->Y; else e1.out_f32 = P->Yf;
     e1.cout_valid = rb.c;
     wire_gn(&e1, &rb.gn2);
     CLPK_TRY(bind_conv(P, &rb.conv1, P->T, e1));
@@ -523,7 +532,9 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   P->flops_fwd += 2.0 * batch * (double)height * width * cfg->base * cfg->img_ch * 9;  // in_conv
   P->flops_fwd += 2.0 * batch * ((double)td * 4 * td * 2 + (double)cfg->z_dim * td + (double)film_n * td);
   // launches per forward: conditioning (5) + stem (2) + per ResBlock (2 GN x 2 + 2 conv) + resamplers + out_norm(2) + out
-  P->launches_fwd = 5 + 2 + (int)P->rbs.size() * 6 + 2 * L + 2 + 1;
+  P->launches_fwd = 5 + 2 + (int)P->rbs.size() * 2 + 2 * L + 1;  // + one or two launches per GroupNorm:
+  for (const ResBlockPlan& rb : P->rbs) P->launches_fwd += (rb.gn1.fused ? 1 : 2) + (rb.gn2.fused ? 1 : 2);
+  P->launches_fwd += P->out_gn.fused ? 1 : 2;
   CLPK_CHECK_CUDA(cudaDeviceSynchronize());
   guard.p = nullptr;
   *out_plan = P;

@@ -137,6 +137,22 @@ def test_conv_in(ops):
         np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
 
 
+def test_conv_16bit_only_output_with_fused_statistics(ops):
+    """conv1 of a ResBlock as the plan runs it: FiLM epilogue, output kept ONLY in the 16-bit operand format, GroupNorm
+    statistics taken from the fp32 accumulators."""
+    g = torch.Generator().manual_seed(3)
+    b, h, w, c = 2, 32, 32, 128
+    xb = torch.randn(b, h, w, c, generator=g).to(torch.float16).cuda()
+    wt = (torch.randn(c, c, 3, 3, generator=g) * 0.03).cuda()
+    bias = torch.randn(c, generator=g).cuda()
+    sc, sh = (1 + 0.3 * torch.randn(b, c, generator=g)).cuda(), torch.randn(b, c, generator=g).cuda()
+    wp = ops.pack_conv_weight(wt, 0)
+    full = ops.conv_igemm(xb, wp, 0, c, bias, film_scale1p=sc, film_shift=sh, want_f32=True, want_op=True, gn_groups=8)
+    only = ops.conv_igemm(xb, wp, 0, c, bias, film_scale1p=sc, film_shift=sh, want_f32=False, want_op=True, gn_groups=8)
+    assert "f32" not in only and torch.equal(only["op"], full["op"]) and torch.equal(only["gn_stats"], full["gn_stats"])
+    assert torch.equal(only["op"], full["f32"].to(torch.float16))          # round-to-nearest-even of the fp32 result
+
+
 def test_stem_im2col_and_pointwise_conv(ops):
     """The stem (unet.py:55) as the plan runs it: im2col (27 -> 32 columns, 16-bit) + CLPK_CONV_1X1 on the tensor cores."""
     import ctypes as C

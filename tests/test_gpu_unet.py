@@ -191,3 +191,54 @@ def test_default_architecture_full_size_properties(oracle):
     with torch.no_grad():
         ref = oracle.ddim_sample(lambda xx, zc, tt: oracle.unet_forward(sd_cu, cfg["ch_mult"], xx, zc, tt), tabs, z, x_T, steps=10)
     assert oracle.psnr_float(out, ref) >= PSNR_BAR
+
+
+def test_wide_architecture_reduced_resolution(oracle):
+    """BASELINE configs[4] architecture (base=192, ch_mult=(1,2,2,4), 768-d CLIP ViT-L/14 vectors; channels
+    192/384/768/3072) at 32 px so the fp32 oracle stays cheap: exercises N = 192 tiles, GroupNorm groups of 24/48
+    channels (separate statistics pass), 96/384 channels (fused), 12 channel tiles per conv, 2x2-pixel bottom level."""
+    cfg = dict(z_dim=768, base=192, ch_mult=(1, 2, 2, 4))
+    net, sd = make_net(oracle, cfg, seed=31, out_gain=0.1)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 32, 32, generator=g).cuda()
+    z = torch.nn.functional.normalize(torch.randn(2, 768, generator=g), dim=-1).cuda()
+    t = torch.tensor([999, 123]).cuda()
+    eps = net(x, z, t)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd_cu = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = oracle.unet_forward(sd_cu, cfg["ch_mult"], x, z, t)
+    for b in range(2):
+        assert oracle.rel_l2(eps[b], ref[b]) < EPS_TOL, (b, oracle.rel_l2(eps[b], ref[b]))
+    del net, sd_cu
+    torch.cuda.empty_cache()
+
+
+def test_ddim_250_steps_stochastic_graph_loop(oracle, golden):
+    """BASELINE configs[3] loop shape (250 steps, eta = 1.0, graph replay) on the small net: the reference's eta = 1
+    output is all-NaN and so is ours; eta = 1e-3 walks the same 250 unique timesteps with finite values and
+    matches the oracle fed with the same pre-drawn noise."""
+    g = golden("ddim")
+    z, x_T = cu(g["z"]), cu(g["x_T"])
+    net, sd = make_net(oracle, TINY, seed=0, out_gain=0.1)
+    xn = _sampler(1.0).sample(net, z, (2, 3, 64, 64), steps=250, x_T=x_T)
+    assert bool(torch.isnan(xn).all())
+    noise = torch.randn(250, 2, 3, 64, 64, generator=torch.Generator().manual_seed(8))
+    tr = {}
+    x = _sampler(1e-3).sample(net, z, (2, 3, 64, 64), steps=250, x_T=x_T, noise=noise.cuda(), trace=tr)
+    assert torch.isfinite(x).all()
+    tabs = oracle.scheduler_tables(1000, "cosine")
+    ref = {}
+    with torch.no_grad():
+        oracle.ddim_sample(lambda xx, zc, t: oracle.unet_forward(sd, (1, 2), xx, zc, t), tabs, z.cpu(), x_T.cpu(),
+                           steps=250, eta=1e-3, noise=noise, trace=ref)
+    # a 250-step closed loop amplifies any epsilon difference chaotically (the reference's own fp64-vs-fp32 runs diverge,
+    # SURVEY 0.5), so: closed loop over the first 10 steps, then teacher-forced epsilon on the oracle's own trajectory
+    assert oracle.psnr_float(tr["x"][10].cpu(), ref["x"][10]) >= PSNR_BAR
+    ts = oracle.ddim_timesteps(1000, 250)
+    assert len(set(ts.tolist())) == 250
+    for i in (11, 60, 125, 200, 249):
+        t_b = torch.full((2,), int(ts[i]), dtype=torch.long).cuda()
+        e = net(ref["x"][i].cuda(), z, t_b).cpu()
+        assert oracle.rel_l2(e, ref["eps"][i]) < EPS_TOL, (i, oracle.rel_l2(e, ref["eps"][i]))
