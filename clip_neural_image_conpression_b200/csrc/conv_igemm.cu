@@ -23,7 +23,8 @@
 
 namespace clpk {
 
-constexpr int kNumThreads = 192;
+constexpr int kEpiGroups = 2;                       // epilogue warp groups (4 warps each) alternating 32-column chunks
+constexpr int kNumThreads = 64 + 128 * kEpiGroups;   // warp 0 TMA, warp 1 MMA, then the epilogue groups
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 232448;  // 227 KB
@@ -33,7 +34,8 @@ struct __align__(8) PipeBarriers {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t res_full[4];  // residual chunk landed in staging slot s
+  uint64_t res_full[kEpiGroups][4];   // residual chunk landed in staging slot s of the group
+  uint64_t slot_free[kEpiGroups][4];  // the TMA store that last read staging slot s has finished reading it
   uint32_t tmem_base;
 };
 
@@ -65,9 +67,9 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int item,
 struct EpiVectors {       // laid out in smem as: float mul[block_n] | float add[block_n] | float2 red[2][4][8]
   float* mul;
   float* add;
-  float2 (*red)[4][8];    // fused GN statistics: [chunk parity][epilogue warp][group pair] partial (sum, sumsq)
+  float2 (*red)[4][8];    // fused GN statistics: [epilogue group * 2 + chunk parity][warp][group pair] partial (sum, sumsq)
 };
-constexpr int kRedBytes = 2 * 4 * 8 * (int)sizeof(float2);
+constexpr int kRedBytes = kEpiGroups * 2 * 4 * 8 * (int)sizeof(float2);
 static inline int epi_vector_bytes(int block_n) { return 2 * 4 * block_n + kRedBytes; }
 
 constexpr int kStagingBytes = kTileM * 128;
@@ -188,9 +190,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
-      mbar_init(&bars->tmem_empty[s], 4 * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&bars->tmem_empty[s], 4 * kEpiGroups * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&bars->res_full[s], 1);
+    for (int g = 0; g < kEpiGroups; ++g)
+      for (int s = 0; s < 4; ++s) { mbar_init(&bars->res_full[g][s], 1); mbar_init(&bars->slot_free[g][s], 1); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -309,38 +312,50 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else {
     // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
+    // kEpiGroups groups of 4 warps; group eg owns the 32-column chunks with (chunk index % kEpiGroups) == eg, its own
+    // staging slots, barriers and named barrier, so two chunks are in flight per CTA and every scheduler has two
+    // epilogue warps to hide TMEM / shuffle / smem latencies.
+    const int eg = (warp - 2) >> 2;          // epilogue group
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int hl = row / p.wbox;
     const int wl = row - hl * p.wbox;
     const clpk_conv_epilogue& ep = p.ep;
     const int ldc = ep.cout_valid;
-    const int etid = threadIdx.x - 64;       // 0..127 among the epilogue threads
-    const bool leader = (etid == 0);
+    const int etid = threadIdx.x - 64;       // 0 .. 128*kEpiGroups-1 among all epilogue threads
+    const int gtid = etid & 127;             // within the group
+    const bool leader = (gtid == 0);
     const bool f16 = p.op_f16 != 0;
+    const int S = p.n_staging / kEpiGroups;  // staging slots of this group
+    uint8_t* gslots = smem_s + (size_t)eg * S * kStagingBytes;
+    uint64_t* res_full = bars->res_full[eg];
+    uint64_t* slot_free = bars->slot_free[eg];
+    const int bar_id = 1 + eg;
     int it = 0;
-    uint32_t gchunk = 0;                     // running chunk counter (selects the staging buffer)
+    uint32_t gchunk = 0;                     // group-local running chunk counter (selects the staging slot)
     int cached_key = -1;
     // Residual chunks are TMA-loaded straight into the staging slot that will later be stored from (read-modify-write in
-    // place).  The leader keeps `res_ahead` chunks in flight; (ld_tile, ld_c, ld_g) is its load cursor.
+    // place).  The group leader keeps `A` chunks in flight; (ld_tile, ld_c, ld_g) is its load cursor.
     const bool res_tma = p.chunked && (ep.resid != nullptr);
     const bool st_f32 = p.chunked && (ep.out_f32 != nullptr);  // fp32 output goes through the staging slots + TMA store
+    const int A = (S >= 2) ? S - 1 : 1;      // residual look-ahead (chunks of this group)
     const uint32_t res_bytes = (uint32_t)(p.wbox * p.hbox) * 128u;
-    int ld_tile = cluster_id, ld_c = 0;
+    const int cstep = 32 * kEpiGroups;
+    int ld_tile = cluster_id, ld_c = 32 * eg;
     uint32_t ld_g = 0;
     auto issue_res_load = [&]() {
+      while (ld_tile < p.num_tiles && ld_c >= p.block_n) { ld_c = 32 * eg; ld_tile += num_clusters; }
       if (ld_tile >= p.num_tiles) return;
       const TileCoord lc = decode_tile(p, ld_tile, (int)rank);
-      const uint32_t slot = ld_g % (uint32_t)p.n_staging;
-      mbar_arrive_expect_tx(&bars->res_full[slot], res_bytes);
-      tma_load_5d(smem_s + (size_t)slot * kStagingBytes, &maps_res.m[lc.phase], &bars->res_full[slot], lc.n0 + ld_c, lc.w0, 0,
-                  lc.h0, lc.b);
+      const uint32_t slot = ld_g % (uint32_t)S;
+      mbar_arrive_expect_tx(&res_full[slot], res_bytes);
+      tma_load_5d(gslots + (size_t)slot * kStagingBytes, &maps_res.m[lc.phase], &res_full[slot], lc.n0 + ld_c, lc.w0, 0, lc.h0,
+                  lc.b);
       ++ld_g;
-      ld_c += 32;
-      if (ld_c >= p.block_n) { ld_c = 0; ld_tile += num_clusters; }
+      ld_c += cstep;
     };
     if (res_tma && leader && !(p.dbg & 1))
-      for (int i = 0; i < p.res_ahead; ++i) issue_res_load();
+      for (int i = 0; i < A; ++i) issue_res_load();
     const uint32_t lead_tmem_empty0 = (NCTA == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[0]), 0u) : 0u;
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
       const int as = it & 1;
@@ -356,9 +371,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ------------------------------------------------ chunked path: TMEM -> regs -> swizzled smem -> TMA store
         const int vb = tc.ok ? tc.b : 0;  // a masked tile still runs the (uniform) protocol, on image 0's vectors
         const int key = vb * 4096 + tc.n0;
-        if (key != cached_key) {  // (image, channel-tile) changed: refresh the folded bias / FiLM vectors
-          named_bar_sync(1, 128);
-          for (int n = etid; n < p.block_n; n += 128) {
+        if (key != cached_key) {  // (image, channel-tile) changed: refresh the folded bias / FiLM vectors (all groups)
+          named_bar_sync(kEpiGroups + 1, 128 * kEpiGroups);
+          for (int n = etid; n < p.block_n; n += 128 * kEpiGroups) {
             float mul = 1.0f, add = __ldg(ep.bias + tc.n0 + n);
             if (ep.film_scale1p) {
               mul = __ldg(ep.film_scale1p + (long long)vb * ep.film_stride + tc.n0 + n);
@@ -367,14 +382,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             vec->mul[n] = mul;
             vec->add[n] = add;
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(kEpiGroups + 1, 128 * kEpiGroups);
           cached_key = key;
         }
         mbar_wait(&bars->tmem_full[as], aphase);
         tc_fence_after();
-        for (int c = 0; c < p.block_n; c += 32, ++gchunk) {
-          const uint32_t slot = p.n_staging > 0 ? gchunk % (uint32_t)p.n_staging : 0u;
-          uint8_t* sbuf = smem_s + (size_t)slot * kStagingBytes;
+        for (int c = 32 * eg; c < p.block_n; c += cstep, ++gchunk) {
+          const uint32_t slot = S > 0 ? gchunk % (uint32_t)S : 0u;
+          const uint32_t use = S > 0 ? gchunk / (uint32_t)S : 0u;  // how often this slot has been used before
+          uint8_t* sbuf = gslots + (size_t)slot * kStagingBytes;
           uint32_t r[32];
           __syncwarp();
           tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
@@ -394,17 +410,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             // staging row = tile row; 16-byte chunk j4 lives at chunk (j4 ^ (row & 7)) — the 128B TMA swizzle
             uint8_t* srow = sbuf + row * 128;
             if (res_tma) {
-              mbar_wait(&bars->res_full[slot], (gchunk / (uint32_t)p.n_staging) & 1u);  // residual chunk has landed
+              mbar_wait(&res_full[slot], use & 1u);  // residual chunk has landed (implies the slot was free)
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 q = *reinterpret_cast<const float4*>(srow + ((j4 ^ (row & 7)) << 4));
                 v[4 * j4 + 0] += q.x; v[4 * j4 + 1] += q.y; v[4 * j4 + 2] += q.z; v[4 * j4 + 3] += q.w;
               }
+            } else if (st_f32) {
+              // slot_free[s] gets one arrival per chunk g with (g+1) % S == s; see the leader section below
+              if (slot != 0) mbar_wait(&slot_free[slot], use & 1u);
+              else if (use > 0) mbar_wait(&slot_free[0], (use - 1u) & 1u);
             }
             if (ep.gn_partial) {
               // per-thread (sum, sumsq) of this row's 32 values split by consumer-GroupNorm group, folded over the warp's
               // 32 rows; the owning lanes park the warp's partials for the fixed-order 4-warp fold after the barrier
-              float2* redw = vec->red[gchunk & 1u][quarter];
+              float2* redw = vec->red[eg * 2 + (int)(gchunk & 1u)][quarter];
               const int cpg = ep.gn_cpg;
               if (cpg >= 32) gn_chunk_partials<1>(v, valid, lane, redw);
               else if (cpg == 16) gn_chunk_partials<2>(v, valid, lane, redw);
@@ -426,32 +446,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
           }
           if (st_f32) fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-          if (leader && p.n_staging > 0) {
-            // Slot reuse.  Before the barrier of chunk g the stores of chunks <= g-1 are committed.  The slot that is
-            // touched next — by the generic writes of chunk g+1 (no residual) or by the residual load of chunk g+A —
-            // was last stored from by chunk g+1-S resp. g+A-S, so at most S-2 resp. S-A-1 groups may stay pending.
-            const int pending_ok = res_tma ? (p.n_staging - p.res_ahead - 1) : (p.n_staging - 2);
-            if (pending_ok >= 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
-            if (res_tma && !(p.dbg & 1)) issue_res_load();
-          }
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           if (leader && st_f32 && !(p.dbg & 1)) {
             tma_store_5d(&maps_out.m[tc.phase], sbuf, tc.n0 + c, tc.w0, 0, tc.h0, tc.b);
             bulk_commit_group();
+            // Slot reuse.  Stores of chunks <= g are now committed.
+            //  residual: the load of chunk g+A targets the slot last stored from by chunk g+A-S -> at most S-A groups may
+            //            still be pending (A = S-1 -> 1; S = 1, A = 1 -> 0);
+            //  plain   : chunk g+1 writes the slot last stored from by chunk g+1-S -> at most S-1 pending, then the
+            //            leader publishes "slot (g+1) % S is free" on its mbarrier.
+            if (res_tma) {
+              if (S - A >= 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+              issue_res_load();
+            } else {
+              if (S - 1 >= 2) bulk_wait_group_read<2>(); else if (S - 1 == 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+              mbar_arrive(&slot_free[(gchunk + 1u) % (uint32_t)S]);
+            }
           }
           if (ep.gn_partial && !(p.dbg & 1)) {
             const int cpg = ep.gn_cpg;
             const int npairs = cpg >= 32 ? 1 : 32 / cpg;
-            if (etid < npairs && tc.ok) {
-              const float2* rr = &vec->red[gchunk & 1u][0][etid];
+            if (gtid < npairs && tc.ok) {
+              const float2* rr = &vec->red[eg * 2 + (int)(gchunk & 1u)][0][gtid];
               float2 acc = rr[0];
 #pragma unroll
               for (int wq = 1; wq < 4; ++wq) { acc.x += rr[wq * 8].x; acc.y += rr[wq * 8].y; }  // fixed order
               const int ch = tc.n0 + c;
-              const int g = (cpg >= 32) ? ch / cpg : ch / cpg + etid;
+              const int g = (cpg >= 32) ? ch / cpg : ch / cpg + gtid;
               const int mtile = (tc.phase * p.tiles_h + tc.h0 / p.hbox) * p.tiles_w + tc.w0 / p.wbox;
-              const int slot = mtile * p.gn_sub + ((cpg >= 32) ? (ch % cpg) / 32 : 0);
-              reinterpret_cast<float2*>(ep.gn_partial)[((long long)tc.b * p.gn_slots + slot) * p.gn_groups + g] = acc;
+              const int slotg = mtile * p.gn_sub + ((cpg >= 32) ? (ch % cpg) / 32 : 0);
+              reinterpret_cast<float2*>(ep.gn_partial)[((long long)tc.b * p.gn_slots + slotg) * p.gn_groups + g] = acc;
             }
           }
         }
@@ -459,24 +483,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ------------------------------------------------ direct path (narrow N: the 3-channel `out` conv, NCHW store)
         mbar_wait(&bars->tmem_full[as], aphase);
         tc_fence_after();
-        for (int c = 0; c < p.block_n; c += 16) {
-          uint32_t r[16];
-          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores of the last chunk
-          tmem_ld16(taddr + (uint32_t)c, r);
-          tmem_ld_wait();
-          const int n = tc.n0 + c;
-          if (valid && n < ldc && !(p.dbg & 1)) {
+        if (eg == 0) {
+          for (int c = 0; c < p.block_n; c += 16) {
+            uint32_t r[16];
+            __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores of the last chunk
+            tmem_ld16(taddr + (uint32_t)c, r);
+            tmem_ld_wait();
+            const int n = tc.n0 + c;
+            if (valid && n < ldc && !(p.dbg & 1)) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (n + j < ldc) {
-                float y = __uint_as_float(r[j]) + __ldg(ep.bias + n + j);
-                if (ep.film_scale1p)
-                  y = fmaf(y, __ldg(ep.film_scale1p + (long long)tc.b * ep.film_stride + n + j),
-                           __ldg(ep.film_shift + (long long)tc.b * ep.film_stride + n + j));
-                if (ep.resid) y += ep.resid[opix * ldc + n + j];
-                if (ep.out_f32) ep.out_f32[opix * ldc + n + j] = y;
-                if (ep.out_op) reinterpret_cast<uint16_t*>(ep.out_op)[opix * ldc + n + j] = to_op(y, f16);
-                if (ep.out_nchw) ep.out_nchw[(((long long)tc.b * ldc + n + j) * p.out_h + oh) * p.out_w + ow] = y;
+              for (int j = 0; j < 16; ++j) {
+                if (n + j < ldc) {
+                  float y = __uint_as_float(r[j]) + __ldg(ep.bias + n + j);
+                  if (ep.film_scale1p)
+                    y = fmaf(y, __ldg(ep.film_scale1p + (long long)tc.b * ep.film_stride + n + j),
+                             __ldg(ep.film_shift + (long long)tc.b * ep.film_stride + n + j));
+                  if (ep.resid) y += ep.resid[opix * ldc + n + j];
+                  if (ep.out_f32) ep.out_f32[opix * ldc + n + j] = y;
+                  if (ep.out_op) reinterpret_cast<uint16_t*>(ep.out_op)[opix * ldc + n + j] = to_op(y, f16);
+                  if (ep.out_nchw) ep.out_nchw[(((long long)tc.b * ldc + n + j) * p.out_h + oh) * p.out_w + ow] = y;
+                }
               }
             }
           }
@@ -741,9 +767,12 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   p.n_staging = 0;
   if (p.chunked && (p.ep.out_f32 || p.ep.resid)) {
     CLPK_REQUIRE(p.ep.out_f32 != nullptr, "a residual input needs the fp32 output");
-    p.n_staging = ((kSmemBudget - fixed - 3 * kStagingBytes) / stage_bytes >= 4 ||
-                   (kSmemBudget - fixed - 3 * kStagingBytes) / stage_bytes == (kSmemBudget - fixed - 2 * kStagingBytes) / stage_bytes)
-                      ? 3 : 2;
+    // two staging slots per epilogue group when the smem ring keeps its depth, else one
+    const int want_stages = (p.block_k == 128) ? 3 : 4;
+    int per_group = 2;
+    if ((kSmemBudget - fixed - kEpiGroups * 2 * kStagingBytes) / stage_bytes < want_stages) per_group = 1;
+    { const char* e = getenv("CLPK_IGEMM_SLOTS"); if (e && atoi(e) >= 1 && atoi(e) <= 3) per_group = atoi(e); }
+    p.n_staging = kEpiGroups * per_group;
     if ((kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes < 2) { p.n_staging = 0; p.chunked = 0; }
   }
   p.gn_groups = p.gn_slots = 0;
@@ -755,9 +784,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     p.gn_groups = cout / p.ep.gn_cpg;
     p.gn_sub = p.ep.gn_cpg >= 32 ? p.ep.gn_cpg / 32 : 1;
   }
-  // residual chunks kept in flight by the epilogue leader: slots - 2 (one slot is being processed, one being stored)
-  p.res_ahead = (p.n_staging > 0 && p.ep.resid) ? std::max(1, p.n_staging - 2) : 0;
-  if (p.n_staging == 2 && p.ep.resid) p.res_ahead = 1;
+  p.res_ahead = 0;  // (look-ahead is derived in the kernel from the slots per epilogue group)
   p.stages = std::min(kMaxStages, (kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes);
   CLPK_REQUIRE(p.stages >= 2, "tile does not fit shared memory");
   out->smem_bytes = p.stages * stage_bytes + p.n_staging * kStagingBytes + fixed;

@@ -18,7 +18,7 @@ from .models.unet import CLIPCondUNet
 
 def codes_to_device(q_host: np.ndarray, device) -> torch.Tensor:
     """uint8 [N, D] host array -> device tensor through pinned memory (one async H2D copy)."""
-    t = torch.from_numpy(np.ascontiguousarray(q_host, dtype=np.uint8))
+    t = torch.from_numpy(np.array(q_host, dtype=np.uint8, order="C", copy=True))  # frombuffer views are read-only
     return t.pin_memory().to(device, non_blocking=True)
 
 
