@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", type=str, default="")
+    ap.add_argument("--model-like", action="store_true", help="epilogues as the plan uses them (16-bit conv1 output, fused GN stats)")
     args = ap.parse_args()
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -54,7 +55,12 @@ def main():
         if resid:
             kw["resid"] = torch.randn(b, oh, ow, cout, device=dev)
         nchw = cout % 16 != 0
-        run = lambda: ops.conv_igemm(x, wp, kind, cout, bias, want_f32=not nchw, want_nchw=nchw, **kw)  # noqa: E731
+        if args.model_like and not nchw:
+            # what the plan launches: conv1 keeps only the 16-bit copy, every producer emits GroupNorm partials
+            only16 = film
+            run = lambda: ops.conv_igemm(x, wp, kind, cout, bias, want_f32=not only16, want_op=only16, gn_groups=8, **kw)  # noqa: E731
+        else:
+            run = lambda: ops.conv_igemm(x, wp, kind, cout, bias, want_f32=not nchw, want_nchw=nchw, **kw)  # noqa: E731
         for _ in range(3):
             run()
         ms = []
