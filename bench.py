@@ -270,7 +270,9 @@ def run_b200_arm(args):
     conv_ms = per_step_ms[cls[0]]
     conv_tflops = fa.value / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     gn_ms = per_step_ms[cls[2]]
-    gn_bytes = ge.value * 6.0  # algorithmic: fp32 read + bf16 write per element, stats assumed fused
+    gb = C.c_double()
+    _lib.check(lib.clpk_plan_groupnorm_bytes(plan.handle, C.byref(gb)), "gn bytes")
+    gn_bytes = gb.value  # algorithmic: input read once (2 B 16-bit / 4 B fp32) + 16-bit write per element
     gn_gbs = gn_bytes / (gn_ms * 1e-3) / 1e9 if gn_ms > 0 else 0.0
     n_conv = cnt6[0] // prof_iters
     roofline = {
@@ -283,9 +285,10 @@ def run_b200_arm(args):
         "how": f"CUDA events around each of the {n_conv} launches of {prof_iters} eager DDIM steps right after the timed region",
     }
     roofline_hbm = {
-        "bound": "hbm", "kernel": "gn_stats_kernel + gn_apply_kernel", "achieved": gn_gbs, "peak": peaks["hbm"],
+        "bound": "hbm", "kernel": "gn_apply_kernel (GroupNorm+SiLU, statistics fused into the producing conv)", "achieved": gn_gbs, "peak": peaks["hbm"],
         "unit": "GB/s", "frac": gn_gbs / peaks["hbm"], "algorithmic_bytes_per_ddim_step": gn_bytes,
-        "note": "algorithmic traffic = 6 B/element (fp32 read + bf16 write); the separate statistics pass re-reads x, so 10 B/element actually move",
+        "gn_elements_per_ddim_step": ge.value, "bytes_per_element": gn_bytes / max(ge.value, 1.0),
+        "note": "algorithmic traffic = input read once (16-bit: 2 B, fp32: 4 B) + 16-bit operand written once",
     }
     share = {c: per_step_ms[c] / sum(per_step_ms.values()) for c in cls}
 

@@ -90,6 +90,7 @@ SIGNATURES = {
     "clpk_ddim_sample": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "clpk_plan_profile_steps": (_i, [_vp, _i, C.POINTER(_f), C.POINTER(_i), _vp]),
     "clpk_plan_work_breakdown": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "clpk_plan_groupnorm_bytes": (_i, [_vp, C.POINTER(C.c_double)]),
     "clpk_to_uint8_hwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "clpk_psnr_sqerr_u8": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
 }

@@ -164,8 +164,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
   return r;
 }
+// Relaxed: the only thing published through these remote arrives is "my tcgen05.ld of the accumulator has completed",
+// which tcgen05.fence::before_thread_sync orders.  (.release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR, which made
+// every epilogue warp wait for all of its outstanding global stores once per tile: 18 % of all stall samples.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // CTA-pair TMA loads: data lands in the issuing CTA's smem, the transaction bytes are signalled on `mbar_cluster_addr`
 // (the pair leader's barrier)

@@ -34,8 +34,7 @@ struct __align__(8) PipeBarriers {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t res_full[kEpiGroups][4];   // residual chunk landed in staging slot s of the group
-  uint64_t slot_free[kEpiGroups][4];  // the TMA store that last read staging slot s has finished reading it
+  uint64_t res_full[4 * kEpiGroups][4];  // per epilogue warp: residual sub-box landed in the warp's staging slot s
   uint32_t tmem_base;
 };
 
@@ -64,12 +63,23 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int item,
 }
 
 // per-tile epilogue vectors: y = acc * mul[n] + add[n]   (mul = 1 + FiLM scale or 1, add = bias * mul + FiLM shift)
-struct EpiVectors {       // laid out in smem as: float mul[block_n] | float add[block_n] | float2 red[2][4][8]
+constexpr int kMaxGroupChunks = 4;  // 32-column chunks one epilogue group handles per tile (block_n <= 256, 2 groups)
+struct EpiVectors {       // laid out in smem as: float mul[block_n] | float add[block_n] | float2 red[...]
   float* mul;
   float* add;
-  float2 (*red)[4][8];    // fused GN statistics: [epilogue group * 2 + chunk parity][warp][group pair] partial (sum, sumsq)
+  // fused GN statistics: [tile parity][epilogue group][chunk of the group][warp][group pair] partial (sum, sumsq)
+  float2 (*red)[kEpiGroups][kMaxGroupChunks][4][8];
 };
-constexpr int kRedBytes = kEpiGroups * 2 * 4 * 8 * (int)sizeof(float2);
+constexpr int kRedBytes = 2 * kEpiGroups * kMaxGroupChunks * 4 * 8 * (int)sizeof(float2);
+constexpr int kWarpSlotBytes = 32 * 128;  // per-warp staging slot: 32 tile rows x 128 B (fp32) or x 64 B (16-bit)
+
+// perf-debug switches (env CLPK_IGEMM_DBG) are compiled in only with -DCLPK_IGEMM_DEBUG: their uniform branches sit in
+// the hottest loops
+#ifdef CLPK_IGEMM_DEBUG
+#define CLPK_DBG(bits) (p.dbg & (bits))
+#else
+#define CLPK_DBG(bits) 0
+#endif
 static inline int epi_vector_bytes(int block_n) { return 2 * 4 * block_n + kRedBytes; }
 
 constexpr int kStagingBytes = kTileM * 128;
@@ -145,7 +155,9 @@ __device__ __forceinline__ void gn_chunk_partials(const float (&v)[32], bool val
   }
 }  // one staging buffer: 128 rows x 32 fp32 columns, 128B-swizzled
 
-template <int BLOCK_K, int NCTA>
+constexpr int kSlabABytes = 17 * 1024;  // (128 + 2) slab rows x 128 B = 16640, padded to the 1024-byte swizzle-atom pitch
+
+template <int BLOCK_K, int NCTA, bool kSlab>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ OutMaps maps_out, const __grid_constant__ OutMaps maps_res,
@@ -156,7 +168,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   constexpr int kAtoms = BLOCK_K / kAtomK;
   constexpr int kSwizzle = kAtomK * 2;            // bytes per smem row
   constexpr int kAAtomBytes = kTileM * kAtomK * 2;
-  constexpr int kABytes = kAAtomBytes * kAtoms;   // one A stage
+  constexpr int kABytes = kSlab ? kSlabABytes : kAAtomBytes * kAtoms;   // one A stage
+  static_assert(!kSlab || BLOCK_K == 64, "slab mode stages 64-channel slabs");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -164,7 +177,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int b_rows = p.block_n / NCTA;            // each CTA of a pair stages half of the B (weight) tile
   const int b_atom_bytes = b_rows * kAtomK * 2;
-  const int b_bytes = b_atom_bytes * kAtoms;
+  const int b_bytes = kSlab ? 3 * b_atom_bytes : b_atom_bytes * kAtoms;  // slab mode: the 3 taps of one kernel row
   const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
   const int cluster_id = blockIdx.x / NCTA, num_clusters = gridDim.x / NCTA;
   uint8_t* smem_a = smem;
@@ -173,13 +186,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   EpiVectors vec_s;
   vec_s.mul = reinterpret_cast<float*>(smem_s + (size_t)p.n_staging * kStagingBytes);
   vec_s.add = vec_s.mul + p.block_n;
-  vec_s.red = reinterpret_cast<float2(*)[4][8]>(vec_s.add + p.block_n);
+  vec_s.red = reinterpret_cast<float2(*)[kEpiGroups][kMaxGroupChunks][4][8]>(vec_s.add + p.block_n);
   const EpiVectors* vec = &vec_s;
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(reinterpret_cast<uint8_t*>(vec_s.red) + kRedBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int k_blocks = p.taps * p.kpt;
+  const int k_blocks = kSlab ? 3 * p.kpt : p.taps * p.kpt;  // pipeline stages per tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -192,8 +205,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(&bars->tmem_full[s], 1);
       mbar_init(&bars->tmem_empty[s], 4 * kEpiGroups * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
-    for (int g = 0; g < kEpiGroups; ++g)
-      for (int s = 0; s < 4; ++s) { mbar_init(&bars->res_full[g][s], 1); mbar_init(&bars->slot_free[g][s], 1); }
+    for (int g = 0; g < 4 * kEpiGroups; ++g)
+      for (int s = 0; s < 4; ++s) mbar_init(&bars->res_full[g][s], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -211,7 +224,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // TMA instructions sits under elect.sync.  Issuing them from a divergent `if (lane == 0)` region makes the compiler
     // wrap each one in an ELECT/BRA.U.ANY serialisation loop, which throttles the pipeline.
     {
-      const uint32_t rows = (uint32_t)(p.wbox * p.hbox);
+      const uint32_t rows = kSlab ? (uint32_t)(p.wbox + 2) : (uint32_t)(p.wbox * p.hbox);
       const uint32_t tx_bytes = rows * BLOCK_K * 2 + (uint32_t)b_bytes;
       int stage = 0;
       uint32_t phase = 0;
@@ -230,30 +243,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           if (elect_one()) {
             uint32_t tx = tx_bytes;
-            if (p.dbg & 4) tx -= rows * BLOCK_K * 2;
-            if (p.dbg & 8) tx -= (uint32_t)b_bytes;
+            if (CLPK_DBG(4)) tx -= rows * BLOCK_K * 2;
+            if (CLPK_DBG(8)) tx -= (uint32_t)b_bytes;
             uint8_t* a_dst = smem_a + (size_t)stage * kABytes;
             uint8_t* b_dst = smem_b + (size_t)stage * b_bytes;
-            if (NCTA == 2) {
+            if (kSlab) {
+              // stage kb = (kernel row r = tap, channel block kc): slab = input row h0 + r - 1, pixels w0 - 1 .. w0 + wbox
+              // (TMA zero-fills what lies outside the image), weights = taps (r, 0..2) of that channel block
+              const uint32_t lead_full = (NCTA == 2) ? mapa_u32(smem_u32(&bars->full[stage]), 0u) : smem_u32(&bars->full[stage]);
+              if (NCTA == 1 || rank == 0) mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)NCTA * tx);
+              if (!(CLPK_DBG(4))) {
+                if (NCTA == 2) tma_load_5d_pair(a_dst, &map_a, lead_full, kc * 64, tc.w0 - 1, 0, tc.h0 + tap - 1, tc.b);
+                else tma_load_5d(a_dst, &map_a, &bars->full[stage], kc * 64, tc.w0 - 1, 0, tc.h0 + tap - 1, tc.b);
+              }
+              if (!(CLPK_DBG(8))) {
+#pragma unroll
+                for (int s3 = 0; s3 < 3; ++s3) {
+                  const int kcol = (tap * 3 + s3) * p.cin + kc * 64;
+                  if (NCTA == 2) tma_load_2d_pair(b_dst + s3 * b_atom_bytes, &map_w, lead_full, kcol, w_row);
+                  else tma_load_2d(b_dst + s3 * b_atom_bytes, &map_w, &bars->full[stage], kcol, w_row);
+                }
+              }
+            } else if (NCTA == 2) {
               // both CTAs' bytes are accounted on the LEADER's full barrier (the MMA issuer lives there)
               if (rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * tx);
               const uint32_t lead_full = mapa_u32(smem_u32(&bars->full[stage]), 0u);
 #pragma unroll
               for (int at = 0; at < kAtoms; ++at) {
-                if (!(p.dbg & 4))
+                if (!(CLPK_DBG(4)))
                   tma_load_5d_pair(a_dst + at * kAAtomBytes, &map_a, lead_full, p.tap_x[ti] + kc * BLOCK_K + at * kAtomK,
                                    tc.w0 + p.tap_dw[ti], p.tap_p[ti], tc.h0 + p.tap_dh[ti], tc.b);
-                if (!(p.dbg & 8))
+                if (!(CLPK_DBG(8)))
                   tma_load_2d_pair(b_dst + at * b_atom_bytes, &map_w, lead_full, kb * BLOCK_K + at * kAtomK, w_row);
               }
             } else {
               mbar_arrive_expect_tx(&bars->full[stage], tx);
 #pragma unroll
               for (int at = 0; at < kAtoms; ++at) {
-                if (!(p.dbg & 4))
+                if (!(CLPK_DBG(4)))
                   tma_load_5d(a_dst + at * kAAtomBytes, &map_a, &bars->full[stage], p.tap_x[ti] + kc * BLOCK_K + at * kAtomK,
                               tc.w0 + p.tap_dw[ti], p.tap_p[ti], tc.h0 + p.tap_dh[ti], tc.b);
-                if (!(p.dbg & 8))
+                if (!(CLPK_DBG(8)))
                   tma_load_2d(b_dst + at * b_atom_bytes, &map_w, &bars->full[stage], kb * BLOCK_K + at * kAtomK, w_row);
               }
             }
@@ -286,7 +316,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (elect_one()) {
             const uint64_t adesc = adesc0 + a_step * (uint64_t)stage;
             const uint64_t bdesc = bdesc0 + b_step * (uint64_t)stage;
-            if (!(p.dbg & 2)) {
+            if (kSlab) {
+              if (!(CLPK_DBG(2))) {
+#pragma unroll
+                for (int s3 = 0; s3 < 3; ++s3) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    // tap (r, s3): the tile's 128 pixels are slab rows s3 .. s3 + 127 -> start address + s3 * 128 B (the
+                    // 128B swizzle is a function of the absolute smem address, so a row-shifted start stays consistent
+                    // with what the TMA wrote); K advance as usual (+32 B = +2 in the addr >> 4 field)
+                    const uint64_t ao = (uint64_t)(s3 * 8 + 2 * kk);
+                    const uint64_t bo = (uint64_t)(s3 * (b_atom_bytes >> 4) + 2 * kk);
+                    const uint32_t acc = (s3 == 0 && kk == 0) ? (uint32_t)(kb != 0) : 1u;
+                    if (NCTA == 2) umma_f16kind_pair(tmem_d, adesc + ao, bdesc + bo, idesc, acc);
+                    else umma_f16kind(tmem_d, adesc + ao, bdesc + bo, idesc, acc);
+                  }
+                }
+              }
+            } else if (!(CLPK_DBG(2))) {
 #pragma unroll
               for (int k = 0; k < BLOCK_K / 16; ++k) {
                 // K advance: 16 elements = 32 bytes inside the swizzled row (+2 in the addr>>4 field); next atom = next
@@ -312,49 +359,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else {
     // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
-    // kEpiGroups groups of 4 warps; group eg owns the 32-column chunks with (chunk index % kEpiGroups) == eg, its own
-    // staging slots, barriers and named barrier, so two chunks are in flight per CTA and every scheduler has two
-    // epilogue warps to hide TMEM / shuffle / smem latencies.
+    // kEpiGroups groups of 4 warps; group eg owns the 32-column chunks with (chunk index % kEpiGroups) == eg.  Every warp
+    // is autonomous inside a tile: it owns the 32 tile rows of its TMEM lane quarter, its own staging slots (32 rows x
+    // 128 B), its own residual-load mbarriers and issues its own TMA loads / stores for that 32-row sub-box — no
+    // cross-warp barrier per chunk.  The only group-wide synchronisation is ONE named barrier per tile for the 4-warp
+    // fold of the fused GroupNorm partial sums.
     const int eg = (warp - 2) >> 2;          // epilogue group
     const int quarter = warp & 3;
+    const int ew = eg * 4 + quarter;         // epilogue warp index
     const int row = quarter * 32 + lane;
     const int hl = row / p.wbox;
     const int wl = row - hl * p.wbox;
+    const int sub_h = (quarter * 32) / p.wbox, sub_w = (quarter * 32) - sub_h * p.wbox;  // this warp's sub-box origin
     const clpk_conv_epilogue& ep = p.ep;
     const int ldc = ep.cout_valid;
     const int etid = threadIdx.x - 64;       // 0 .. 128*kEpiGroups-1 among all epilogue threads
     const int gtid = etid & 127;             // within the group
-    const bool leader = (gtid == 0);
     const bool f16 = p.op_f16 != 0;
-    const int S = p.n_staging / kEpiGroups;  // staging slots of this group
-    uint8_t* gslots = smem_s + (size_t)eg * S * kStagingBytes;
-    uint64_t* res_full = bars->res_full[eg];
-    uint64_t* slot_free = bars->slot_free[eg];
+    const int S = p.n_staging / kEpiGroups;  // staging slots of this warp (a 16 KB staging buffer = 4 warp slots)
+    uint8_t* wslots = smem_s + (size_t)ew * S * kWarpSlotBytes;
+    uint64_t* res_full = bars->res_full[ew];
     const int bar_id = 1 + eg;
     int it = 0;
-    uint32_t gchunk = 0;                     // group-local running chunk counter (selects the staging slot)
+    uint32_t slot = 0, sphase = 0;           // staging slot of the current chunk and how often the ring has wrapped (parity)
     int cached_key = -1;
-    // Residual chunks are TMA-loaded straight into the staging slot that will later be stored from (read-modify-write in
-    // place).  The group leader keeps `A` chunks in flight; (ld_tile, ld_c, ld_g) is its load cursor.
+    // Residual sub-boxes are TMA-loaded straight into the staging slot that is later stored from (read-modify-write in
+    // place).  Lane 0 keeps `A` of them in flight; (ld_tile, ld_c, ld_slot) is its load cursor.
     const bool res_tma = p.chunked && (ep.resid != nullptr);
     const bool st_f32 = p.chunked && (ep.out_f32 != nullptr);  // fp32 output goes through the staging slots + TMA store
-    const int A = (S >= 2) ? S - 1 : 1;      // residual look-ahead (chunks of this group)
-    const uint32_t res_bytes = (uint32_t)(p.wbox * p.hbox) * 128u;
+    // a 16-bit-only output (ResBlock conv1) is staged too (64-byte rows, 64B swizzle): 4x fewer L1/smem wavefronts than
+    // 32 lanes x 16 B scattered over 32 lines per store instruction
+    const bool st_16 = p.chunked && (ep.out_f32 == nullptr) && (ep.out_op != nullptr) && p.n_staging > 0;
+    const bool st_tma = st_f32 || st_16;
+    const int A = (S >= 2) ? S - 1 : 1;      // residual look-ahead (chunks of this warp)
     const int cstep = 32 * kEpiGroups;
+    const int cpg = ep.gn_cpg;
+    const int npairs = cpg >= 32 ? 1 : (cpg > 0 ? 32 / cpg : 0);
     int ld_tile = cluster_id, ld_c = 32 * eg;
-    uint32_t ld_g = 0;
-    auto issue_res_load = [&]() {
+    uint32_t ld_slot = 0;
+    auto issue_res_load = [&]() {  // lane 0 only
       while (ld_tile < p.num_tiles && ld_c >= p.block_n) { ld_c = 32 * eg; ld_tile += num_clusters; }
       if (ld_tile >= p.num_tiles) return;
       const TileCoord lc = decode_tile(p, ld_tile, (int)rank);
-      const uint32_t slot = ld_g % (uint32_t)S;
-      mbar_arrive_expect_tx(&res_full[slot], res_bytes);
-      tma_load_5d(gslots + (size_t)slot * kStagingBytes, &maps_res.m[lc.phase], &res_full[slot], lc.n0 + ld_c, lc.w0, 0, lc.h0,
-                  lc.b);
-      ++ld_g;
+      mbar_arrive_expect_tx(&res_full[ld_slot], (uint32_t)kWarpSlotBytes);
+      tma_load_5d(wslots + (size_t)ld_slot * kWarpSlotBytes, &maps_res.m[lc.phase], &res_full[ld_slot], lc.n0 + ld_c,
+                  lc.w0 + sub_w, 0, lc.h0 + sub_h, lc.b);
+      if (++ld_slot == (uint32_t)S) ld_slot = 0;
       ld_c += cstep;
     };
-    if (res_tma && leader && !(p.dbg & 1))
+    if (res_tma && lane == 0 && !(CLPK_DBG(1)))
       for (int i = 0; i < A; ++i) issue_res_load();
     const uint32_t lead_tmem_empty0 = (NCTA == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[0]), 0u) : 0u;
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
@@ -385,18 +438,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           named_bar_sync(kEpiGroups + 1, 128 * kEpiGroups);
           cached_key = key;
         }
+        float2 (*red_t)[4][8] = vec->red[it & 1][eg];  // [chunk of this group][warp][pair]
         mbar_wait(&bars->tmem_full[as], aphase);
         tc_fence_after();
-        for (int c = 32 * eg; c < p.block_n; c += cstep, ++gchunk) {
-          const uint32_t slot = S > 0 ? gchunk % (uint32_t)S : 0u;
-          const uint32_t use = S > 0 ? gchunk / (uint32_t)S : 0u;  // how often this slot has been used before
-          uint8_t* sbuf = gslots + (size_t)slot * kStagingBytes;
+        int ci = 0;
+        for (int c = 32 * eg; c < p.block_n; c += cstep, ++ci) {
+          uint8_t* sbuf = wslots + (size_t)slot * kWarpSlotBytes;
           uint32_t r[32];
-          __syncwarp();
+          __syncwarp();  // also orders lane 0's slot bookkeeping of the previous chunk before this chunk's smem writes
           tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
           tmem_ld16(taddr + (uint32_t)c + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
           tmem_ld_wait();
-          if (!(p.dbg & 1)) {
+          if (!(CLPK_DBG(1))) {
             float v[32];
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
@@ -407,25 +460,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), m4.z, a4.z);
               v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), m4.w, a4.w);
             }
-            // staging row = tile row; 16-byte chunk j4 lives at chunk (j4 ^ (row & 7)) — the 128B TMA swizzle
-            uint8_t* srow = sbuf + row * 128;
+            // staging row = lane (row of the warp's sub-box); 16-byte piece j4 lives at piece (j4 ^ (lane & 7)) — the
+            // 128B TMA swizzle (slots are 1024-byte aligned)
+            uint8_t* srow = sbuf + lane * 128;
             if (res_tma) {
-              mbar_wait(&res_full[slot], use & 1u);  // residual chunk has landed (implies the slot was free)
+              mbar_wait(&res_full[slot], sphase);  // residual sub-box has landed (implies the slot was free)
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 q = *reinterpret_cast<const float4*>(srow + ((j4 ^ (row & 7)) << 4));
+                const float4 q = *reinterpret_cast<const float4*>(srow + ((j4 ^ (lane & 7)) << 4));
                 v[4 * j4 + 0] += q.x; v[4 * j4 + 1] += q.y; v[4 * j4 + 2] += q.z; v[4 * j4 + 3] += q.w;
               }
-            } else if (st_f32) {
-              // slot_free[s] gets one arrival per chunk g with (g+1) % S == s; see the leader section below
-              if (slot != 0) mbar_wait(&slot_free[slot], use & 1u);
-              else if (use > 0) mbar_wait(&slot_free[0], (use - 1u) & 1u);
             }
-            if (ep.gn_partial) {
+            if (ep.gn_partial && !(CLPK_DBG(32))) {
               // per-thread (sum, sumsq) of this row's 32 values split by consumer-GroupNorm group, folded over the warp's
-              // 32 rows; the owning lanes park the warp's partials for the fixed-order 4-warp fold after the barrier
-              float2* redw = vec->red[eg * 2 + (int)(gchunk & 1u)][quarter];
-              const int cpg = ep.gn_cpg;
+              // 32 rows; the owning lanes park the warp's partials for the fixed-order 4-warp fold at the end of the tile
+              float2* redw = red_t[ci][quarter];
               if (cpg >= 32) gn_chunk_partials<1>(v, valid, lane, redw);
               else if (cpg == 16) gn_chunk_partials<2>(v, valid, lane, redw);
               else if (cpg == 8) gn_chunk_partials<4>(v, valid, lane, redw);
@@ -434,51 +483,83 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (st_f32) {
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4)
-                *reinterpret_cast<float4*>(srow + ((j4 ^ (row & 7)) << 4)) =
+                *reinterpret_cast<float4*>(srow + ((j4 ^ (lane & 7)) << 4)) =
                     make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
             }
-            if (ep.out_op && valid) {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out_op) + opix * ldc + tc.n0 + c);
+            if (st_16 || (ep.out_op && !(CLPK_DBG(16)))) {
+              uint4 pk[4];
+              if (f16) {
 #pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8)
-                op[j8] = make_uint4(pack_op2(v[8 * j8 + 0], v[8 * j8 + 1], f16), pack_op2(v[8 * j8 + 2], v[8 * j8 + 3], f16),
-                                    pack_op2(v[8 * j8 + 4], v[8 * j8 + 5], f16), pack_op2(v[8 * j8 + 6], v[8 * j8 + 7], f16));
+                for (int j8 = 0; j8 < 4; ++j8)
+                  pk[j8] = make_uint4(pack_f16x2(v[8 * j8 + 0], v[8 * j8 + 1]), pack_f16x2(v[8 * j8 + 2], v[8 * j8 + 3]),
+                                      pack_f16x2(v[8 * j8 + 4], v[8 * j8 + 5]), pack_f16x2(v[8 * j8 + 6], v[8 * j8 + 7]));
+              } else {
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8)
+                  pk[j8] = make_uint4(pack_bf16x2(v[8 * j8 + 0], v[8 * j8 + 1]), pack_bf16x2(v[8 * j8 + 2], v[8 * j8 + 3]),
+                                      pack_bf16x2(v[8 * j8 + 4], v[8 * j8 + 5]), pack_bf16x2(v[8 * j8 + 6], v[8 * j8 + 7]));
+              }
+              if (st_16) {
+                // 16-byte piece j (channels 8j .. 8j+7) of row `lane` lives at piece (j ^ ((lane >> 1) & 3)): 64B swizzle
+                uint8_t* srow16 = sbuf + lane * 64;
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) *reinterpret_cast<uint4*>(srow16 + ((j8 ^ ((lane >> 1) & 3)) << 4)) = pk[j8];
+              } else if (valid) {
+                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out_op) + opix * ldc + tc.n0 + c);
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) op[j8] = pk[j8];
+              }
             }
           }
-          if (st_f32) fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-          named_bar_sync(bar_id, 128);
-          if (leader && st_f32 && !(p.dbg & 1)) {
-            tma_store_5d(&maps_out.m[tc.phase], sbuf, tc.n0 + c, tc.w0, 0, tc.h0, tc.b);
-            bulk_commit_group();
-            // Slot reuse.  Stores of chunks <= g are now committed.
-            //  residual: the load of chunk g+A targets the slot last stored from by chunk g+A-S -> at most S-A groups may
-            //            still be pending (A = S-1 -> 1; S = 1, A = 1 -> 0);
-            //  plain   : chunk g+1 writes the slot last stored from by chunk g+1-S -> at most S-1 pending, then the
-            //            leader publishes "slot (g+1) % S is free" on its mbarrier.
-            if (res_tma) {
-              if (S - A >= 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
-              issue_res_load();
-            } else {
-              if (S - 1 >= 2) bulk_wait_group_read<2>(); else if (S - 1 == 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
-              mbar_arrive(&slot_free[(gchunk + 1u) % (uint32_t)S]);
+          if (st_tma) {
+            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0 && !(CLPK_DBG(1))) {
+              tma_store_5d(&maps_out.m[tc.phase], sbuf, tc.n0 + c, tc.w0 + sub_w, 0, tc.h0 + sub_h, tc.b);
+              bulk_commit_group();
+              // Slot reuse (per warp; stores of chunks <= g are now committed).
+              //  residual: the load of chunk g+A targets the slot last stored from by chunk g+A-S -> at most S-A groups may
+              //            still be pending (A = S-1 -> 1; S = 1, A = 1 -> 0);
+              //  plain   : chunk g+1 writes the slot last stored from by chunk g+1-S -> at most S-1 pending; the
+              //            __syncwarp at the top of the next chunk publishes it to the other lanes.
+              if (res_tma) {
+                if (S - A >= 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+                issue_res_load();
+              } else {
+                if (S - 1 >= 2) bulk_wait_group_read<2>(); else if (S - 1 == 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+              }
             }
-          }
-          if (ep.gn_partial && !(p.dbg & 1)) {
-            const int cpg = ep.gn_cpg;
-            const int npairs = cpg >= 32 ? 1 : 32 / cpg;
-            if (gtid < npairs && tc.ok) {
-              const float2* rr = &vec->red[eg * 2 + (int)(gchunk & 1u)][0][gtid];
-              float2 acc = rr[0];
-#pragma unroll
-              for (int wq = 1; wq < 4; ++wq) { acc.x += rr[wq * 8].x; acc.y += rr[wq * 8].y; }  // fixed order
-              const int ch = tc.n0 + c;
-              const int g = (cpg >= 32) ? ch / cpg : ch / cpg + gtid;
-              const int mtile = (tc.phase * p.tiles_h + tc.h0 / p.hbox) * p.tiles_w + tc.w0 / p.wbox;
-              const int slotg = mtile * p.gn_sub + ((cpg >= 32) ? (ch % cpg) / 32 : 0);
-              reinterpret_cast<float2*>(ep.gn_partial)[((long long)tc.b * p.gn_slots + slotg) * p.gn_groups + g] = acc;
-            }
+            if (++slot == (uint32_t)S) { slot = 0; sphase ^= 1u; }
           }
         }
+        // accumulator drained: hand it back to the MMA issuer before the statistics fold
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_cluster(lead_tmem_empty0 + (uint32_t)as * 8u);  // the issuer waits in the leader CTA
+          else mbar_arrive(&bars->tmem_empty[as]);
+        }
+        if (ep.gn_partial && !(CLPK_DBG(33))) {
+          // one barrier per tile: the 4 warps' partials of every chunk of this group are parked in red_t; thread
+          // (chunk ci, pair pr) folds them in fixed order.  red is double-buffered by tile parity: a thread can only write
+          // red[it & 1] again (tile it + 2) after passing the barrier of tile it + 1, which the folding threads of tile it
+          // reach after their fold.
+          named_bar_sync(bar_id, 128);
+          const int nch = (p.block_n - 32 * eg + cstep - 1) / cstep;
+          if (gtid < nch * npairs && tc.ok) {
+            const int fci = gtid / npairs, pr = gtid - fci * npairs;
+            const float2* rr = &red_t[fci][0][pr];
+            float2 acc = rr[0];
+#pragma unroll
+            for (int wq = 1; wq < 4; ++wq) { acc.x += rr[wq * 8].x; acc.y += rr[wq * 8].y; }  // fixed order
+            const int ch = tc.n0 + 32 * eg + cstep * fci;
+            const int g = (cpg >= 32) ? ch / cpg : ch / cpg + pr;
+            const int mtile = (tc.phase * p.tiles_h + tc.h0 / p.hbox) * p.tiles_w + tc.w0 / p.wbox;
+            const int slotg = mtile * p.gn_sub + ((cpg >= 32) ? (ch % cpg) / 32 : 0);
+            reinterpret_cast<float2*>(ep.gn_partial)[((long long)tc.b * p.gn_slots + slotg) * p.gn_groups + g] = acc;
+          }
+        }
+        continue;
       } else {
         // ------------------------------------------------ direct path (narrow N: the 3-channel `out` conv, NCHW store)
         mbar_wait(&bars->tmem_full[as], aphase);
@@ -490,7 +571,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tmem_ld16(taddr + (uint32_t)c, r);
             tmem_ld_wait();
             const int n = tc.n0 + c;
-            if (valid && n < ldc && !(p.dbg & 1)) {
+            if (valid && n < ldc && !(CLPK_DBG(1))) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 if (n + j < ldc) {
@@ -515,7 +596,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         else mbar_arrive(&bars->tmem_empty[as]);
       }
     }
-    if (leader && st_f32) bulk_wait_group_all();  // all stores retired before smem goes away
+    if (lane == 0 && st_tma) bulk_wait_group_all();  // all of this warp's stores retired before smem goes away
   }
 
   tc_fence_before();
@@ -610,12 +691,16 @@ static void tile_geometry(int kind, int h_in, int w_in, int* grid_h, int* grid_w
   *hbox = std::max(1, std::min(*grid_h, kTileM / *wbox));
 }
 
+// the chunked epilogue moves per-warp sub-boxes (32 tile rows) by TMA: 32 rows must form a rectangle of the tile
+static bool warp_subbox_ok(int wbox) { return wbox % 32 == 0 || 32 % wbox == 0; }
+
 int igemm_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg) {
   if (gn_cpg <= 0 || cout % gn_cpg != 0 || cout % 32 != 0) return 0;
   if (!(gn_cpg == 4 || gn_cpg == 8 || gn_cpg == 16 || gn_cpg % 32 == 0)) return 0;
   if (cout / gn_cpg > 32) return 0;
   int gh, gw, wbox, hbox, phases;
   tile_geometry(kind, h_in, w_in, &gh, &gw, &wbox, &hbox, &phases);
+  if (!warp_subbox_ok(wbox)) return 0;
   const int sub = gn_cpg >= 32 ? gn_cpg / 32 : 1;
   return phases * ((gh + hbox - 1) / hbox) * ((gw + wbox - 1) / wbox) * sub;
 }
@@ -692,6 +777,14 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   { const char* e = getenv("CLPK_IGEMM_BK");
     if (e && atoi(e) == 64 && p.block_k == 128) p.block_k = 64;
     if (e && atoi(e) == 128 && cin % 128 == 0) p.block_k = 128; }
+  // Row-slab mainloop for 3x3 s1 convs whose M tile is one image row segment (W >= 128): operand fill traffic drops
+  // from 9 A tiles + 9 B tiles to 3 slabs + 9 B tiles per channel block, and CTA pairs halve the B part again.
+  p.slab = 0;
+  if (kind == CLPK_CONV_3X3_S1 && cin % 64 == 0 && w_in >= kTileM && p.block_n % 32 == 0 && p.block_n <= 128) {
+    const char* e = getenv("CLPK_IGEMM_SLAB");
+    p.slab = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (p.slab) { p.ncta = 2; p.block_k = 64; }
   p.n_tiles_n = p.cout_pad / p.block_n;
   p.kpt = cin / p.block_k;
   p.ep = *ep;
@@ -758,22 +851,29 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   p.num_tiles = (int)nt;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
-  const int stage_bytes = kTileM * p.block_k * 2 + (p.block_n / p.ncta) * p.block_k * 2;
+  const int stage_bytes = p.slab ? kSlabABytes + 3 * (p.block_n / p.ncta) * 128
+                                 : kTileM * p.block_k * 2 + (p.block_n / p.ncta) * p.block_k * 2;
   // chunked epilogue whenever the tile has >= 32 channels and an NHWC output; its fp32 output (if any) is staged
   // through smem and written by TMA, a 16-bit output is stored directly from registers
   const bool f32_ok = p.ep.out_f32 != nullptr && (reinterpret_cast<uintptr_t>(p.ep.out_f32) & 15) == 0;
-  p.chunked = (p.block_n % 32 == 0 && cout % 32 == 0 && (f32_ok || (p.ep.out_op && !p.ep.out_f32)) && !p.ep.out_nchw) ? 1 : 0;
+  p.chunked = (p.block_n % 32 == 0 && cout % 32 == 0 && (f32_ok || (p.ep.out_op && !p.ep.out_f32)) && !p.ep.out_nchw &&
+               warp_subbox_ok(p.wbox)) ? 1 : 0;
   const int fixed = 1024 /*alignment slack*/ + epi_vector_bytes(p.block_n) + (int)sizeof(PipeBarriers) + 16;
   p.n_staging = 0;
-  if (p.chunked && (p.ep.out_f32 || p.ep.resid)) {
-    CLPK_REQUIRE(p.ep.out_f32 != nullptr, "a residual input needs the fp32 output");
-    // two staging slots per epilogue group when the smem ring keeps its depth, else one
-    const int want_stages = (p.block_k == 128) ? 3 : 4;
-    int per_group = 2;
-    if ((kSmemBudget - fixed - kEpiGroups * 2 * kStagingBytes) / stage_bytes < want_stages) per_group = 1;
+  const bool op16_ok = p.ep.out_op != nullptr && (reinterpret_cast<uintptr_t>(p.ep.out_op) & 15) == 0;
+  if (p.chunked && (p.ep.out_f32 || p.ep.resid || op16_ok)) {
+    CLPK_REQUIRE(p.ep.out_f32 != nullptr || !p.ep.resid, "a residual input needs the fp32 output");
+    // as many staging slots per epilogue group (<= 3) as the smem ring can spare without losing depth; a residual
+    // epilogue keeps (slots - 1) chunk loads in flight per group, so its throughput hangs on this
+    const int want_stages = (p.block_k == 128 || p.slab) ? 3 : 4;
+    int per_group = p.ep.resid ? 3 : 2;
+    while (per_group > 1 && (kSmemBudget - fixed - kEpiGroups * per_group * kStagingBytes) / stage_bytes < want_stages) --per_group;
     { const char* e = getenv("CLPK_IGEMM_SLOTS"); if (e && atoi(e) >= 1 && atoi(e) <= 3) per_group = atoi(e); }
     p.n_staging = kEpiGroups * per_group;
-    if ((kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes < 2) { p.n_staging = 0; p.chunked = 0; }
+    if ((kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes < 2) {
+      p.n_staging = 0;
+      if (p.ep.out_f32 || p.ep.resid) p.chunked = 0;  // (a 16-bit-only output falls back to direct stores from registers)
+    }
   }
   p.gn_groups = p.gn_slots = 0;
   p.gn_sub = 1;
@@ -792,7 +892,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
 
   const int atom_k = std::min(p.block_k, 64);  // one TMA box = one swizzle atom (<= 128 bytes of K per row)
   const int swz = atom_k * 2;
-  cuuint32_t box_a[5] = {(cuuint32_t)atom_k, (cuuint32_t)p.wbox, 1, (cuuint32_t)p.hbox, 1};
+  cuuint32_t box_a[5] = {(cuuint32_t)atom_k, (cuuint32_t)(p.slab ? p.wbox + 2 : p.wbox), 1, (cuuint32_t)p.hbox, 1};
   const CUtensorMapDataType op_dt = p.op_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   int rc = encode_map(&out->map_a, x_bf16, 5, dims, strides, box_a, swz, op_dt);
   if (rc) return rc;
@@ -804,12 +904,26 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   // fp32 NHWC output maps for the TMA-store epilogue: [C, Wgrid, 1, Hgrid, B] per phase (transposed conv: the phase
   // (ph,pw) owns output pixels (2h+ph, 2w+pw) -> base offset + doubled w/h strides)
   memset(&out->maps_out, 0, sizeof(out->maps_out));
+  const int wsub = std::min(p.wbox, 32);
+  if (p.chunked && !p.ep.out_f32 && p.ep.out_op && p.n_staging > 0) {
+    // 16-bit NHWC output map for the staged store of a 16-bit-only output: 32 channels (64 B) per row, 64B swizzle
+    const long long CO = cout, OW = p.out_w, OH = p.out_h, sc = p.out_scale;
+    cuuint64_t odims[5] = {(cuuint64_t)CO, (cuuint64_t)p.grid_w, 1, (cuuint64_t)p.grid_h, (cuuint64_t)batch};
+    cuuint64_t ostr[4] = {(cuuint64_t)(sc * CO * 2), (cuuint64_t)(sc * OW * CO * 2), (cuuint64_t)(sc * OW * CO * 2),
+                          (cuuint64_t)(OH * OW * CO * 2)};
+    cuuint32_t obox[5] = {32, (cuuint32_t)wsub, 1, (cuuint32_t)(32 / wsub), 1};  // one epilogue warp's 32 tile rows
+    for (int phase = 0; phase < p.phases; ++phase) {
+      const long long off = ((long long)(phase >> 1) * OW + (phase & 1)) * CO;
+      rc = encode_map(&out->maps_out.m[phase], reinterpret_cast<uint16_t*>(p.ep.out_op) + off, 5, odims, ostr, obox, 64, op_dt);
+      if (rc) return rc;
+    }
+  }
   if (p.chunked && p.ep.out_f32) {
     const long long CO = cout, OW = p.out_w, OH = p.out_h, sc = p.out_scale;
     cuuint64_t odims[5] = {(cuuint64_t)CO, (cuuint64_t)p.grid_w, 1, (cuuint64_t)p.grid_h, (cuuint64_t)batch};
     cuuint64_t ostr[4] = {(cuuint64_t)(sc * CO * 4), (cuuint64_t)(sc * OW * CO * 4), (cuuint64_t)(sc * OW * CO * 4),
                           (cuuint64_t)(OH * OW * CO * 4)};
-    cuuint32_t obox[5] = {32, (cuuint32_t)p.wbox, 1, (cuuint32_t)p.hbox, 1};
+    cuuint32_t obox[5] = {32, (cuuint32_t)wsub, 1, (cuuint32_t)(32 / wsub), 1};  // one epilogue warp's 32 tile rows
     memset(&out->maps_res, 0, sizeof(out->maps_res));
     for (int phase = 0; phase < p.phases; ++phase) {
       const long long off = ((long long)(phase >> 1) * OW + (phase & 1)) * CO;
@@ -827,9 +941,9 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   return rc;
 }
 
-template <int BK, int NC>
+template <int BK, int NC, bool SLAB = false>
 static cudaError_t set_smem_attr() {
-  return cudaFuncSetAttribute(conv_igemm_kernel<BK, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  return cudaFuncSetAttribute(conv_igemm_kernel<BK, NC, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
 }
 
 int igemm_init() {
@@ -842,12 +956,13 @@ int igemm_init() {
     if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2>();
     if (attr_err == cudaSuccess) attr_err = set_smem_attr<32, 2>();
     if (attr_err == cudaSuccess) attr_err = set_smem_attr<128, 2>();
+    if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2, true>();
   });
   CLPK_CHECK_CUDA(attr_err);
   return CLPK_OK;
 }
 
-template <int BK, int NC>
+template <int BK, int NC, bool SLAB = false>
 static cudaError_t launch_variant(const IgemmLaunch& L, cudaStream_t stream) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)L.grid);
@@ -861,14 +976,15 @@ static cudaError_t launch_variant(const IgemmLaunch& L, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (NC > 1) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BK, NC>, L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
+  return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BK, NC, SLAB>, L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
 }
 
 int igemm_launch(const IgemmLaunch& L, cudaStream_t stream) {
   int irc = igemm_init();
   if (irc) return irc;
   cudaError_t e;
-  if (L.p.block_k == 128) e = (L.p.ncta == 2) ? launch_variant<128, 2>(L, stream) : launch_variant<128, 1>(L, stream);
+  if (L.p.slab) e = launch_variant<64, 2, true>(L, stream);
+  else if (L.p.block_k == 128) e = (L.p.ncta == 2) ? launch_variant<128, 2>(L, stream) : launch_variant<128, 1>(L, stream);
   else if (L.p.block_k == 64) e = (L.p.ncta == 2) ? launch_variant<64, 2>(L, stream) : launch_variant<64, 1>(L, stream);
   else e = (L.p.ncta == 2) ? launch_variant<32, 2>(L, stream) : launch_variant<32, 1>(L, stream);
   CLPK_CHECK_CUDA(e);

@@ -20,6 +20,9 @@ struct IgemmParams {
   int ncta;                 // 1, or 2 = CTA pairs (tcgen05 cta_group::2): two M tiles share one B tile split over the pair
   int spatial_tiles;        // batch * tiles_h * tiles_w
   int op_f16;               // operand format: 1 = fp16, 0 = bf16
+  int slab;                 // 1: row-slab mainloop (3x3 s1, one image row per tile): a stage holds ONE (wbox+2)-pixel slab of
+                            // input row h+r-1 and the three weight blocks of taps (r, 0..2); the taps read the slab at row
+                            // offsets 0/1/2 through shifted smem descriptors -> each A byte is fetched 3x instead of 9x
   int chunked;              // 1: chunked epilogue (32 columns at a time: folded vectors, fused GN stats, staged TMA store of
                             // the fp32 output if there is one); 0: narrow direct path (the 3-channel `out` conv)
   int n_staging;            // epilogue staging buffers (128 rows x 128 B each) for the TMA-store path, 0 = direct stores

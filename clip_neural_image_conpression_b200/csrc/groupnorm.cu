@@ -133,12 +133,81 @@ gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float
   }
 }
 
-// y = (x - mean) * rstd * gamma + beta, optional SiLU, 8 channels per thread iteration (32 B fp32 or 16 B 16-bit in,
-// 16 B out).  Statistics come either from `stats` (mean, rstd) or — when `partial` is given — are folded in-kernel from
-// the per-tile partial sums a conv epilogue wrote (same fixed-order fp64 fold as gn_finalize_kernel, one warp per
-// group, redundantly per block: a few KB of L2 reads instead of a separate launch).
+// y = (x - mean) * rstd * gamma + beta, optional SiLU, 8 channels per thread and access (32 B fp32 or 16 B 16-bit in,
+// 16 B out), evaluated as one FMA per element with (scale, shift) = (rstd*gamma, beta - mean*rstd*gamma).  Statistics
+// come either from `stats` (mean, rstd) or — when `partial` is given — are folded in-kernel from the per-tile partial
+// sums a conv epilogue wrote (same fixed-order fp64 fold as gn_finalize_kernel, one warp per group, redundantly per
+// block: a few KB of L2 reads instead of a separate launch).
+// HBM-bound: every thread keeps kGnUnroll independent 16/32-byte loads in flight (2048 threads/SM x 16 B alone is below
+// the ~44 KB/SM that 6.5 TB/s x ~1 us of loaded latency needs), SiLU costs ONE MUFU op per element
+// (x*sigmoid(x) = h + h*tanh(h), h = x/2, tanh.approx.f32) instead of ex2 + rcp, and when the grid stride is a multiple
+// of the octets per pixel (kHoist) each thread owns one channel octet, so its 8 (scale, shift) pairs live in registers.
+constexpr int kGnUnroll = 4;
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+
 template <bool kIn16>
-__global__ void __launch_bounds__(kGnThreads)
+__device__ __forceinline__ void gn_load8(const void* __restrict__ xin, long long idx, uint4& a, uint4& b) {
+  if (kIn16) {
+    a = __ldcs(reinterpret_cast<const uint4*>(xin) + idx);
+  } else {
+    const uint4* xb = reinterpret_cast<const uint4*>(xin) + 2 * idx;
+    a = __ldcs(xb);
+    b = __ldcs(xb + 1);
+  }
+}
+
+template <bool kIn16>
+__device__ __forceinline__ uint4 gn_transform8(const uint4& a, const uint4& b, const float (&sc)[8], const float (&sh)[8],
+                                               bool silu, bool f16) {
+  float v[8];
+  if (kIn16) {
+    const uint32_t w4[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[2 * k] = from_op((uint16_t)(w4[k] & 0xffffu), f16);
+      v[2 * k + 1] = from_op((uint16_t)(w4[k] >> 16), f16);
+    }
+  } else {
+    v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+    v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+  }
+  float r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    r[k] = fmaf(v[k], sc[k], sh[k]);
+    if (silu) r[k] = silu_tanh(r[k]);
+  }
+  return make_uint4(pack_op2(r[0], r[1], f16), pack_op2(r[2], r[3], f16), pack_op2(r[4], r[5], f16),
+                    pack_op2(r[6], r[7], f16));
+}
+
+// (scale, shift) of the 8 channels starting at `ch`
+__device__ __forceinline__ void gn_affine8(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           const float2* st_s, int ch, int cpg, float (&sc)[8], float (&sh)[8]) {
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch) + 1);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch) + 1);
+  const float2 s0 = st_s[ch / cpg], s1 = st_s[(ch + 4) / cpg];
+  const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float2 s = k < 4 ? s0 : s1;
+    sc[k] = s.y * g[k];
+    sh[k] = fmaf(-s.x, sc[k], bb[k]);
+  }
+}
+
+template <bool kIn16, bool kHoist>
+__global__ void __launch_bounds__(kGnThreads, 4)
 gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float2* __restrict__ stats, const float2* __restrict__ partial, int slots, double n_per_group,
                 float eps, uint16_t* __restrict__ y, int hw, int c, int groups, int silu, int op_f16) {
@@ -173,38 +242,29 @@ gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, c
   const unsigned oc = (unsigned)c >> 3;  // 8-channel octets per pixel
   const int cpg = c / groups;
   const unsigned total = (unsigned)hw * oc;
-  uint4* yb = reinterpret_cast<uint4*>(y) + (long long)b * total;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const unsigned o = i % oc;
-    const int ch = (int)o * 8;
-    float v[8];
-    if (kIn16) {
-      const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(xin) + (long long)b * total + i);
-      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+  const unsigned stride = gridDim.x * blockDim.x;
+  const long long base = (long long)b * total;
+  uint4* yb = reinterpret_cast<uint4*>(y) + base;
+  const bool act = silu != 0;
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  float sc[8], sh[8];
+  if (kHoist) gn_affine8(gamma, beta, st_s, (int)(i % oc) * 8, cpg, sc, sh);
+  // main loop: kGnUnroll independent loads in flight, then transform + store
+  for (; (unsigned long long)i + (unsigned long long)(kGnUnroll - 1) * stride < total; i += kGnUnroll * stride) {
+    uint4 a[kGnUnroll], bq[kGnUnroll];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        v[2 * k] = from_op((uint16_t)(w4[k] & 0xffffu), f16);
-        v[2 * k + 1] = from_op((uint16_t)(w4[k] >> 16), f16);
-      }
-    } else {
-      const float4* xb = reinterpret_cast<const float4*>(xin) + (long long)b * total * 2;
-      const float4 v0 = __ldcs(xb + 2ll * i), v1 = __ldcs(xb + 2ll * i + 1);
-      v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-    }
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch) + 1);
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch) + 1);
-    const float2 s0 = st_s[ch / cpg], s1 = st_s[(ch + 4) / cpg];
-    float r[8];
-    r[0] = (v[0] - s0.x) * s0.y * g0.x + b0.x; r[1] = (v[1] - s0.x) * s0.y * g0.y + b0.y;
-    r[2] = (v[2] - s0.x) * s0.y * g0.z + b0.z; r[3] = (v[3] - s0.x) * s0.y * g0.w + b0.w;
-    r[4] = (v[4] - s1.x) * s1.y * g1.x + b1.x; r[5] = (v[5] - s1.x) * s1.y * g1.y + b1.y;
-    r[6] = (v[6] - s1.x) * s1.y * g1.z + b1.z; r[7] = (v[7] - s1.x) * s1.y * g1.w + b1.w;
-    if (silu) {
+    for (int u = 0; u < kGnUnroll; ++u) gn_load8<kIn16>(xin, base + i + (long long)u * stride, a[u], bq[u]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) r[k] = silu_f(r[k]);
+    for (int u = 0; u < kGnUnroll; ++u) {
+      if (!kHoist) gn_affine8(gamma, beta, st_s, (int)((i + u * stride) % oc) * 8, cpg, sc, sh);
+      yb[i + u * stride] = gn_transform8<kIn16>(a[u], bq[u], sc, sh, act, f16);
     }
-    yb[i] = make_uint4(pack_op2(r[0], r[1], f16), pack_op2(r[2], r[3], f16), pack_op2(r[4], r[5], f16),
-                       pack_op2(r[6], r[7], f16));
+  }
+  for (; i < total; i += stride) {
+    uint4 a, bq;
+    gn_load8<kIn16>(xin, base + i, a, bq);
+    if (!kHoist) gn_affine8(gamma, beta, st_s, (int)(i % oc) * 8, cpg, sc, sh);
+    yb[i] = gn_transform8<kIn16>(a, bq, sc, sh, act, f16);
   }
 }
 
@@ -251,15 +311,17 @@ int launch_gn_apply_ex(const void* x, int x_is_16, const float* gamma, const flo
                "GroupNorm needs C %% 8 == 0 and (C/groups) %% 4 == 0 (C=%d groups=%d)", s.c, s.groups);
   CLPK_REQUIRE(octs < (1ll << 31) && s.groups <= 32, "GroupNorm: image too large or too many groups");
   const int per_img_blocks = (int)std::min<long long>((octs + kGnThreads - 1) / kGnThreads,
-                                                      std::max(1, num_sms() * 8 / s.batch));
+                                                      std::max(1, num_sms() * 4 / s.batch));  // one wave at 4 blocks / SM
   dim3 agrid(std::max(per_img_blocks, 1), s.batch);
   uint16_t* y = reinterpret_cast<uint16_t*>(y_op);
-  if (x_is_16)
-    gn_apply_kernel<true><<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, partial, slots, n_per_group, eps, y, s.hw,
-                                                            s.c, s.groups, silu, op_dtype == CLPK_OP_F16);
-  else
-    gn_apply_kernel<false><<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, partial, slots, n_per_group, eps, y,
-                                                             s.hw, s.c, s.groups, silu, op_dtype == CLPK_OP_F16);
+  const bool hoist = ((long long)agrid.x * kGnThreads) % (s.c / 8) == 0;  // every thread stays on one channel octet
+  const bool f16 = op_dtype == CLPK_OP_F16;
+#define CLPK_GN_APPLY(IN16, HOIST)                                                                                    \
+  gn_apply_kernel<IN16, HOIST><<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, partial, slots, n_per_group, eps, \
+                                                                 y, s.hw, s.c, s.groups, silu, f16)
+  if (x_is_16) { if (hoist) CLPK_GN_APPLY(true, true); else CLPK_GN_APPLY(true, false); }
+  else { if (hoist) CLPK_GN_APPLY(false, true); else CLPK_GN_APPLY(false, false); }
+#undef CLPK_GN_APPLY
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }

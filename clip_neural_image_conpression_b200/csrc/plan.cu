@@ -6,7 +6,10 @@
 //   Y     16-bit NHWC conv1 output of the current ResBlock (max size over levels); its GroupNorm statistics are taken
 //         from the fp32 accumulators in the conv1 epilogue, only the stored copy is rounded
 //   T     bf16 NHWC  GroupNorm+SiLU output = A operand of the ResBlock convs (max size)
-//   D     bf16 NHWC  bf16 copy of x feeding the stride-2 / transposed convs (max size)
+//   X16[l] 16-bit NHWC copy of X[l] = the A operand of the stride-2 / transposed convs, written by the conv2 epilogue of
+//         the last ResBlock of a level.  (With env CLPK_X16=1 EVERY producer of X[l] writes it and the GroupNorms on the
+//         residual stream read it instead of fp32 X: same HBM bytes, but measured slower — the extra direct 16-bit
+//         stores cost the smem/L1-bound conv epilogues more than the GroupNorm reads save.)
 //   packed bf16 weights [Cout][tap][Cin] per conv, fp32 bias / gamma / beta / Linear weights, FiLM weights of all
 //   ResBlocks concatenated into one [2*sumC, time_dim] matrix so ONE small GEMV launch yields every (1+scale, shift).
 #include "conv_igemm.cuh"
@@ -43,7 +46,7 @@ struct ResBlockPlan {
   GnPlan gn1, gn2;
   ConvPlan conv1, conv2;
   int film_off = 0;      // scale1p at [film_off, film_off+c), shift at [film_off+c, film_off+2c)
-  bool emit_bf16 = false;  // conv2 also writes a bf16 copy of x into D (feeds the next resampling conv)
+  bool emit16 = false;   // conv2 also writes the 16-bit copy X16[level] (feeds the next resampling conv)
   bool y16 = false;        // conv1 output kept in the 16-bit operand format (needs fused GroupNorm statistics)
 };
 
@@ -71,7 +74,9 @@ struct clpk_plan {
   // workspace
   std::vector<float*> X;
   uint16_t* Y = nullptr;     // conv1 output of the current ResBlock, stored in the 16-bit operand format
-  uint16_t *T = nullptr, *D = nullptr;  // 16-bit operand buffers (fp16 or bf16, cfg.op_dtype)
+  uint16_t* T = nullptr;     // GroupNorm+SiLU output = conv A operand (fp16 or bf16, cfg.op_dtype)
+  std::vector<uint16_t*> X16;  // per level: 16-bit copy of X[l]
+  bool x16_gn = false;       // env CLPK_X16=1: GroupNorms on the residual stream read X16 instead of fp32 X
   float* Yf = nullptr;       // fp32 conv1 output, only for ResBlocks whose GroupNorm statistics cannot be fused
   void* gn_ws = nullptr;
   float *temb = nullptr, *h1 = nullptr, *ht = nullptr, *hcond = nullptr, *film = nullptr, *zemb = nullptr;
@@ -250,9 +255,14 @@ int run_groupnorm(clpk_plan* P, const void* x, int x_is_16, const GnPlan& gn, cu
   return rc;
 }
 
+// GroupNorm over the residual stream of `level`: the 16-bit copy when its statistics are fused, else fp32 X
+int run_groupnorm_x(clpk_plan* P, int level, const GnPlan& gn, cudaStream_t s) {
+  if (gn.fused && P->x16_gn) return run_groupnorm(P, P->X16[level], 1, gn, s);
+  return run_groupnorm(P, P->X[level], 0, gn, s);
+}
+
 int run_resblock(clpk_plan* P, ResBlockPlan& rb, cudaStream_t s) {
-  float* X = P->X[rb.level];
-  CLPK_TRY(run_groupnorm(P, X, 0, rb.gn1, s));                     // blocks.py:41 act(norm1(x))
+  CLPK_TRY(run_groupnorm_x(P, rb.level, rb.gn1, s));               // blocks.py:41 act(norm1(x))
   CLPK_TIMED(P, kProfConvRes, s, igemm_launch(rb.conv1.L, s));     // conv1 + FiLM -> Y   (blocks.py:41-42)
   CLPK_TRY(run_groupnorm(P, rb.y16 ? (const void*)P->Y : (const void*)P->Yf, rb.y16 ? 1 : 0, rb.gn2, s));  // blocks.py:43
   CLPK_TIMED(P, kProfConvRes, s, igemm_launch(rb.conv2.L, s));     // conv2 + x -> X      (blocks.py:43-44)
@@ -271,16 +281,16 @@ int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s) {
   for (int l = 0; l < P->n_levels; ++l) {
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
-    CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->downs[l].L, s));  // D (bf16 copy of X[l]) -> X[l+1]
+    CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->downs[l].L, s));  // X16[l] -> X[l+1], X16[l+1]
   }
   CLPK_TRY(run_resblock(P, P->rbs[r++], s));
   CLPK_TRY(run_resblock(P, P->rbs[r++], s));
   for (int l = P->n_levels - 1; l >= 0; --l) {
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
-    CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->ups[l].L, s));  // D (bf16 of X[l+1]) -> X[l] += convT (unet.py:102-104)
+    CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->ups[l].L, s));  // X16[l+1] -> X[l] += convT (unet.py:102-104)
   }
-  CLPK_TRY(run_groupnorm(P, P->X[0], 0, P->out_gn, s));            // out_norm, no activation (unet.py:105)
+  CLPK_TRY(run_groupnorm_x(P, 0, P->out_gn, s));                   // out_norm, no activation (unet.py:105)
   CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->out_conv.L, s));  // -> eps_buf (NCHW)
   return CLPK_OK;
 }
@@ -380,11 +390,14 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     float* x = nullptr;
     CLPK_TRY(P->alloc(&x, n));
     P->X.push_back(x);
+    uint16_t* x16 = nullptr;
+    CLPK_TRY(P->alloc(&x16, n));
+    P->X16.push_back(x16);
   }
+  P->x16_gn = getenv("CLPK_X16") != nullptr;
   CLPK_TRY(P->alloc(&P->Y, max_act));
   CLPK_TRY(P->alloc(&P->Yf, max_act));
   CLPK_TRY(P->alloc(&P->T, max_act));
-  CLPK_TRY(P->alloc(&P->D, max_act));
   long long gn_bytes = 0;
   for (int l = 0; l <= L; ++l)
     gn_bytes = std::max(gn_bytes, gn_ws_bytes(gn_shape(batch, P->lv_h[l] * P->lv_w[l], P->lv_c[l],
@@ -414,7 +427,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   for (size_t i = 0; i < specs.size(); ++i) {
     ResBlockPlan& rb = P->rbs[i];
     rb.film_off = off;
-    rb.emit_bf16 = specs[i].emit;
+    rb.emit16 = specs[i].emit || P->x16_gn;
     CLPK_TRY(make_resblock(P, tab, specs[i].prefix, specs[i].level, &rb));
     off += 2 * rb.c;
   }
@@ -460,7 +473,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     e2.bias = rb.conv2.bias;
     e2.resid = P->X[rb.level];
     e2.out_f32 = P->X[rb.level];
-    e2.out_op = rb.emit_bf16 ? P->D : nullptr;
+    e2.out_op = rb.emit16 ? P->X16[rb.level] : nullptr;
     e2.cout_valid = rb.c;
     wire_gn(&e2, gn_after_conv2[i]);
     CLPK_TRY(bind_conv(P, &rb.conv2, P->T, e2));
@@ -476,9 +489,10 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     clpk_conv_epilogue ed{};
     ed.bias = dn.bias;
     ed.out_f32 = P->X[l + 1];
+    ed.out_op = P->x16_gn ? P->X16[l + 1] : nullptr;
     ed.cout_valid = P->lv_c[l + 1];
     wire_gn(&ed, gn_after_down[l]);
-    CLPK_TRY(bind_conv(P, &dn, P->D, ed));
+    CLPK_TRY(bind_conv(P, &dn, P->X16[l], ed));
     P->flops_fwd += dn.flops;
     // up stage i = L-1-l maps level l+1 -> l: module up.(3*i+2), ConvTranspose2d(C[l+1] -> C[l])
     const int i = L - 1 - l;
@@ -489,9 +503,10 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     eu.bias = up.bias;
     eu.resid = P->X[l];  // skip connection, added in place
     eu.out_f32 = P->X[l];
+    eu.out_op = P->x16_gn ? P->X16[l] : nullptr;
     eu.cout_valid = P->lv_c[l];
     wire_gn(&eu, gn_after_up[l]);
-    CLPK_TRY(bind_conv(P, &up, P->D, eu));
+    CLPK_TRY(bind_conv(P, &up, P->X16[l + 1], eu));
     P->flops_fwd += up.flops;
   }
   // ---- stem: in_conv.weight [base, img_ch, 3, 3] = [base][27] -> zero-padded [base][32] -> packed pointwise weight
@@ -515,6 +530,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     clpk_conv_epilogue es{};
     es.bias = st.bias;
     es.out_f32 = P->X[0];
+    es.out_op = P->x16_gn ? P->X16[0] : nullptr;
     es.cout_valid = cfg->base;
     wire_gn(&es, &P->rbs[0].gn1);
     CLPK_TRY(bind_conv(P, &st, P->stem_cols, es));
@@ -704,5 +720,20 @@ extern "C" int clpk_plan_work_breakdown(const clpk_plan* P, double* conv_res_flo
   b += P->out_conv.flops;
   g += (double)P->B * P->H * P->W * P->cfg.base;  // out_norm
   *conv_res_flops = a; *conv_other_flops = b; *gn_elements = g;
+  return CLPK_OK;
+}
+
+// algorithmic HBM bytes of all GroupNorm(+SiLU) applies of one forward at the plan's batch: every instance reads its
+// input once (2 B / element from a 16-bit tensor, 4 B from fp32) and writes the 16-bit operand once (2 B)
+extern "C" int clpk_plan_groupnorm_bytes(const clpk_plan* P, double* bytes) {
+  CLPK_REQUIRE(P && bytes, "clpk_plan_groupnorm_bytes: null argument");
+  double tot = 0;
+  auto in_bytes_x = [&](const GnPlan& gn) { return (gn.fused && P->x16_gn) ? 2.0 : 4.0; };
+  for (const ResBlockPlan& rb : P->rbs) {
+    const double n = (double)P->B * rb.h * rb.w * rb.c;
+    tot += n * (in_bytes_x(rb.gn1) + 2.0) + n * ((rb.y16 ? 2.0 : 4.0) + 2.0);
+  }
+  tot += (double)P->B * P->H * P->W * P->cfg.base * (in_bytes_x(P->out_gn) + 2.0);
+  *bytes = tot;
   return CLPK_OK;
 }

@@ -214,6 +214,9 @@ int clpk_plan_profile_steps(clpk_plan* plan, int iters, float* ms_out6, int* cou
 /* Algorithmic work of one forward at the plan's batch: FLOPs of conv classes 0 and 1, fp32 elements read by GroupNorm. */
 int clpk_plan_work_breakdown(const clpk_plan* plan, double* conv_res_flops, double* conv_other_flops,
                              double* gn_elements);
+/* Algorithmic HBM bytes of all GroupNorm(+SiLU) applies of one forward: input read once (2 B / element when the input is
+ * a 16-bit tensor, 4 B when fp32) + 16-bit operand written once. */
+int clpk_plan_groupnorm_bytes(const clpk_plan* plan, double* bytes);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Output side: reconstruct_diffusion.py:55-56, PKG/eval/metrics.py:16-29
