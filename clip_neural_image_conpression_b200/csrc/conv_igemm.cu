@@ -687,7 +687,15 @@ static void tile_geometry(int kind, int h_in, int w_in, int* grid_h, int* grid_w
   *grid_h = (kind == CLPK_CONV_3X3_S2) ? h_in / 2 : h_in;
   *grid_w = (kind == CLPK_CONV_3X3_S2) ? w_in / 2 : w_in;
   *phases = (kind == CLPK_CONVT_4X4_S2) ? 4 : 1;
-  *wbox = std::min(*grid_w, kTileM);
+  // tile width: the whole row when it is <= 128 pixels and 32 tile rows form a rectangle of it (the epilogue moves
+  // per-warp 32-row sub-boxes by TMA), else the largest power of two below it (edge tiles are masked / clipped)
+  int wb = std::min(*grid_w, kTileM);
+  if (!(wb % 32 == 0 || 32 % wb == 0)) {
+    int p2 = 1;
+    while (p2 * 2 <= wb) p2 *= 2;
+    wb = p2;
+  }
+  *wbox = wb;
   *hbox = std::max(1, std::min(*grid_h, kTileM / *wbox));
 }
 
@@ -841,8 +849,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     p.a_dim_w = w_in; p.a_dim_p = 1; p.a_dim_h = h_in;
   }
   // M tile = wbox x hbox patch, wbox*hbox <= 128
-  p.wbox = std::min(p.grid_w, kTileM);
-  p.hbox = std::max(1, std::min(p.grid_h, kTileM / p.wbox));
+  { int gh, gw, ph; tile_geometry(kind, h_in, w_in, &gh, &gw, &p.wbox, &p.hbox, &ph); }
   p.tiles_w = (p.grid_w + p.wbox - 1) / p.wbox;
   p.tiles_h = (p.grid_h + p.hbox - 1) / p.hbox;
   p.spatial_tiles = batch * p.tiles_h * p.tiles_w;
