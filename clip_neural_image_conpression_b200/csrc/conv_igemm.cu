@@ -232,9 +232,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const TileCoord tc = decode_tile(p, tile, (int)rank);
         const int w_row = tc.phase * p.cout_pad + tc.n0 + (int)rank * b_rows;
         if (p.ep.resid && p.chunked && tc.ok && elect_one()) {
-          // the epilogue will add this residual tile: pull it into L2 while the MMAs run
-          for (int c = 0; c < p.block_n; c += 32)
-            tma_prefetch_5d(&maps_res.m[tc.phase], tc.n0 + c, tc.w0, 0, tc.h0, tc.b);
+          // the epilogue will add this residual tile: pull it into L2 while the MMAs run (the residual map's box is one
+          // epilogue warp's 32-row sub-box)
+          for (int q = 0; q < p.res_ahead; ++q) {
+            const int qh = (q * 32) / p.wbox, qw = q * 32 - qh * p.wbox;
+            if (qh >= p.hbox) break;
+            for (int c = 0; c < p.block_n; c += 32)
+              tma_prefetch_5d(&maps_res.m[tc.phase], tc.n0 + c, tc.w0 + qw, 0, tc.h0 + qh, tc.b);
+          }
         }
         __syncwarp();
         int tap = 0, kc = 0;
@@ -775,24 +780,30 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   p.cin = cin;
   p.cout_pad = igemm_cout_pad(cout);
   p.block_n = igemm_block_n(p.cout_pad);
-  // Tile configuration (measured on B200, tools/bench_conv.py): N >= 256 tiles run as CTA pairs (cta_group::2, the B
-  // tile split over the pair) with 64-wide k-blocks; N <= 128 tiles run single-CTA with 128-wide k-blocks (8 MMAs per
-  // barrier handshake) — the handshake, not the MMA, bounds a 128x128 k-block of 64.
-  p.ncta = (p.block_n >= 256) ? 2 : 1;
+  // Tile configuration (measured on B200, tools/bench_conv.py): N >= 128 tiles run as CTA pairs (cta_group::2, M = 256,
+  // the B tile split over the pair -> a third less operand fill per MMA) with 64-wide k-blocks; narrower tiles and the
+  // pointwise stem GEMM run single-CTA (128-wide k-blocks when Cin allows: 8 MMAs per barrier handshake).
+  p.ncta = (p.block_n >= 256 || (p.block_n == 128 && kind != CLPK_CONV_1X1)) ? 2 : 1;
   { const char* e = getenv("CLPK_IGEMM_NCTA"); if (e && (atoi(e) == 1 || atoi(e) == 2)) p.ncta = atoi(e); }
   if (p.block_n % 32 != 0) p.ncta = 1;  // a CTA pair splits N in two halves that must stay multiples of 16
   p.block_k = (cin % 128 == 0 && p.ncta == 1) ? 128 : (cin % 64 == 0) ? 64 : 32;
+  // a short K loop with a residual epilogue (the transposed conv: 4 taps) is epilogue-bound: spend the shared memory on
+  // residual look-ahead slots rather than on 128-wide k-blocks
+  if (p.block_k == 128 && ep->resid) p.block_k = 64;
   { const char* e = getenv("CLPK_IGEMM_BK");
     if (e && atoi(e) == 64 && p.block_k == 128) p.block_k = 64;
     if (e && atoi(e) == 128 && cin % 128 == 0) p.block_k = 128; }
   // Row-slab mainloop for 3x3 s1 convs whose M tile is one image row segment (W >= 128): operand fill traffic drops
   // from 9 A tiles + 9 B tiles to 3 slabs + 9 B tiles per channel block, and CTA pairs halve the B part again.
   p.slab = 0;
-  if (kind == CLPK_CONV_3X3_S1 && cin % 64 == 0 && w_in >= kTileM && p.block_n % 32 == 0 && p.block_n <= 128) {
+  // A stage holds the 3 weight blocks of a kernel row, so the per-CTA share of N must stay <= 64 rows: CTA pairs for
+  // N <= 128, a single CTA for narrow N (the 3-channel `out` conv, N padded to 16).
+  const bool slab_pair = p.block_n % 32 == 0 && p.block_n <= 128;
+  if (kind == CLPK_CONV_3X3_S1 && cin % 64 == 0 && w_in >= kTileM && (slab_pair || p.block_n <= 64)) {
     const char* e = getenv("CLPK_IGEMM_SLAB");
     p.slab = (e && atoi(e) == 0) ? 0 : 1;
   }
-  if (p.slab) { p.ncta = 2; p.block_k = 64; }
+  if (p.slab) { p.ncta = slab_pair ? 2 : 1; p.block_k = 64; }
   p.n_tiles_n = p.cout_pad / p.block_n;
   p.kpt = cin / p.block_k;
   p.ep = *ep;
@@ -891,7 +902,10 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     p.gn_groups = cout / p.ep.gn_cpg;
     p.gn_sub = p.ep.gn_cpg >= 32 ? p.ep.gn_cpg / 32 : 1;
   }
-  p.res_ahead = 0;  // (look-ahead is derived in the kernel from the slots per epilogue group)
+  // residual sub-boxes (of 4 per chunk) the producer prefetches into L2 per tile: measured neutral-to-harmful for the
+  // 3x3 convs (their per-warp look-ahead loads cover the latency), a small win for the short-K transposed conv
+  p.res_ahead = (kind == CLPK_CONVT_4X4_S2) ? 2 : 0;
+  { const char* e = getenv("CLPK_IGEMM_PREFETCH"); if (e) p.res_ahead = std::max(0, std::min(4, atoi(e))); }
   p.stages = std::min(kMaxStages, (kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes);
   CLPK_REQUIRE(p.stages >= 2, "tile does not fit shared memory");
   out->smem_bytes = p.stages * stage_bytes + p.n_staging * kStagingBytes + fixed;
@@ -964,6 +978,7 @@ int igemm_init() {
     if (attr_err == cudaSuccess) attr_err = set_smem_attr<32, 2>();
     if (attr_err == cudaSuccess) attr_err = set_smem_attr<128, 2>();
     if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2, true>();
+    if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 1, true>();
   });
   CLPK_CHECK_CUDA(attr_err);
   return CLPK_OK;
@@ -990,7 +1005,7 @@ int igemm_launch(const IgemmLaunch& L, cudaStream_t stream) {
   int irc = igemm_init();
   if (irc) return irc;
   cudaError_t e;
-  if (L.p.slab) e = launch_variant<64, 2, true>(L, stream);
+  if (L.p.slab) e = (L.p.ncta == 2) ? launch_variant<64, 2, true>(L, stream) : launch_variant<64, 1, true>(L, stream);
   else if (L.p.block_k == 128) e = (L.p.ncta == 2) ? launch_variant<128, 2>(L, stream) : launch_variant<128, 1>(L, stream);
   else if (L.p.block_k == 64) e = (L.p.ncta == 2) ? launch_variant<64, 2>(L, stream) : launch_variant<64, 1>(L, stream);
   else e = (L.p.ncta == 2) ? launch_variant<32, 2>(L, stream) : launch_variant<32, 1>(L, stream);
