@@ -5,8 +5,9 @@ Drop-in for the reference CLI (PKG/cli/eval.py:33-86): same flags, same printed 
   * images are decoded in micro-batches (`--batch`, default 8) instead of one at a time;
   * under torchrun the manifest is partitioned contiguously over the ranks (one GPU each); PSNR sums are all-reduced
     and rank 0 prints — nothing is exchanged inside the DDIM loop;
-  * PSNR is computed on the device in the uint8 domain; SSIM / LPIPS / CLIP-similarity are NaN (scikit-image, lpips and
-    open_clip are not part of this stack — the reference also reports NaN for the first two when they are missing).
+  * PSNR and SSIM are computed on the device in the uint8 domain (SSIM = scikit-image's structural_similarity defaults,
+    see eval/metrics.py); LPIPS / CLIP-similarity are NaN (lpips and open_clip need pretrained networks that are not
+    part of this stack — the reference also reports NaN for LPIPS when the package is missing).
 """
 from __future__ import annotations
 
@@ -19,7 +20,7 @@ import torch
 
 from .. import parallel
 from ..diffusion import DDIMSampler, NoiseScheduler
-from ..eval.metrics import psnr_batch
+from ..eval.metrics import psnr_batch, ssim_batch
 from ..io.bitstream import read_bitstreams
 from ..pipeline import decode_codes
 from .reconstruct_diffusion import load_net, load_store_meta
@@ -75,12 +76,13 @@ def main(argv=None) -> None:
     for i in range(0, len(mine), 64):
         chunk = mine[i:i + 64]
         orig = torch.from_numpy(np.stack([load_original(r["image"], args.size) for r in chunk])).to(device)
-        for r, p in zip(chunk, psnr_batch(orig, recon[i:i + len(chunk)])):
-            metrics.append({"image": r["image"], "psnr": p, "ssim": float("nan"), "lpips": float("nan"),
-                            "clip_sim": float("nan")})
+        rec = recon[i:i + len(chunk)]
+        for r, p, ss in zip(chunk, psnr_batch(orig, rec), ssim_batch(orig, rec)):   # eval.py:69-70, on the device
+            metrics.append({"image": r["image"], "psnr": p, "ssim": ss, "lpips": float("nan"), "clip_sim": float("nan")})
     finite = [m["psnr"] for m in metrics if np.isfinite(m["psnr"])]
+    ssims = [m["ssim"] for m in metrics if not np.isnan(m["ssim"])]
     # mean over non-NaN like eval.py:77-79 (inf from identical images is kept out of the all-reduced sum)
-    sums = parallel.reduce_sums([sum(finite), len(finite)], device)
+    sums = parallel.reduce_sums([sum(finite), len(finite), sum(ssims), len(ssims)], device)
     if world > 1:
         gathered = [None] * world
         torch.distributed.all_gather_object(gathered, metrics)
@@ -88,7 +90,8 @@ def main(argv=None) -> None:
     if rank == 0:
         avg = float(sums[0] / sums[1]) if float(sums[1]) > 0 else _nanmean([m["psnr"] for m in metrics])
         print(f"Average PSNR: {avg:.2f} dB")
-        print(f"Average SSIM: {_nanmean([m['ssim'] for m in metrics]):.4f}")
+        avg_ssim = float(sums[2] / sums[3]) if float(sums[3]) > 0 else float("nan")
+        print(f"Average SSIM: {avg_ssim:.4f}")
         print(f"Average LPIPS: {_nanmean([m['lpips'] for m in metrics]):.4f}")
         print(f"Average CLIP similarity: {_nanmean([m['clip_sim'] for m in metrics]):.4f}")
         if args.out_json:

@@ -335,9 +335,109 @@ __global__ void psnr_sqerr_kernel(const float* __restrict__ a, const float* __re
   if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out + img, acc);  // integer atomics: order independent, exact
 }
 
+// ------------------------------------------------------------------------------------------------ SSIM
+// metrics.py:32-46 -> skimage.metrics.structural_similarity(x1, x2, data_range=255, channel_axis=-1) on the uint8 images
+// of _to_uint8 (metrics.py:16-19).  scikit-image is neither vendored nor installed (parity unpinned); this
+// follows its published defaults: 7x7 uniform window (mean filter), K1 = 0.01, K2 = 0.03, sample covariance
+// (NP / (NP - 1)), float64 arithmetic, S = ((2 ux uy + C1)(2 vxy + C2)) / ((ux^2 + uy^2 + C1)(vx + vy + C2)), the
+// (win - 1) / 2 border cropped, mean over the remaining pixels per channel, then the mean over channels.
+// The window sums are exact integers here (skimage's two separable float64 passes round each 1-D mean: <= 1e-15 rel).
+constexpr int kSsimWin = 7, kSsimPad = 3, kSsimTileW = 32, kSsimTileH = 8;
+
+__global__ void __launch_bounds__(kSsimTileW * kSsimTileH)
+ssim_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, double* __restrict__ partial, int h, int w,
+                    int tiles_x) {
+  __shared__ uint8_t sa[kSsimTileH + 2 * kSsimPad][kSsimTileW + 2 * kSsimPad];
+  __shared__ uint8_t sb[kSsimTileH + 2 * kSsimPad][kSsimTileW + 2 * kSsimPad];
+  __shared__ double wsum[kSsimTileH];
+  const int tile = blockIdx.x, plane = blockIdx.y;  // plane = image * channels + channel (NCHW)
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int oy0 = kSsimPad + ty * kSsimTileH, ox0 = kSsimPad + tx * kSsimTileW;  // first output pixel of the tile
+  const float* pa = a + (long long)plane * h * w;
+  const float* pb = b + (long long)plane * h * w;
+  const int tid = threadIdx.y * kSsimTileW + threadIdx.x;
+  constexpr int kHaloW = kSsimTileW + 2 * kSsimPad, kHaloH = kSsimTileH + 2 * kSsimPad;
+  for (int i = tid; i < kHaloW * kHaloH; i += kSsimTileW * kSsimTileH) {
+    const int ly = i / kHaloW, lx = i - ly * kHaloW;
+    const int gy = oy0 - kSsimPad + ly, gx = ox0 - kSsimPad + lx;
+    const bool in = gy < h && gx < w;
+    sa[ly][lx] = in ? (uint8_t)metric_u8(pa[(long long)gy * w + gx]) : (uint8_t)0;
+    sb[ly][lx] = in ? (uint8_t)metric_u8(pb[(long long)gy * w + gx]) : (uint8_t)0;
+  }
+  __syncthreads();
+  const int oy = oy0 + threadIdx.y, ox = ox0 + threadIdx.x;
+  double s = 0.0;
+  if (oy < h - kSsimPad && ox < w - kSsimPad) {
+    int sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+#pragma unroll
+    for (int dy = 0; dy < kSsimWin; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < kSsimWin; ++dx) {
+        const int x = sa[threadIdx.y + dy][threadIdx.x + dx], y = sb[threadIdx.y + dy][threadIdx.x + dx];
+        sx += x; sy += y; sxx += x * x; syy += y * y; sxy += x * y;
+      }
+    constexpr double np_ = (double)(kSsimWin * kSsimWin), cov_norm = np_ / (np_ - 1.0);
+    const double c1 = (0.01 * 255.0) * (0.01 * 255.0), c2 = (0.03 * 255.0) * (0.03 * 255.0);
+    const double ux = sx / np_, uy = sy / np_;
+    const double vx = cov_norm * (sxx / np_ - ux * ux), vy = cov_norm * (syy / np_ - uy * uy);
+    const double vxy = cov_norm * (sxy / np_ - ux * uy);
+    s = ((2.0 * ux * uy + c1) * (2.0 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2));
+  }
+  // fixed-order block sum: shuffle tree per warp (= tile row), then the rows in order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) wsum[threadIdx.y] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int r = 0; r < kSsimTileH; ++r) t += wsum[r];
+    partial[(long long)plane * gridDim.x + tile] = t;
+  }
+}
+
+// one warp per image: per-channel mean of S over the cropped pixels, then the mean over channels
+__global__ void ssim_fold_kernel(const double* __restrict__ partial, double* __restrict__ out, int ch, int tiles,
+                                 double pixels_per_channel) {
+  const int img = blockIdx.x, lane = threadIdx.x;
+  double acc = 0.0;
+  for (int c = 0; c < ch; ++c) {
+    const double* pp = partial + ((long long)img * ch + c) * tiles;
+    double s = 0.0;
+    for (int k = lane; k < tiles; k += 32) s += pp[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    acc += s / pixels_per_channel;
+  }
+  if (lane == 0) out[img] = acc / (double)ch;
+}
+
 }  // namespace clpk
 
 using namespace clpk;
+
+extern "C" int64_t clpk_ssim_ws_bytes(int batch, int ch, int h, int w) {
+  if (batch <= 0 || ch <= 0 || h < kSsimWin || w < kSsimWin) return -1;
+  const long long tiles = (long long)((w - 2 * kSsimPad + kSsimTileW - 1) / kSsimTileW) *
+                          ((h - 2 * kSsimPad + kSsimTileH - 1) / kSsimTileH);
+  return (int64_t)(tiles * batch * ch * (long long)sizeof(double));
+}
+
+extern "C" int clpk_ssim_u8(const float* a, const float* b, double* out, void* ws, int batch, int ch, int h, int w,
+                            void* stream) {
+  CLPK_REQUIRE(a && b && out && ws && batch > 0 && ch > 0, "clpk_ssim_u8: bad arguments");
+  CLPK_REQUIRE(h >= kSsimWin && w >= kSsimWin, "clpk_ssim_u8: win_size 7 exceeds the image extent (%d x %d)", h, w);
+  const int tiles_x = (w - 2 * kSsimPad + kSsimTileW - 1) / kSsimTileW;
+  const int tiles_y = (h - 2 * kSsimPad + kSsimTileH - 1) / kSsimTileH;
+  CLPK_REQUIRE((long long)batch * ch <= 65535, "clpk_ssim_u8: too many image planes");
+  dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)(batch * ch));
+  dim3 block(kSsimTileW, kSsimTileH);
+  ssim_partial_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, b, reinterpret_cast<double*>(ws), h, w, tiles_x);
+  CLPK_CHECK_LAUNCH();
+  ssim_fold_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(ws), out, ch, tiles_x * tiles_y,
+                                                           (double)(h - 2 * kSsimPad) * (double)(w - 2 * kSsimPad));
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
 
 extern "C" const char* clpk_last_error(void) { return g_err; }
 extern "C" int clpk_version(void) { return 100; }

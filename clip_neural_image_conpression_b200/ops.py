@@ -15,7 +15,7 @@ from ._lib import CONV_3X3_S1, CONV_3X3_S2, CONVT_4X4_S2, ConvEpilogue, check, o
 
 __all__ = [
     "dequant_l2norm", "quant_encode", "quant_fit", "ddim_step", "timestep_embedding", "linear", "film_apply",
-    "groupnorm_silu", "pack_conv_weight", "conv_igemm", "conv_direct", "conv_in", "to_uint8_hwc", "psnr_sqerr_u8",
+    "groupnorm_silu", "pack_conv_weight", "conv_igemm", "conv_direct", "conv_in", "to_uint8_hwc", "psnr_sqerr_u8", "ssim_u8",
     "CONV_3X3_S1", "CONV_3X3_S2", "CONVT_4X4_S2",
 ]
 
@@ -253,4 +253,23 @@ def psnr_sqerr_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     per = a.numel() // bsz
     out = torch.empty(bsz, dtype=torch.int64, device=a.device)
     check(_lib.load().clpk_psnr_sqerr_u8(ptr(a), ptr(b), ptr(out), bsz, per, stream_ptr()), "clpk_psnr_sqerr_u8")
+    return out
+
+
+def ssim_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Per-image SSIM (metrics.py:32-46, scikit-image defaults: 7x7 uniform window, uint8 domain, data_range 255) of two
+    fp32 NCHW [B,C,H,W] tensors in [-1,1], as fp64 [B]."""
+    require_cuda(a, b)
+    a, b = _f32c(a), _f32c(b)
+    assert a.shape == b.shape and a.dim() == 4
+    bsz, ch, h, w = a.shape
+    lib = _lib.load()
+    nbytes = int(lib.clpk_ssim_ws_bytes(bsz, ch, h, w))
+    if nbytes < 0:
+        raise ValueError("win_size exceeds image extent. Either ensure that your images are at least 7x7; or pass "
+                         "win_size explicitly in the function call, with an odd value less than or equal to the smaller "
+                         "side of your images.")
+    ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=a.device)
+    out = torch.empty(bsz, dtype=torch.float64, device=a.device)
+    check(lib.clpk_ssim_u8(ptr(a), ptr(b), ptr(out), ptr(ws), bsz, ch, h, w, stream_ptr()), "clpk_ssim_u8")
     return out

@@ -230,6 +230,14 @@ int clpk_to_uint8_hwc(const float* x_nchw_dev, uint8_t* out_hwc_dev, int batch, 
 int clpk_psnr_sqerr_u8(const float* a_dev, const float* b_dev, int64_t* sq_err_sum_dev, int batch, int64_t per_image,
                        void* stream);
 
+/* per-image SSIM in the uint8 domain (metrics.py:32-46: skimage structural_similarity(HWC uint8, data_range=255,
+ * channel_axis=-1) with its defaults — 7x7 uniform window, K1 0.01, K2 0.03, sample covariance, float64, 3-pixel border
+ * cropped, mean over pixels then over channels).  a, b: fp32 NCHW [batch,ch,h,w] in [-1,1]; out: fp64 [batch];
+ * ws: clpk_ssim_ws_bytes(...) bytes of device scratch.  h, w < 7 is an error (skimage raises ValueError). */
+int64_t clpk_ssim_ws_bytes(int batch, int ch, int h, int w);
+int clpk_ssim_u8(const float* a_nchw_dev, const float* b_nchw_dev, double* ssim_dev, void* ws_dev, int batch, int ch, int h,
+                 int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,8 +10,11 @@ build container: tests/golden/*.npz, written by oracle/gen_golden.py (committed)
 present — a live comparison in tests/test_oracle_vs_reference.py.  Exceptions, stated per SURVEY.md §8(c):
   * zstd frames: arithmetic lives in the un-vendored PyPI wheel `zstandard>=0.22.0` (pyproject.toml:21), absent here.
     Pinned through the reference's own reader/writer running over a ctypes shim of the system libzstd 1.5.5.
-  * SSIM: lives in un-vendored scikit-image (absent) -> not restated, parity unpinned (returns NaN like the reference
-    does when skimage is missing, PKG/eval/metrics.py:34-37).
+  * SSIM: the arithmetic lives in un-vendored scikit-image (`scikit-image>=0.22.0`, pyproject.toml:23; absent here, and
+    the reference returns NaN without it, PKG/eval/metrics.py:34-37) -> PARITY UNPINNED.  `ssim` below restates
+    skimage 0.22's `structural_similarity` as the reference calls it (metrics.py:45), from its published algorithm and
+    defaults, on top of the same scipy.ndimage.uniform_filter skimage itself uses; it is anchored by closed-form
+    known answers (identical images -> 1; constant images -> (2ab+C1)/(a^2+b^2+C1)) in tests/test_oracle_golden.py.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
 """
@@ -314,6 +317,40 @@ def psnr(img1: np.ndarray, img2: np.ndarray) -> float:
     if mse == 0:
         return float("inf")
     return float(20.0 * np.log10(255.0 / np.sqrt(mse)))
+
+
+def ssim(img1: np.ndarray, img2: np.ndarray) -> float:
+    """PKG/eval/metrics.py:32-46 with scikit-image present: structural_similarity(x1, x2, data_range=255,
+    channel_axis=-1) on the HWC uint8 images.  Restatement of skimage 0.22 `skimage/metrics/_structural_similarity.py`
+    for these arguments (PARITY UNPINNED, see the module header): win_size 7, uniform filter, K1 = 0.01, K2 = 0.03,
+    use_sample_covariance=True, float64 arithmetic (uint8 input), border of (win_size - 1) // 2 cropped, mean of S per
+    channel in float64, then the mean over channels."""
+    from scipy.ndimage import uniform_filter
+
+    x1, x2 = metric_uint8(img1), metric_uint8(img2)
+    if x1.ndim == 3 and x1.shape[0] in (1, 3):                      # metrics.py:41-43
+        x1, x2 = x1.transpose(1, 2, 0), x2.transpose(1, 2, 0)
+    multichannel = x1.ndim == 3 and x1.shape[2] > 1                 # metrics.py:44
+
+    def plane(a: np.ndarray, b: np.ndarray) -> float:
+        win, k1, k2, r = 7, 0.01, 0.03, 255.0
+        if min(a.shape) < win:
+            raise ValueError("win_size exceeds image extent.")
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        npx = win ** a.ndim
+        cov_norm = npx / (npx - 1)
+        ux, uy = uniform_filter(a, size=win), uniform_filter(b, size=win)
+        uxx, uyy, uxy = uniform_filter(a * a, size=win), uniform_filter(b * b, size=win), uniform_filter(a * b, size=win)
+        vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+        c1, c2 = (k1 * r) ** 2, (k2 * r) ** 2
+        s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+        pad = (win - 1) // 2
+        return float(s[tuple(slice(pad, -pad) for _ in range(a.ndim))].mean(dtype=np.float64))
+
+    if multichannel:
+        return float(np.mean([plane(x1[..., c], x2[..., c]) for c in range(x1.shape[-1])]))
+    # single channel: skimage filters over every axis of whatever array it is given (HW, or HW1 after the transpose)
+    return plane(x1, x2)
 
 
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:

@@ -304,3 +304,28 @@ def test_to_uint8_and_psnr(ops, oracle, golden):
     sq = ops.psnr_sqerr_u8(cu(g["a"]), cu(g["b"])).cpu().numpy()
     ref = ((oracle.metric_uint8(g["a"]).astype(np.int64) - oracle.metric_uint8(g["b"]).astype(np.int64)) ** 2).reshape(3, -1).sum(1)
     assert np.array_equal(sq, ref)                                           # integer work: exact
+
+
+def test_ssim_matches_oracle(ops, oracle, golden):
+    """clpk_ssim_u8 vs the oracle's restatement of skimage.structural_similarity (float64 both sides)."""
+    from clip_neural_image_conpression_b200.eval.metrics import ssim, ssim_batch
+    g = golden("metrics")
+    got = ssim_batch(cu(g["a"]), cu(g["b"]))
+    ref = [oracle.ssim(g["a"][i], g["b"][i]) for i in range(len(got))]
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
+    rng = np.random.default_rng(11)
+    for (c, h, w) in [(3, 7, 7), (3, 9, 41), (3, 37, 53), (2, 64, 64), (3, 256, 256)]:   # ragged tiles, minimum size
+        a = rng.uniform(-1.2, 1.2, (2, c, h, w)).astype(np.float32)                        # values beyond [-1,1] clip
+        b = (a + rng.normal(0, 0.3, a.shape)).astype(np.float32)
+        got = ops.ssim_u8(cu(a), cu(b)).cpu().numpy()
+        ref = []
+        for i in range(2):
+            planes = [oracle.ssim(np.repeat(a[i][k:k + 1], 3, 0), np.repeat(b[i][k:k + 1], 3, 0)) for k in range(c)]
+            ref.append(np.mean(planes))
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9, err_msg=str((c, h, w)))
+    assert ssim(g["a"][0], g["a"][0]) == 1.0
+    assert abs(ssim(g["a"][0], g["b"][0]) - oracle.ssim(g["a"][0], g["b"][0])) < 1e-12
+    with pytest.raises(ValueError):
+        ops.ssim_u8(cu(g["a"][:, :, :5]), cu(g["b"][:, :, :5]))
+    with pytest.raises(ValueError):
+        ssim(g["a"][0][:1], g["b"][0][:1])                                  # (1,H,W): skimage raises, so do we

@@ -59,6 +59,8 @@ def test_cli_reconstruct_and_eval(tmp_path, oracle, capsys):
     rows = json.loads((tmp_path / "m.json").read_text())
     assert len(rows) == 5 and set(rows[0]) == {"image", "psnr", "ssim", "lpips", "clip_sim"}
     assert all(4.0 < r["psnr"] < 20.0 for r in rows)   # random images vs untrained decoder: finite, low
+    assert all(-1.0 <= r["ssim"] <= 1.0 for r in rows)  # on-device SSIM (eval.py:70), finite
+    assert "Average SSIM: nan" not in out
 
 
 def test_decode_codes_matches_per_image_decoding(tmp_path, oracle):

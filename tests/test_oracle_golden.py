@@ -1,6 +1,7 @@
 """The oracle (oracle/codec_oracle.py) against the golden vectors produced by the unmodified reference
 (tests/golden/*.npz, generator: oracle/gen_golden.py).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 TINY = dict(z_dim=512, base=32, ch_mult=(1, 2))
@@ -96,3 +97,32 @@ def test_metrics_match_reference(oracle, golden):
         assert oracle.psnr(g["a"][i], g["b"][i]) == g["psnr"][i]
     assert oracle.psnr(g["a"][0], g["a"][0]) == float("inf") == g["psnr"][3]
     assert np.array_equal(oracle.metric_uint8(g["a"]), g["metric_u8"])
+
+
+def test_ssim_known_answers(oracle):
+    """SSIM (metrics.py:32-46) is restated from scikit-image's published algorithm (parity unpinned: skimage is not
+    vendored); anchor it on closed-form answers and structural properties."""
+    rng = np.random.default_rng(3)
+    a = rng.uniform(-1, 1, (3, 33, 47)).astype(np.float32)
+    b = np.clip(a + rng.normal(0, 0.2, a.shape), -1, 1).astype(np.float32)
+    assert oracle.ssim(a, a) == 1.0                                           # identical images
+    assert oracle.ssim(a, b) == oracle.ssim(b, a) and 0.0 < oracle.ssim(a, b) < 1.0
+    # constant images: zero variances -> S = (2 ux uy + C1) / (ux^2 + uy^2 + C1) everywhere
+    ca, cb = np.full((3, 16, 16), -0.2, np.float32), np.full((3, 16, 16), 0.5, np.float32)
+    ua, ub = float(oracle.metric_uint8(ca)[0, 0, 0]), float(oracle.metric_uint8(cb)[0, 0, 0])
+    c1 = (0.01 * 255) ** 2
+    np.testing.assert_allclose(oracle.ssim(ca, cb), (2 * ua * ub + c1) / (ua * ua + ub * ub + c1), rtol=1e-12)
+    # brute-force 7x7 windows (no filter library) on a small plane, interior pixels only
+    x, y = oracle.metric_uint8(a[0]).astype(np.float64), oracle.metric_uint8(b[0]).astype(np.float64)
+    vals = []
+    for i in range(3, x.shape[0] - 3):
+        for j in range(3, x.shape[1] - 3):
+            wx, wy = x[i - 3:i + 4, j - 3:j + 4], y[i - 3:i + 4, j - 3:j + 4]
+            ux, uy = wx.mean(), wy.mean()
+            vx, vy = wx.var(ddof=1), wy.var(ddof=1)
+            vxy = ((wx - ux) * (wy - uy)).sum() / 48.0
+            vals.append(((2 * ux * uy + c1) * (2 * vxy + (0.03 * 255) ** 2)) /
+                        ((ux * ux + uy * uy + c1) * (vx + vy + (0.03 * 255) ** 2)))
+    np.testing.assert_allclose(oracle.ssim(a[:1].repeat(3, 0), b[:1].repeat(3, 0)), np.mean(vals), rtol=1e-10)
+    with pytest.raises(ValueError):
+        oracle.ssim(a[:, :5], b[:, :5])                                       # smaller than the 7x7 window
