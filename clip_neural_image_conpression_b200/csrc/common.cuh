@@ -46,8 +46,35 @@ void count_launch(int n = 1);
 
 int num_sms();
 
+// Programmatic dependent launch (PDL), OFF by default (env CLPK_PDL=1 turns it on): every kernel of the DDIM step graph
+// can be launched with the programmatic stream serialization attribute and starts with pdl_wait()
+// (= cudaGridDependencySynchronize: returns once the preceding kernel has completed and its writes are visible), so the
+// next kernel's CTAs are scheduled SM by SM as this kernel's CTAs retire and run their prologue under its tail.
+// Measured on B200 inside the captured step graph (103 kernel nodes): neutral (60.1 vs 60.2 images/s) — the graph's
+// kernel-to-kernel latency is already hidden — and an early griddepcontrol.launch_dependents made it 3 % slower, so the
+// attribute stays off and the device-side wait is a no-op.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------ device side
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue_done() { pdl_wait(); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

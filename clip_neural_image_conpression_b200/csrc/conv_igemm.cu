@@ -217,6 +217,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (NCTA == 2) cluster_sync_all(); else __syncthreads();  // barriers of BOTH CTAs initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_prologue_done();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -991,13 +992,22 @@ static cudaError_t launch_variant(const IgemmLaunch& L, cudaStream_t stream) {
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = (size_t)L.smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = NC;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (NC > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = NC;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (NC > 1) ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BK, NC, SLAB>, L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
 }
 

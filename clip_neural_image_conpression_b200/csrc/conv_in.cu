@@ -91,6 +91,7 @@ int launch_conv_in(const float* x, const float* w, const float* b, float* y, int
 // Reads are coalesced along W within each (channel, row).
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ cols, int batch, int cin, int h, int wd, int f16) {
+  pdl_prologue_done();
   const long long npix = (long long)batch * h * wd;
   const long long plane = (long long)h * wd;
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
@@ -127,8 +128,8 @@ int launch_stem_im2col(const float* x, void* cols, int batch, int cin, int h, in
   CLPK_REQUIRE(cin >= 1 && cin * 9 <= 27, "stem im2col supports cin <= 3 (got %d)", cin);
   const long long npix = (long long)batch * h * wd;
   const int blocks = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 16);
-  stem_im2col_kernel<<<blocks, 256, 0, stream>>>(x, reinterpret_cast<uint16_t*>(cols), batch, cin, h, wd,
-                                                 op_dtype == CLPK_OP_F16);
+  CLPK_CHECK_CUDA(launch_kernel_pdl(stem_im2col_kernel, dim3(blocks), dim3(256), 0, stream, x, reinterpret_cast<uint16_t*>(cols),
+                                    batch, cin, h, wd, (int)(op_dtype == CLPK_OP_F16)));
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }

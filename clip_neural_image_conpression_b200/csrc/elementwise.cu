@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <stdarg.h>
 #include <string.h>
@@ -20,6 +22,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("CLPK_PDL"); return e && atoi(e) != 0; }();
+  return on;
+}
 
 int num_sms() {
   static int sms = 0;
@@ -126,6 +133,7 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
                                  const float* __restrict__ coef_tab, const DdimRun* __restrict__ run,
                                  float* __restrict__ x_out, long long n) {
+  pdl_prologue_done();
   const int step = run->step;
   const float* noise = run->noise;
   const long long noise_step_stride = run->noise_step_stride;
@@ -181,14 +189,18 @@ int launch_ddim_step(const float* x, const float* eps, const float* coef_tab_dev
                      long long n, cudaStream_t stream) {
   const long long work = (n + 3) / 4;
   const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)num_sms() * 8);
-  ddim_step_kernel<<<std::max(blocks, 1), 256, 0, stream>>>(x, eps, coef_tab_dev, run_dev, x_out, n);
+  CLPK_CHECK_CUDA(launch_kernel_pdl(ddim_step_kernel, dim3(std::max(blocks, 1)), dim3(256), 0, stream, x, eps, coef_tab_dev, run_dev,
+                                    x_out, n));
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }
 
-__global__ void ddim_advance_kernel(DdimRun* run) { run->step += 1; }
+__global__ void ddim_advance_kernel(DdimRun* run) {
+  pdl_prologue_done();
+  run->step += 1;
+}
 int launch_ddim_advance(DdimRun* run_dev, cudaStream_t stream) {
-  ddim_advance_kernel<<<1, 1, 0, stream>>>(run_dev);
+  CLPK_CHECK_CUDA(launch_kernel_pdl(ddim_advance_kernel, dim3(1), dim3(1), 0, stream, run_dev));
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }
@@ -196,6 +208,7 @@ int launch_ddim_advance(DdimRun* run_dev, cudaStream_t stream) {
 // h[b,:] = zemb[b,:] + ht_tab[run->step,:]   (unet.py:86 with the step-invariant / batch-invariant halves hoisted)
 __global__ void cond_combine_kernel(const float* __restrict__ zemb, const float* __restrict__ ht_tab,
                                     const DdimRun* __restrict__ run, float* __restrict__ h, int batch, int dim) {
+  pdl_prologue_done();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * dim) return;
   const int d = i % dim;
@@ -203,7 +216,8 @@ __global__ void cond_combine_kernel(const float* __restrict__ zemb, const float*
 }
 int launch_cond_combine(const float* zemb, const float* ht_tab, const DdimRun* run, float* h, int batch, int dim,
                         cudaStream_t stream) {
-  cond_combine_kernel<<<(batch * dim + 255) / 256, 256, 0, stream>>>(zemb, ht_tab, run, h, batch, dim);
+  CLPK_CHECK_CUDA(launch_kernel_pdl(cond_combine_kernel, dim3((batch * dim + 255) / 256), dim3(256), 0, stream, zemb, ht_tab, run, h,
+                                    batch, dim));
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }
@@ -248,6 +262,7 @@ int launch_timestep_embedding(const int64_t* t, float* out, int batch, int dim, 
 __global__ void linear_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                               const float* __restrict__ add, int add_rows, float* __restrict__ y, int m, int n, int k,
                               int act) {
+  pdl_prologue_done();
   const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (col >= n) return;
@@ -279,7 +294,8 @@ __global__ void linear_kernel(const float* __restrict__ x, const float* __restri
 int launch_linear(const float* x, const float* w, const float* b, const float* add, int add_rows, float* y, int m, int n,
                   int k, int act, cudaStream_t stream) {
   dim3 grid((n + 7) / 8, std::min((m + 7) / 8, 64));
-  linear_kernel<<<grid, 256, 0, stream>>>(x, w, b, add, add_rows > 0 ? add_rows : m, y, m, n, k, act);
+  CLPK_CHECK_CUDA(launch_kernel_pdl(linear_kernel, grid, dim3(256), 0, stream, x, w, b, add, add_rows > 0 ? add_rows : m, y, m, n, k,
+                                    act));
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }

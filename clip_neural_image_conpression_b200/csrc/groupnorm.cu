@@ -38,6 +38,7 @@ gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float
                 int* __restrict__ counter, int hw, int c, int groups, int chunks, int pix_per_chunk, float eps) {
   __shared__ float2 red[kGnThreads * J];
   __shared__ int is_last;
+  pdl_prologue_done();
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int qc = c >> 2;           // float4 quads per pixel
   const int cpg = c / groups;
@@ -212,6 +213,7 @@ gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, c
                 const float2* __restrict__ stats, const float2* __restrict__ partial, int slots, double n_per_group,
                 float eps, uint16_t* __restrict__ y, int hw, int c, int groups, int silu, int op_f16) {
   __shared__ float2 st_s[32];
+  pdl_prologue_done();
   const bool f16 = op_f16 != 0;
   const int b = blockIdx.y;
   if (partial) {
@@ -317,11 +319,13 @@ int launch_gn_apply_ex(const void* x, int x_is_16, const float* gamma, const flo
   const bool hoist = ((long long)agrid.x * kGnThreads) % (s.c / 8) == 0;  // every thread stays on one channel octet
   const bool f16 = op_dtype == CLPK_OP_F16;
 #define CLPK_GN_APPLY(IN16, HOIST)                                                                                    \
-  gn_apply_kernel<IN16, HOIST><<<agrid, kGnThreads, 0, stream>>>(x, gamma, beta, stats, partial, slots, n_per_group, eps, \
-                                                                 y, s.hw, s.c, s.groups, silu, f16)
+  launch_err = launch_kernel_pdl(gn_apply_kernel<IN16, HOIST>, agrid, dim3(kGnThreads), 0, stream, x, gamma, beta, stats,  \
+                                 partial, slots, n_per_group, eps, y, s.hw, s.c, s.groups, silu, (int)f16)
+  cudaError_t launch_err = cudaSuccess;
   if (x_is_16) { if (hoist) CLPK_GN_APPLY(true, true); else CLPK_GN_APPLY(true, false); }
   else { if (hoist) CLPK_GN_APPLY(false, true); else CLPK_GN_APPLY(false, false); }
 #undef CLPK_GN_APPLY
+  CLPK_CHECK_CUDA(launch_err);
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }
@@ -355,19 +359,19 @@ int launch_gn_stats(const float* x, void* ws, const GnShape& s, float eps, const
   dim3 grid(s.chunks, s.batch);
   if (qc <= kGnThreads) {
     const int threads = ((kGnThreads / qc) * qc + 31) / 32 * 32;
-    gn_stats_kernel<1><<<grid, threads, 0, stream>>>(x, partial, stats, counter, s.hw, s.c, s.groups, s.chunks,
-                                                     pix_per_chunk, eps);
+    CLPK_CHECK_CUDA(launch_kernel_pdl(gn_stats_kernel<1>, grid, dim3(threads), 0, stream, x, partial, stats, counter, s.hw,
+                                      s.c, s.groups, s.chunks, pix_per_chunk, eps));
   } else {
     const int j = (qc + kGnThreads - 1) / kGnThreads;
     if (j == 2)
-      gn_stats_kernel<2><<<grid, kGnThreads, 0, stream>>>(x, partial, stats, counter, s.hw, s.c, s.groups, s.chunks,
-                                                          pix_per_chunk, eps);
+      CLPK_CHECK_CUDA(launch_kernel_pdl(gn_stats_kernel<2>, grid, dim3(kGnThreads), 0, stream, x, partial, stats, counter, s.hw,
+                                      s.c, s.groups, s.chunks, pix_per_chunk, eps));
     else if (j == 3)
-      gn_stats_kernel<3><<<grid, kGnThreads, 0, stream>>>(x, partial, stats, counter, s.hw, s.c, s.groups, s.chunks,
-                                                          pix_per_chunk, eps);
+      CLPK_CHECK_CUDA(launch_kernel_pdl(gn_stats_kernel<3>, grid, dim3(kGnThreads), 0, stream, x, partial, stats, counter, s.hw,
+                                      s.c, s.groups, s.chunks, pix_per_chunk, eps));
     else
-      gn_stats_kernel<4><<<grid, kGnThreads, 0, stream>>>(x, partial, stats, counter, s.hw, s.c, s.groups, s.chunks,
-                                                          pix_per_chunk, eps);
+      CLPK_CHECK_CUDA(launch_kernel_pdl(gn_stats_kernel<4>, grid, dim3(kGnThreads), 0, stream, x, partial, stats, counter, s.hw,
+                                      s.c, s.groups, s.chunks, pix_per_chunk, eps));
   }
   CLPK_CHECK_LAUNCH();
   *stats_out = stats;
