@@ -197,13 +197,13 @@ def run_b200_arm(args):
     x_T_host = torch.randn(B, 3, S, S, generator=g).pin_memory()
     codes_host = codes_dev.cpu().pin_memory()
     out_host = torch.empty((B, S, S, 3), dtype=torch.uint8).pin_memory()
-    metric_host = torch.empty(2, dtype=torch.float64).pin_memory()
+    metric_host = torch.empty(3, dtype=torch.float64).pin_memory()
     x_T_dev = x_T_host.to(dev)
     sampler = DDIMSampler(NoiseScheduler(1000, "cosine", dev), eta=args.eta)
     sampler.use_graph = not args.no_graph
     stream = torch.cuda.current_stream()
 
-    # eval-style tail of every step (north-star: NCCL only AFTER the loop): PSNR vs a synthetic "original" on the device,
+    # eval-style tail of every step (north-star: NCCL only AFTER the loop): PSNR + SSIM vs a synthetic "original" on the device,
     # then one gather of the uint8 reconstructions and one fp64 all-reduce of the metric sums
     target = torch.tanh(torch.randn(B, 3, S, S, generator=g)).to(dev)
     gathered = torch.empty((world * B, S, S, 3), dtype=torch.uint8, device=dev) if world > 1 else None
@@ -211,7 +211,8 @@ def run_b200_arm(args):
     def finish(x):
         u8 = ops.to_uint8_hwc(x)
         sq = ops.psnr_sqerr_u8(x, target)
-        sums = torch.stack([sq.sum().double(), torch.tensor(float(B), dtype=torch.float64, device=dev)])
+        ss = ops.ssim_u8(x, target)
+        sums = torch.stack([sq.sum().double(), ss.sum(), torch.tensor(float(B), dtype=torch.float64, device=dev)])
         if world > 1:
             torch.distributed.all_gather_into_tensor(gathered, u8)
             torch.distributed.all_reduce(sums)
@@ -276,7 +277,7 @@ def run_b200_arm(args):
     gn_gbs = gn_bytes / (gn_ms * 1e-3) / 1e9 if gn_ms > 0 else 0.0
     n_conv = cnt6[0] // prof_iters
     roofline = {
-        "bound": "tensor", "kernel": "conv_igemm_kernel<64> (ResBlock 3x3 convs)",
+        "bound": "tensor", "kernel": "conv_igemm_kernel (the 28 ResBlock 3x3 convs: row-slab CTA-pair variant at 256/128 px, CTA-pair k-block variant at 64/32 px)",
         "achieved": conv_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": conv_tflops / peaks["tf_sustained"], "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
         "traffic": None,
@@ -307,7 +308,7 @@ def run_b200_arm(args):
                                    f"batch {B} per GPU, {'CUDA-graph' if sampler.use_graph else 'eager'} step loop",
                        "batch_per_gpu": B, "global_batch": B * world, "ddim_steps": T, "z_dim": ARCH["z_dim"],
                        "weights": "random init (seed 0), out.* x0.1",
-                       "precision": f"{args.operand} tensor-core operands, fp32 accumulation (TMEM), fp32 residual stream and GroupNorm statistics", "sharding": f"dp{world} by image, no collective in the DDIM loop; per step one all_gather of the uint8 reconstructions + one fp64 all_reduce of PSNR sums (NCCL) when n_gpus > 1",
+                       "precision": f"{args.operand} tensor-core operands, fp32 accumulation (TMEM), fp32 residual stream and GroupNorm statistics", "sharding": f"dp{world} by image, no collective in the DDIM loop; per step one all_gather of the uint8 reconstructions + one fp64 all_reduce of PSNR + SSIM sums (NCCL) when n_gpus > 1",
                        "l2": "per-step working set (>= 270 MB per activation tensor at batch 8) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(codes_host.numel() + x_T_host.numel() * 4),
