@@ -41,7 +41,7 @@ def main():
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"{k[:58]:58s} {n:8d} {t:10.1f} {t / tot * 100:6.1f}% {t / n:9.1f}")
     out.append(f"{'TOTAL':58s} {len(seq):8d} {tot:10.1f}")
-    idx = [i for i, s in enumerate(seq) if "conv_in" in s[0]]
+    idx = [i for i, s in enumerate(seq) if "stem_im2col" in s[0]]
     if len(idx) >= 2:
         out += ["", "# one UNet forward + DDIM update in launch order (default config, batch 8):"]
         for n, g, b, v in seq[idx[0]:idx[1]]:
