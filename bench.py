@@ -167,6 +167,17 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def conv_traffic_from_profile():
+    """Bytes of DRAM traffic per ResBlock-conv launch from the committed ncu summary (None if it is missing)."""
+    import re
+    path = ROOT / "profiles" / "conv_traffic_r1.txt"
+    try:
+        m = re.search(r"= ([0-9.]+) MB per launch", path.read_text())
+        return float(m.group(1)) * 1e6 if m else None
+    except OSError:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200_arm(args):
     from clip_neural_image_conpression_b200 import _lib, ops, parallel
@@ -280,7 +291,8 @@ def run_b200_arm(args):
         "bound": "tensor", "kernel": "conv_igemm_kernel (the 28 ResBlock 3x3 convs: row-slab CTA-pair variant at 256/128 px, CTA-pair k-block variant at 64/32 px)",
         "achieved": conv_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": conv_tflops / peaks["tf_sustained"], "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
-        "traffic": None,
+        "traffic": conv_traffic_from_profile(),
+        "traffic_note": "mean dram__bytes_read.sum + dram__bytes_write.sum per launch over the same 28 launches of one DDIM step, from the committed ncu capture profiles/conv_traffic_r1.txt (not measured in this run); reads equal the algorithmic operand + residual bytes",
         "flops_per_launch": fa.value / max(n_conv, 1), "ms_per_launch": per_launch_ms[cls[0]],
         "launches_per_ddim_step": n_conv,
         "how": f"CUDA events around each of the {n_conv} launches of {prof_iters} eager DDIM steps right after the timed region",
