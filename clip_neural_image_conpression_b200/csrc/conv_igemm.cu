@@ -77,8 +77,20 @@ constexpr int kWarpSlotBytes = 32 * 128;  // per-warp staging slot: 32 tile rows
 // the hottest loops
 #ifdef CLPK_IGEMM_DEBUG
 #define CLPK_DBG(bits) (p.dbg & (bits))
+// phase trace of ONE epilogue warp (CTA 0, group 0, quarter 0) and of the MMA issuer: clock64 stamps, read back with
+// clpk_debug_trace (debug builds only)
+__device__ long long g_trace[8192];
+__device__ int g_trace_n;
+#define CLPK_TRACE(cond, tag)                                                        \
+  do {                                                                               \
+    if ((p.dbg & 64) && (cond)) {                                                    \
+      const int _i = atomicAdd(&g_trace_n, 1);                                       \
+      if (_i < 4096) { g_trace[2 * _i] = (tag); g_trace[2 * _i + 1] = clock64(); }   \
+    }                                                                                \
+  } while (0)
 #else
 #define CLPK_DBG(bits) 0
+#define CLPK_TRACE(cond, tag) do { } while (0)
 #endif
 static inline int epi_vector_bytes(int block_n) { return 2 * 4 * block_n + kRedBytes; }
 
@@ -139,10 +151,20 @@ __device__ __forceinline__ int scatter_owner_index(int lane) {
   return idx;
 }
 
+// phase 1 (while the chunk's values are live): per-thread row sums into sums[0 .. 2P)
 template <int P>
-__device__ __forceinline__ void gn_chunk_partials(const float (&v)[32], bool valid, int lane, float2* redw) {
+__device__ __forceinline__ void gn_row_sums(const float (&v)[32], bool valid, float (&sums)[16]) {
   float vals[2 * P];
   row_sums<P>(v, valid, vals);
+#pragma unroll
+  for (int i = 0; i < 2 * P; ++i) sums[i] = vals[i];
+}
+// phase 2 (after the chunk's store has been issued): fold over the warp's 32 rows and park the warp's partials
+template <int P>
+__device__ __forceinline__ void gn_chunk_reduce(const float (&sums)[16], int lane, float2* redw) {
+  float vals[2 * P];
+#pragma unroll
+  for (int i = 0; i < 2 * P; ++i) vals[i] = sums[i];
   const float r = warp_reduce_scatter<2 * P>(vals, lane);
   // Which original value does this lane hold?  At the first step the kept half is [h, 2h) for `upper` lanes, i.e. the
   // top bit of the original index = lane bit 4; the next step decides the next bit, and so on.
@@ -313,8 +335,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        CLPK_TRACE(blockIdx.x == 0 && lane == 0, 200);
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);  // epilogue(s) have drained this accumulator
         tc_fence_after();
+        CLPK_TRACE(blockIdx.x == 0 && lane == 0, 201);
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&bars->full[stage], phase);  // TMA bytes (of both CTAs) have landed
@@ -403,10 +427,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int npairs = cpg >= 32 ? 1 : (cpg > 0 ? 32 / cpg : 0);
     int ld_tile = cluster_id, ld_c = 32 * eg;
     uint32_t ld_slot = 0;
+    int lc_tile = -1;
+    TileCoord lc{};
     auto issue_res_load = [&]() {  // lane 0 only
       while (ld_tile < p.num_tiles && ld_c >= p.block_n) { ld_c = 32 * eg; ld_tile += num_clusters; }
       if (ld_tile >= p.num_tiles) return;
-      const TileCoord lc = decode_tile(p, ld_tile, (int)rank);
+      if (ld_tile != lc_tile) { lc = decode_tile(p, ld_tile, (int)rank); lc_tile = ld_tile; }  // (integer divisions)
       mbar_arrive_expect_tx(&res_full[ld_slot], (uint32_t)kWarpSlotBytes);
       tma_load_5d(wslots + (size_t)ld_slot * kWarpSlotBytes, &maps_res.m[lc.phase], &res_full[ld_slot], lc.n0 + ld_c,
                   lc.w0 + sub_w, 0, lc.h0 + sub_h, lc.b);
@@ -445,16 +471,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           cached_key = key;
         }
         float2 (*red_t)[4][8] = vec->red[it & 1][eg];  // [chunk of this group][warp][pair]
+        const bool tr = blockIdx.x == 0 && ew == 0 && lane == 0;
+        CLPK_TRACE(tr, 100);
         mbar_wait(&bars->tmem_full[as], aphase);
         tc_fence_after();
+        CLPK_TRACE(tr, 101);
         int ci = 0;
         for (int c = 32 * eg; c < p.block_n; c += cstep, ++ci) {
           uint8_t* sbuf = wslots + (size_t)slot * kWarpSlotBytes;
           uint32_t r[32];
+          float gsums[16];
           __syncwarp();  // also orders lane 0's slot bookkeeping of the previous chunk before this chunk's smem writes
           tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
           tmem_ld16(taddr + (uint32_t)c + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
           tmem_ld_wait();
+          CLPK_TRACE(tr, 102);
           if (!(CLPK_DBG(1))) {
             float v[32];
 #pragma unroll
@@ -470,7 +501,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             // 128B TMA swizzle (slots are 1024-byte aligned)
             uint8_t* srow = sbuf + lane * 128;
             if (res_tma) {
+              CLPK_TRACE(tr, 103);
               mbar_wait(&res_full[slot], sphase);  // residual sub-box has landed (implies the slot was free)
+              CLPK_TRACE(tr, 104);
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 q = *reinterpret_cast<const float4*>(srow + ((j4 ^ (lane & 7)) << 4));
@@ -478,13 +511,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               }
             }
             if (ep.gn_partial && !(CLPK_DBG(32))) {
-              // per-thread (sum, sumsq) of this row's 32 values split by consumer-GroupNorm group, folded over the warp's
-              // 32 rows; the owning lanes park the warp's partials for the fixed-order 4-warp fold at the end of the tile
-              float2* redw = red_t[ci][quarter];
-              if (cpg >= 32) gn_chunk_partials<1>(v, valid, lane, redw);
-              else if (cpg == 16) gn_chunk_partials<2>(v, valid, lane, redw);
-              else if (cpg == 8) gn_chunk_partials<4>(v, valid, lane, redw);
-              else gn_chunk_partials<8>(v, valid, lane, redw);
+              // per-thread (sum, sumsq) of this row's 32 values split by consumer-GroupNorm group; the cross-lane fold
+              // happens after the chunk's store has been issued (it is off the store's critical path)
+              if (cpg >= 32) gn_row_sums<1>(v, valid, gsums);
+              else if (cpg == 16) gn_row_sums<2>(v, valid, gsums);
+              else if (cpg == 8) gn_row_sums<4>(v, valid, gsums);
+              else gn_row_sums<8>(v, valid, gsums);
             }
             if (st_f32) {
 #pragma unroll
@@ -517,9 +549,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               }
             }
           }
+          CLPK_TRACE(tr, 105);
           if (st_tma) {
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();
+            CLPK_TRACE(tr, 106);
             if (lane == 0 && !(CLPK_DBG(1))) {
               tma_store_5d(&maps_out.m[tc.phase], sbuf, tc.n0 + c, tc.w0 + sub_w, 0, tc.h0 + sub_h, tc.b);
               bulk_commit_group();
@@ -537,6 +571,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             if (++slot == (uint32_t)S) { slot = 0; sphase ^= 1u; }
           }
+          CLPK_TRACE(tr, 107);
+          if (ep.gn_partial && !(CLPK_DBG(33))) {
+            // fold the row sums over the warp's 32 rows; the owning lanes park the warp's partials for the fixed-order
+            // 4-warp fold at the end of the tile
+            __syncwarp();
+            float2* redw = red_t[ci][quarter];
+            if (cpg >= 32) gn_chunk_reduce<1>(gsums, lane, redw);
+            else if (cpg == 16) gn_chunk_reduce<2>(gsums, lane, redw);
+            else if (cpg == 8) gn_chunk_reduce<4>(gsums, lane, redw);
+            else gn_chunk_reduce<8>(gsums, lane, redw);
+          }
+          CLPK_TRACE(tr, 108);
         }
         // accumulator drained: hand it back to the MMA issuer before the statistics fold
         tc_fence_before();
@@ -565,6 +611,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             reinterpret_cast<float2*>(ep.gn_partial)[((long long)tc.b * p.gn_slots + slotg) * p.gn_groups + g] = acc;
           }
         }
+        CLPK_TRACE(tr, 109);
         continue;
       } else {
         // ------------------------------------------------ direct path (narrow N: the 3-channel `out` conv, NCHW store)
@@ -1080,3 +1127,17 @@ extern "C" int clpk_conv_direct(const void* x, const void* w, int kind, int batc
   if (rc) return rc;
   return direct_launch(L, x, w, (cudaStream_t)stream);
 }
+
+#ifdef CLPK_IGEMM_DEBUG
+// debug builds only: copies the phase trace (pairs of tag, clock64) to the host and resets it; returns the pair count
+extern "C" int clpk_debug_trace(long long* out_host, int max_pairs) {
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(int));
+  n = std::min(std::min(n, 4096), max_pairs);
+  cudaMemcpyFromSymbol(out_host, g_trace, sizeof(long long) * 2 * n);
+  const int zero = 0;
+  cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(int));
+  return n;
+}
+#endif
