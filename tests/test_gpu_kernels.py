@@ -140,8 +140,12 @@ def test_conv_in(ops):
 def test_conv_16bit_only_output_with_fused_statistics(ops):
     """conv1 of a ResBlock as the plan runs it: FiLM epilogue, output kept ONLY in the 16-bit operand format, GroupNorm
     statistics taken from the fp32 accumulators."""
+    _conv1_like(ops, 2, 32, 32, 128)
+    _conv1_like(ops, 1, 3, 256, 128)     # row-slab kernel: staged 16-bit TMA store from per-warp 64-byte-row slots
+
+
+def _conv1_like(ops, b, h, w, c):
     g = torch.Generator().manual_seed(3)
-    b, h, w, c = 2, 32, 32, 128
     xb = torch.randn(b, h, w, c, generator=g).to(torch.float16).cuda()
     wt = (torch.randn(c, c, 3, 3, generator=g) * 0.03).cuda()
     bias = torch.randn(c, generator=g).cuda()
@@ -183,7 +187,12 @@ CONV_CASES = [
     (0, 2, 32, 32, 128, 128, False, True),     # conv2 + residual epilogue
     (0, 1, 16, 16, 32, 32, False, False),      # BLOCK_K = 32 (64-byte swizzle)
     (0, 1, 8, 8, 512, 512, False, True),       # two N tiles, 72 k-blocks, half-filled M tile
-    (0, 1, 4, 256, 128, 128, False, False),    # W > 128
+    (0, 1, 4, 256, 128, 128, False, False),    # W > 128: row-slab mainloop (shifted smem descriptors), CTA pair
+    (0, 3, 5, 192, 64, 64, True, True),        # slab: partial second row tile, odd tile count (masked pair half), 1 k-block
+    (0, 1, 3, 128, 192, 128, False, True),     # slab: three channel blocks, residual look-ahead across tiles
+    (0, 2, 6, 320, 128, 3, False, False),      # slab, single CTA, narrow N (`out` conv at full width), ragged W
+    (0, 1, 2, 256, 64, 192, True, False),      # slab declined (N = 192 > 128): generic CTA-pair path on a wide row
+    (0, 1, 9, 40, 64, 64, False, True),        # width that is neither a multiple nor a divisor of 32: 32-pixel tiles
     (0, 1, 24, 24, 64, 64, False, False),      # ragged boxes
     (0, 2, 16, 16, 128, 3, False, False),      # `out` conv: N padded to 16, NCHW output
     (0, 4, 64, 64, 256, 256, True, False),     # several tiles per CTA: smem ring wrap + TMEM double buffering
@@ -248,6 +257,8 @@ def test_conv_igemm(ops, kind, b, h, w, cin, cout, film, resid, dtype):
     (1, 2, 32, 32, 128, 256, False),     # stride-2 producer
     (2, 2, 16, 16, 256, 128, True),      # transposed-conv producer (4 phases)
     (0, 1, 24, 24, 64, 64, False),       # ragged tiles: masked rows must not contribute
+    (0, 3, 5, 256, 128, 128, True),      # row-slab mainloop on CTA pairs, odd tile count, per-warp residual sub-boxes
+    (0, 1, 7, 40, 64, 64, False),        # 32-pixel tiles on a 40-pixel row: masked columns must not contribute
 ])
 def test_conv_fused_groupnorm_statistics(ops, kind, b, h, w, cin, cout, resid):
     """The conv epilogue's fused (mean, rstd) equal a GroupNorm statistics pass over its own fp32 output."""
