@@ -295,7 +295,7 @@ def run_b200_arm(args):
         "traffic_note": "mean dram__bytes_read.sum + dram__bytes_write.sum per launch over the same 28 launches of one DDIM step, from the committed ncu capture profiles/conv_traffic_r1.txt (not measured in this run); reads equal the algorithmic operand + residual bytes",
         "flops_per_launch": fa.value / max(n_conv, 1), "ms_per_launch": per_launch_ms[cls[0]],
         "launches_per_ddim_step": n_conv,
-        "how": f"CUDA events around each of the {n_conv} launches of {prof_iters} eager DDIM steps right after the timed region",
+        "how": f"CUDA events around each of the {n_conv} launches of {prof_iters} eager DDIM steps right after the timed region, enqueued behind a stream-holding delay kernel (no host launch latency inside a pair) and with the cost of an empty event pair, calibrated in the same stream, subtracted; the per-class sum (unet_fwd_ms) reproduces the graph-replayed step time",
     }
     roofline_hbm = {
         "bound": "hbm", "kernel": "gn_apply_kernel (GroupNorm+SiLU, statistics fused into the producing conv)", "achieved": gn_gbs, "peak": peaks["hbm"],

@@ -205,6 +205,25 @@ int launch_ddim_advance(DdimRun* run_dev, cudaStream_t stream) {
   return CLPK_OK;
 }
 
+// Holds the stream for `ns` nanoseconds (one thread).  Used by the profiling pass: while it runs, the host enqueues a whole
+// DDIM step (launches + event records), so the bracketed kernels then execute back to back and the event timestamps do
+// not contain host launch latency.
+__global__ void delay_kernel(long long ns) {
+  long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 >= ns) break;
+    __nanosleep(1000);
+  }
+}
+int launch_delay(long long ns, cudaStream_t stream) {
+  delay_kernel<<<1, 1, 0, stream>>>(ns);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
 // h[b,:] = zemb[b,:] + ht_tab[run->step,:]   (unet.py:86 with the step-invariant / batch-invariant halves hoisted)
 __global__ void cond_combine_kernel(const float* __restrict__ zemb, const float* __restrict__ ht_tab,
                                     const DdimRun* __restrict__ run, float* __restrict__ h, int batch, int dim) {

@@ -22,6 +22,7 @@ int launch_ddim_advance(DdimRun* run_dev, cudaStream_t stream);
 int launch_cond_combine(const float* zemb, const float* ht_tab, const DdimRun* run, float* h, int batch, int dim,
                         cudaStream_t stream);
 int launch_add_const(float* p, float v, int n, cudaStream_t stream);
+int launch_delay(long long ns, cudaStream_t stream);
 int launch_timestep_embedding(const int64_t* t, float* out, int batch, int dim, float max_period, cudaStream_t stream);
 int launch_linear(const float* x, const float* w, const float* b, const float* add, int add_rows, float* y, int m, int n,
                   int k, int act, cudaStream_t stream);

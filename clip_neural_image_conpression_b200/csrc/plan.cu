@@ -688,18 +688,31 @@ extern "C" int clpk_plan_profile_steps(clpk_plan* P, int iters, float* ms_out6, 
     run.seed = 0;
     run.noise_step_stride = 0;
     CLPK_CHECK_CUDA(cudaMemcpyAsync(P->run_dev, &run, sizeof(run), cudaMemcpyHostToDevice, s));
+    // hold the stream while the host enqueues the step, so that no event pair contains host launch latency
+    CLPK_TRY(launch_delay(3000000, s));
     P->prof_on = true;
     P->prof_used = 0;
     P->prof_cat.clear();
     int rc = ddim_step_body(P, s);
+    // calibration: 16 EMPTY event pairs in the same stream give the cost of the bracketing itself (event processing
+    // between two timestamps), which is subtracted from every measured pair
+    constexpr int kCal = 16;
+    for (int k = 0; k < kCal; ++k) { P->prof_mark(6, s); P->prof_mark(-1, s); }
     P->prof_on = false;
     if (rc != CLPK_OK) return rc;
     CLPK_CHECK_CUDA(cudaStreamSynchronize(s));
+    float overhead = 0.f;
+    for (size_t i = 0; i + 1 < P->prof_used; i += 2) {
+      if (P->prof_cat[i] != 6) continue;
+      float ms = 0.f;
+      CLPK_CHECK_CUDA(cudaEventElapsedTime(&ms, P->prof_ev[i], P->prof_ev[i + 1]));
+      overhead += ms / kCal;
+    }
     for (size_t i = 0; i + 1 < P->prof_used; i += 2) {
       float ms = 0.f;
       CLPK_CHECK_CUDA(cudaEventElapsedTime(&ms, P->prof_ev[i], P->prof_ev[i + 1]));
       const int cat = P->prof_cat[i];
-      if (cat >= 0 && cat < 6) { ms_out6[cat] += ms; count_out6[cat] += 1; }
+      if (cat >= 0 && cat < 6) { ms_out6[cat] += std::max(ms - overhead, 0.f); count_out6[cat] += 1; }
     }
   }
   return CLPK_OK;
