@@ -831,7 +831,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   // Tile configuration (measured on B200, tools/bench_conv.py): N >= 128 tiles run as CTA pairs (cta_group::2, M = 256,
   // the B tile split over the pair -> a third less operand fill per MMA) with 64-wide k-blocks; narrower tiles and the
   // pointwise stem GEMM run single-CTA (128-wide k-blocks when Cin allows: 8 MMAs per barrier handshake).
-  p.ncta = (p.block_n >= 256 || (p.block_n == 128 && kind != CLPK_CONV_1X1)) ? 2 : 1;
+  p.ncta = (p.block_n >= 256 || (p.block_n >= 128 && kind != CLPK_CONV_1X1)) ? 2 : 1;
   { const char* e = getenv("CLPK_IGEMM_NCTA"); if (e && (atoi(e) == 1 || atoi(e) == 2)) p.ncta = atoi(e); }
   if (p.block_n % 32 != 0) p.ncta = 1;  // a CTA pair splits N in two halves that must stay multiples of 16
   p.block_k = (cin % 128 == 0 && p.ncta == 1) ? 128 : (cin % 64 == 0) ? 64 : 32;
