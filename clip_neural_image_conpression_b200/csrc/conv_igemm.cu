@@ -12,9 +12,15 @@
 //        3x3 s2         : [2C, W/2, 2, H/2, B]   (x = wpar*C + c, p = hpar)  -> stride-2 taps become unit-stride boxes
 //   * ConvTranspose2d(4,2,1) = 4 output phases, each a 2x2-tap stride-1 conv of the input (K = 4*Cin) whose result is
 //     scattered to (2h+ph, 2w+pw).
-//   * Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer (+TMEM
-//     alloc), warps 2..5 = epilogue (TMEM -> registers -> bias/FiLM/residual -> global).  smem ring of `stages`
-//     k-blocks; TMEM accumulator double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * Row-slab mainloop (kSlab; 3x3 s1 convs on rows of >= 128 pixels): a stage = one (wbox+2)-pixel slab of input row
+//     h+r-1 (64 channels) + the weight blocks of taps (r, 0..2); the three taps read the slab through smem descriptors
+//     shifted by 0 / 128 / 256 bytes, so each A byte is fetched 3x instead of 9x.
+//   * Warp roles (320 threads, 1 CTA/SM or one CTA pair per two SMs, persistent over tiles): warp0 = TMA producer,
+//     warp1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue (two groups of four; every warp moves its own 32-row
+//     sub-box: TMEM -> registers -> bias/FiLM/residual/statistics -> swizzled smem -> TMA store).  smem ring of `stages`
+//     stages; TMEM accumulator double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * Env switches read at setup (experiments; defaults are the measured best): CLPK_IGEMM_SLAB=0, CLPK_IGEMM_NCTA,
+//     CLPK_IGEMM_BK, CLPK_IGEMM_SLOTS, CLPK_IGEMM_PREFETCH; debug builds (-DCLPK_IGEMM_DEBUG) add CLPK_IGEMM_DBG.
 #include "conv_igemm.cuh"
 
 #include <algorithm>
