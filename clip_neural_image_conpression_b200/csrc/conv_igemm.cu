@@ -937,7 +937,8 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     CLPK_REQUIRE(p.ep.out_f32 != nullptr || !p.ep.resid, "a residual input needs the fp32 output");
     // as many staging slots per epilogue group (<= 3) as the smem ring can spare without losing depth; a residual
     // epilogue keeps (slots - 1) chunk loads in flight per group, so its throughput hangs on this
-    const int want_stages = (p.block_k == 128 || p.slab) ? 3 : 4;
+    // (measured: the 256-wide CTA-pair tiles of the 64x64 / 32x32 layers prefer a 5-deep ring over a second staging slot)
+    const int want_stages = (p.block_k == 128 || p.slab) ? 3 : (p.ncta == 2 && p.block_n >= 256) ? 5 : 4;
     int per_group = p.ep.resid ? 3 : 2;
     while (per_group > 1 && (kSmemBudget - fixed - kEpiGroups * per_group * kStagingBytes) / stage_bytes < want_stages) --per_group;
     { const char* e = getenv("CLPK_IGEMM_SLOTS"); if (e && atoi(e) >= 1 && atoi(e) <= 3) per_group = atoi(e); }
