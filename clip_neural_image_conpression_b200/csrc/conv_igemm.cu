@@ -418,6 +418,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int bar_id = 1 + eg;
     int it = 0;
     uint32_t slot = 0, sphase = 0;           // staging slot of the current chunk and how often the ring has wrapped (parity)
+    bool slot_pending = false;               // a store was committed whose slot-reuse bookkeeping is still to be done
     int cached_key = -1;
     // Residual sub-boxes are TMA-loaded straight into the staging slot that is later stored from (read-modify-write in
     // place).  Lane 0 keeps `A` of them in flight; (ld_tile, ld_c, ld_slot) is its load cursor.
@@ -487,9 +488,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           uint8_t* sbuf = wslots + (size_t)slot * kWarpSlotBytes;
           uint32_t r[32];
           float gsums[16];
-          __syncwarp();  // also orders lane 0's slot bookkeeping of the previous chunk before this chunk's smem writes
+          __syncwarp();
           tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
           tmem_ld16(taddr + (uint32_t)c + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+          if (slot_pending) {
+            // Deferred slot bookkeeping of the previous chunk (its store was committed there), done by lane 0 while the
+            // TMEM loads are in flight instead of right after the store, when its wait would stall the whole warp:
+            //  residual: the load of chunk g+A targets the slot last stored from by chunk g+A-S -> at most S-A store groups
+            //            may still be reading smem (A = S-1 -> 1; S = 1, A = 1 -> 0);
+            //  plain   : this chunk writes the slot last stored from S chunks ago -> at most S-1 pending.
+            if (lane == 0) {
+              if (res_tma) {
+                if (S - A >= 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+                issue_res_load();
+              } else {
+                if (S - 1 >= 2) bulk_wait_group_read<2>(); else if (S - 1 == 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+              }
+            }
+            slot_pending = false;
+            __syncwarp();  // publishes the slot state to the other lanes before this chunk's smem accesses
+          }
           tmem_ld_wait();
           CLPK_TRACE(tr, 102);
           if (!(CLPK_DBG(1))) {
@@ -563,18 +581,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (lane == 0 && !(CLPK_DBG(1))) {
               tma_store_5d(&maps_out.m[tc.phase], sbuf, tc.n0 + c, tc.w0 + sub_w, 0, tc.h0 + sub_h, tc.b);
               bulk_commit_group();
-              // Slot reuse (per warp; stores of chunks <= g are now committed).
-              //  residual: the load of chunk g+A targets the slot last stored from by chunk g+A-S -> at most S-A groups may
-              //            still be pending (A = S-1 -> 1; S = 1, A = 1 -> 0);
-              //  plain   : chunk g+1 writes the slot last stored from by chunk g+1-S -> at most S-1 pending; the
-              //            __syncwarp at the top of the next chunk publishes it to the other lanes.
-              if (res_tma) {
-                if (S - A >= 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
-                issue_res_load();
-              } else {
-                if (S - 1 >= 2) bulk_wait_group_read<2>(); else if (S - 1 == 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
-              }
             }
+            slot_pending = !(CLPK_DBG(1));  // slot reuse is settled at the top of the next chunk
             if (++slot == (uint32_t)S) { slot = 0; sphase ^= 1u; }
           }
           CLPK_TRACE(tr, 107);
