@@ -205,6 +205,30 @@ int launch_ddim_advance(DdimRun* run_dev, cudaStream_t stream) {
   return CLPK_OK;
 }
 
+// DDPM helpers (PKG/diffusion/scheduler.py:46-68: q_sample, predict_x0_from_eps, the posterior mean of p_mean_variance):
+//   out[b, i] = clamp?( (ca[b] * x[b, i] + cb[b] * y[b, i]) / cdiv[b]? )
+// with per-sample coefficients gathered from the schedule tables on the host side.  Every multiply / add / divide is
+// individually rounded (no FMA contraction), so the result is bit-identical to the reference's ATen expression:
+//   q_sample            : ca = sqrt_ac[t], cb = sqrt_1m_ac[t]                     (a*x0 + b*noise)
+//   predict_x0_from_eps : ca = 1, cb = -sqrt_1m_ac[t], cdiv = sqrt_ac[t]           ((x_t - b*eps) / a; 1*x and -(b*eps) exact)
+//   posterior mean      : ca = coef1, cb = coef2                                   (c1*x0_pred + c2*x_t)
+__global__ void ddpm_combine_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ ca,
+                                    const float* __restrict__ cb, const float* __restrict__ cdiv, float* __restrict__ out,
+                                    long long per_image, int clamp) {
+  const int b = blockIdx.y;
+  const float a = ca[b], bb = cb[b];
+  const float d = cdiv ? cdiv[b] : 1.0f;
+  const float* px = x + (long long)b * per_image;
+  const float* py = y + (long long)b * per_image;
+  float* po = out + (long long)b * per_image;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_image; i += (long long)gridDim.x * blockDim.x) {
+    float v = __fadd_rn(__fmul_rn(a, px[i]), __fmul_rn(bb, py[i]));
+    if (cdiv) v = __fdiv_rn(v, d);
+    if (clamp && v == v) v = fminf(fmaxf(v, -1.0f), 1.0f);  // torch.clamp(-1, 1) propagates NaN; fmaxf/fminf would drop it
+    po[i] = v;
+  }
+}
+
 // Holds the stream for `ns` nanoseconds (one thread).  Used by the profiling pass: while it runs, the host enqueues a whole
 // DDIM step (launches + event records), so the bracketed kernels then execute back to back and the event timestamps do
 // not contain host launch latency.
@@ -449,6 +473,16 @@ __global__ void ssim_fold_kernel(const double* __restrict__ partial, double* __r
 }  // namespace clpk
 
 using namespace clpk;
+
+extern "C" int clpk_ddpm_combine(const float* x, const float* y, const float* ca, const float* cb, const float* cdiv,
+                                 float* out, int batch, int64_t per_image, int clamp, void* stream) {
+  CLPK_REQUIRE(x && y && ca && cb && out && batch > 0 && per_image > 0, "clpk_ddpm_combine: bad arguments");
+  CLPK_REQUIRE(batch <= 65535, "clpk_ddpm_combine: batch too large");
+  dim3 grid((unsigned)std::min<long long>((per_image + 255) / 256, (long long)num_sms() * 4), (unsigned)batch);
+  ddpm_combine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, ca, cb, cdiv, out, per_image, clamp);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
 
 extern "C" int64_t clpk_ssim_ws_bytes(int batch, int ch, int h, int w) {
   if (batch <= 0 || ch <= 0 || h < kSsimWin || w < kSsimWin) return -1;

@@ -3,8 +3,9 @@
 Only the table constructor and the attributes the DDIM sampler reads are on the decode path.  The tables are built
 ONCE with torch on the host — the same op sequence as the reference (`scheduler.py:25-44`) so they are bit-identical
 to its CPU tables — and then placed on `device`.  (A GPU `linspace`/`cumprod` can differ from the CPU oracle in the
-last ulp)  `q_sample` / `predict_x0_from_eps` / `p_mean_variance` are training / DDPM helpers kept for
-interface parity; they are plain tensor expressions and not part of the accelerated path.
+last ulp)  `q_sample` / `predict_x0_from_eps` / `p_mean_variance` (training / DDPM ancestral sampling
+helpers) run as ONE fused pass each on CUDA tensors (`clpk_ddpm_combine`, bit-identical to the
+reference's ATen expressions); on host tensors they stay plain tensor expressions (table-level host utility only).
 """
 from __future__ import annotations
 
@@ -52,17 +53,30 @@ class NoiseScheduler:
     def _col(v: torch.Tensor) -> torch.Tensor:
         return v.view(-1, 1, 1, 1)
 
-    def q_sample(self, x0: torch.Tensor, t: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
-        return self._col(self.sqrt_alphas_cumprod[t]) * x0 + self._col(self.sqrt_one_minus_alphas_cumprod[t]) * noise
+    def _combine(self, x, y, ca, cb, cdiv=None, clamp=False):
+        if x.is_cuda:
+            from .. import ops
+            return ops.ddpm_combine(x, y, ca, cb, cdiv, clamp)
+        out = self._col(ca) * x + self._col(cb) * y
+        if cdiv is not None:
+            out = out / self._col(cdiv)
+        return out.clamp(-1, 1) if clamp else out
 
-    def predict_x0_from_eps(self, x_t: torch.Tensor, t: torch.Tensor, eps_hat: torch.Tensor) -> torch.Tensor:
-        return (x_t - self._col(self.sqrt_one_minus_alphas_cumprod[t]) * eps_hat) / self._col(self.sqrt_alphas_cumprod[t])
+    def q_sample(self, x0: torch.Tensor, t: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+        """scheduler.py:46-49."""
+        return self._combine(x0, noise, self.sqrt_alphas_cumprod[t], self.sqrt_one_minus_alphas_cumprod[t])
+
+    def predict_x0_from_eps(self, x_t: torch.Tensor, t: torch.Tensor, eps_hat: torch.Tensor, clamp: bool = False) -> torch.Tensor:
+        """scheduler.py:51-55: (x_t - b*eps) / a, evaluated as (1*x_t + (-b)*eps) / a — the same roundings."""
+        b = self.sqrt_one_minus_alphas_cumprod[t]
+        return self._combine(x_t, eps_hat, torch.ones_like(b), -b, self.sqrt_alphas_cumprod[t], clamp)
 
     def p_mean_variance(self, model, x_t: torch.Tensor, z_clip: torch.Tensor, t: torch.Tensor):
+        """scheduler.py:57-68."""
         eps = model(x_t, z_clip, t)
-        x0_pred = self.predict_x0_from_eps(x_t, t, eps).clamp(-1, 1)
+        x0_pred = self.predict_x0_from_eps(x_t, t, eps, clamp=True)
         a_t, abar_t, abar_prev = self.alphas[t], self.alphas_cumprod[t], self.alphas_cumprod_prev[t]
         c0 = (torch.sqrt(abar_prev) * (1 - a_t)) / (1 - abar_t)
         c1 = (torch.sqrt(a_t) * (1 - abar_prev)) / (1 - abar_t)
-        mean = self._col(c0) * x0_pred + self._col(c1) * x_t
+        mean = self._combine(x0_pred, x_t, c0, c1)
         return mean, self._col(self.posterior_variance[t]), x0_pred

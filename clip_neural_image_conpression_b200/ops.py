@@ -15,7 +15,7 @@ from ._lib import CONV_3X3_S1, CONV_3X3_S2, CONVT_4X4_S2, ConvEpilogue, check, o
 
 __all__ = [
     "dequant_l2norm", "quant_encode", "quant_fit", "ddim_step", "timestep_embedding", "linear", "film_apply",
-    "groupnorm_silu", "pack_conv_weight", "conv_igemm", "conv_direct", "conv_in", "to_uint8_hwc", "psnr_sqerr_u8", "ssim_u8",
+    "groupnorm_silu", "pack_conv_weight", "conv_igemm", "conv_direct", "conv_in", "to_uint8_hwc", "psnr_sqerr_u8", "ssim_u8", "ddpm_combine",
     "CONV_3X3_S1", "CONV_3X3_S2", "CONVT_4X4_S2",
 ]
 
@@ -272,4 +272,20 @@ def ssim_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=a.device)
     out = torch.empty(bsz, dtype=torch.float64, device=a.device)
     check(lib.clpk_ssim_u8(ptr(a), ptr(b), ptr(out), ptr(ws), bsz, ch, h, w, stream_ptr()), "clpk_ssim_u8")
+    return out
+
+
+def ddpm_combine(x: torch.Tensor, y: torch.Tensor, ca: torch.Tensor, cb: torch.Tensor, cdiv: torch.Tensor | None = None,
+                 clamp: bool = False) -> torch.Tensor:
+    """out[b] = (ca[b]*x[b] + cb[b]*y[b]) [/ cdiv[b]] [clamp(-1, 1)] with every operation individually rounded — the DDPM
+    helpers of the reference scheduler (scheduler.py:46-68) as one fused pass (see clpk.h)."""
+    require_cuda(x, y, ca, cb)
+    x, y = _f32c(x), _f32c(y)
+    assert x.shape == y.shape and x.dim() >= 1
+    bsz = x.shape[0]
+    ca, cb = _f32c(ca).reshape(bsz), _f32c(cb).reshape(bsz)
+    cd = _f32c(cdiv).reshape(bsz) if cdiv is not None else None
+    out = torch.empty_like(x)
+    check(_lib.load().clpk_ddpm_combine(ptr(x), ptr(y), ptr(ca), ptr(cb), ptr(cd), ptr(out), bsz, x.numel() // bsz,
+                                        1 if clamp else 0, stream_ptr()), "clpk_ddpm_combine")
     return out

@@ -230,6 +230,13 @@ int clpk_to_uint8_hwc(const float* x_nchw_dev, uint8_t* out_hwc_dev, int batch, 
 int clpk_psnr_sqerr_u8(const float* a_dev, const float* b_dev, int64_t* sq_err_sum_dev, int batch, int64_t per_image,
                        void* stream);
 
+/* DDPM helpers (PKG/diffusion/scheduler.py:46-68): out[b,i] = (ca[b]*x[b,i] + cb[b]*y[b,i]) [/ cdiv[b]] [clamped to
+ * [-1,1]], every operation individually rounded like the reference's ATen expressions.  q_sample: ca = sqrt_ac[t],
+ * cb = sqrt_1m_ac[t]; predict_x0_from_eps: ca = 1, cb = -sqrt_1m_ac[t], cdiv = sqrt_ac[t]; posterior mean of
+ * p_mean_variance: ca = coef1[t], cb = coef2[t].  ca / cb / cdiv: device fp32 [batch] (cdiv may be NULL). */
+int clpk_ddpm_combine(const float* x_dev, const float* y_dev, const float* ca_dev, const float* cb_dev, const float* cdiv_dev,
+                      float* out_dev, int batch, int64_t per_image, int clamp, void* stream);
+
 /* per-image SSIM in the uint8 domain (metrics.py:32-46: skimage structural_similarity(HWC uint8, data_range=255,
  * channel_axis=-1) with its defaults — 7x7 uniform window, K1 0.01, K2 0.03, sample covariance, float64, 3-pixel border
  * cropped, mean over pixels then over channels).  a, b: fp32 NCHW [batch,ch,h,w] in [-1,1]; out: fp64 [batch];

@@ -135,6 +135,28 @@ def scheduler_tables(timesteps: int = 1000, schedule: str = "cosine") -> Dict[st
 
 
 # ---------------------------------------------------------------------------------------------------------------- UNet
+def q_sample(tabs: Dict[str, torch.Tensor], x0: torch.Tensor, t: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """PKG/diffusion/scheduler.py:46-49."""
+    return (tabs["sqrt_alphas_cumprod"][t].view(-1, 1, 1, 1) * x0 +
+            tabs["sqrt_one_minus_alphas_cumprod"][t].view(-1, 1, 1, 1) * noise)
+
+
+def predict_x0_from_eps(tabs: Dict[str, torch.Tensor], x_t: torch.Tensor, t: torch.Tensor, eps_hat: torch.Tensor) -> torch.Tensor:
+    """PKG/diffusion/scheduler.py:51-55."""
+    return (x_t - tabs["sqrt_one_minus_alphas_cumprod"][t].view(-1, 1, 1, 1) * eps_hat) / \
+        tabs["sqrt_alphas_cumprod"][t].view(-1, 1, 1, 1)
+
+
+def p_mean_variance(tabs: Dict[str, torch.Tensor], eps: torch.Tensor, x_t: torch.Tensor, t: torch.Tensor):
+    """PKG/diffusion/scheduler.py:57-68 given the model output eps = model(x_t, z_clip, t)."""
+    x0_pred = predict_x0_from_eps(tabs, x_t, t, eps).clamp(-1, 1)
+    al_t, al_bar_t, al_bar_prev = tabs["alphas"][t], tabs["alphas_cumprod"][t], tabs["alphas_cumprod_prev"][t]
+    coef1 = (torch.sqrt(al_bar_prev) * (1 - al_t)) / (1 - al_bar_t)
+    coef2 = (torch.sqrt(al_t) * (1 - al_bar_prev)) / (1 - al_bar_t)
+    mean = coef1.view(-1, 1, 1, 1) * x0_pred + coef2.view(-1, 1, 1, 1) * x_t
+    return mean, tabs["posterior_variance"][t].view(-1, 1, 1, 1), x0_pred
+
+
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: int = 10000) -> torch.Tensor:
     """PKG/models/unet.py:22-39."""
     half = dim // 2

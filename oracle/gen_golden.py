@@ -69,8 +69,27 @@ def ref_net(R, cfg, seed, out_gain=1.0):
     return net.eval()
 
 
+def write_ddpm(R, out) -> None:
+    """DDPM helpers of the reference scheduler (PKG/diffusion/scheduler.py:46-68) on CPU -> tests/golden/ddpm.npz."""
+    g = torch.Generator().manual_seed(13)
+    x0 = torch.randn(4, 3, 16, 16, generator=g) * 0.8
+    noise, eps = torch.randn(4, 3, 16, 16, generator=g), torch.randn(4, 3, 16, 16, generator=g)
+    t = torch.tensor([0, 17, 500, 999])
+    dd = {"x0": x0.numpy(), "noise": noise.numpy(), "eps": eps.numpy(), "t": t.numpy()}
+    for sch in ("cosine", "linear"):
+        s = R.sched.NoiseScheduler(1000, sch, "cpu")
+        xt = s.q_sample(x0, t, noise)
+        mean, var, x0c = s.p_mean_variance(lambda x, z, tt: eps, xt, None, t)
+        dd.update({f"{sch}.xt": xt.numpy(), f"{sch}.x0_pred": s.predict_x0_from_eps(xt, t, eps).numpy(),
+                   f"{sch}.mean": mean.numpy(), f"{sch}.var": var.numpy(), f"{sch}.x0_clamped": x0c.numpy()})
+    np.savez_compressed(out / "ddpm.npz", **dd)
+
+
 def main() -> None:
     R = import_reference()
+    if "--only-ddpm" in sys.argv:   # adds the ddpm fixture without rewriting the others
+        write_ddpm(R, ROOT / "tests" / "golden")
+        return
     out = ROOT / "tests" / "golden"
     out.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
@@ -168,6 +187,7 @@ def main() -> None:
     u8 = np.stack([((np.clip(a[i], -1, 1).transpose(1, 2, 0) + 1.0) * 127.5).astype(np.uint8) for i in range(3)])
     ps = np.array([R.metrics.psnr(a[i], b[i]) for i in range(3)] + [R.metrics.psnr(a[0], a[0])])
     np.savez_compressed(out / "metrics.npz", a=a, b=b, u8=u8, psnr=ps, metric_u8=R.metrics._to_uint8(a))
+    write_ddpm(R, out)
     total = sum(p.stat().st_size for p in out.glob("*.npz"))
     print(f"wrote {len(list(out.glob('*.npz')))} fixtures, {total / 1024:.0f} KiB")
 

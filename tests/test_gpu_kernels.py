@@ -340,3 +340,24 @@ def test_ssim_matches_oracle(ops, oracle, golden):
         ops.ssim_u8(cu(g["a"][:, :, :5]), cu(g["b"][:, :, :5]))
     with pytest.raises(ValueError):
         ssim(g["a"][0][:1], g["b"][0][:1])                                  # (1,H,W): skimage raises, so do we
+
+
+def test_ddpm_helpers_bit_exact(golden):
+    """clpk_ddpm_combine through the NoiseScheduler mirror == the reference's CPU results, bit for bit (scheduler.py:46-68)."""
+    from clip_neural_image_conpression_b200.diffusion import NoiseScheduler
+    g = golden("ddpm")
+    x0, noise, eps = (cu(g[k]) for k in ("x0", "noise", "eps"))
+    t = torch.from_numpy(g["t"]).cuda()
+    for sch in ("cosine", "linear"):
+        s = NoiseScheduler(1000, sch, "cuda")
+        xt = s.q_sample(x0, t, noise)
+        assert np.array_equal(xt.cpu().numpy(), g[f"{sch}.xt"])
+        assert np.array_equal(s.predict_x0_from_eps(xt, t, eps).cpu().numpy(), g[f"{sch}.x0_pred"])
+        mean, var, x0c = s.p_mean_variance(lambda x, z, tt: eps, xt, None, t)
+        assert np.array_equal(mean.cpu().numpy(), g[f"{sch}.mean"])
+        assert np.array_equal(var.cpu().numpy(), g[f"{sch}.var"]) and var.shape == (4, 1, 1, 1)
+        assert np.array_equal(x0c.cpu().numpy(), g[f"{sch}.x0_clamped"])
+    # NaN propagates through the clamp like torch.clamp
+    bad = x0.clone(); bad[0, 0, 0, 0] = float("nan")
+    out = s.predict_x0_from_eps(bad, t, eps, clamp=True)
+    assert torch.isnan(out[0, 0, 0, 0]) and float(out[1:].abs().max()) <= 1.0

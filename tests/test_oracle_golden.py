@@ -126,3 +126,17 @@ def test_ssim_known_answers(oracle):
     np.testing.assert_allclose(oracle.ssim(a[:1].repeat(3, 0), b[:1].repeat(3, 0)), np.mean(vals), rtol=1e-10)
     with pytest.raises(ValueError):
         oracle.ssim(a[:, :5], b[:, :5])                                       # smaller than the 7x7 window
+
+
+def test_ddpm_helpers_match_reference(oracle, golden):
+    """q_sample / predict_x0_from_eps / p_mean_variance (scheduler.py:46-68): oracle == reference output, bit for bit."""
+    g = golden("ddpm")
+    x0, noise, eps, t = (torch.from_numpy(g[k]) for k in ("x0", "noise", "eps", "t"))
+    for sch in ("cosine", "linear"):
+        tabs = oracle.scheduler_tables(1000, sch)
+        xt = oracle.q_sample(tabs, x0, t, noise)
+        assert np.array_equal(xt.numpy(), g[f"{sch}.xt"])
+        assert np.array_equal(oracle.predict_x0_from_eps(tabs, xt, t, eps).numpy(), g[f"{sch}.x0_pred"])
+        mean, var, x0c = oracle.p_mean_variance(tabs, eps, xt, t)
+        assert np.array_equal(mean.numpy(), g[f"{sch}.mean"]) and np.array_equal(var.numpy(), g[f"{sch}.var"])
+        assert np.array_equal(x0c.numpy(), g[f"{sch}.x0_clamped"])
