@@ -478,7 +478,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           cached_key = key;
         }
         float2 (*red_t)[4][8] = vec->red[it & 1][eg];  // [chunk of this group][warp][pair]
-        const bool tr = blockIdx.x == 0 && ew == 0 && lane == 0;
+        [[maybe_unused]] const bool tr = blockIdx.x == 0 && ew == 0 && lane == 0;  // traced warp (debug builds)
         CLPK_TRACE(tr, 100);
         mbar_wait(&bars->tmem_full[as], aphase);
         tc_fence_after();
