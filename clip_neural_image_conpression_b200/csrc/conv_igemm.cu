@@ -53,6 +53,7 @@ struct TileCoord {
 // phases of one spatial tile adjacent in time lets their interleaved output rows meet in L2 before they reach HBM.
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int item, int rank) {
   TileCoord c;
+  if (p.reverse) item = p.num_tiles - 1 - item;  // walk the tensor back to front (see IgemmParams::reverse)
   const int nt = item % p.n_tiles_n;
   int r = item / p.n_tiles_n;
   c.phase = r % p.phases;
@@ -837,6 +838,8 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   IgemmParams& p = out->p;
   memset(&p, 0, sizeof(p));
   { const char* e = getenv("CLPK_IGEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
+  // default on: +0.5 % images/s measured in the step graph (the tail of the operand is what the preceding kernel wrote last)
+  { const char* e = getenv("CLPK_IGEMM_REVERSE"); p.reverse = (e && atoi(e) == 0) ? 0 : 1; }
   p.batch = batch;
   p.op_f16 = (op_dtype == CLPK_OP_F16) ? 1 : 0;
   p.cin = cin;

@@ -28,6 +28,8 @@ struct IgemmParams {
   int n_staging;            // epilogue staging buffers (128 rows x 128 B each) for the TMA-store path, 0 = direct stores
   int res_ahead;            // residual chunks the epilogue leader keeps in flight ahead of the one being processed
   int gn_groups, gn_slots, gn_sub;  // fused GroupNorm statistics: groups, partial slots per image, chunks per group slot
+  int reverse;              // 1 (default; env CLPK_IGEMM_REVERSE=0 turns it off): tiles are walked from the END of the tensor —
+                            // the tail of the operand is what the preceding kernel wrote last and is the likeliest L2 resident
   int dbg;                  // perf-debug switches (env CLPK_IGEMM_DBG): 1 no epilogue memory ops, 2 no MMA, 4 no A loads, 8 no B loads
   // A-operand coordinates (5-D view of the NHWC input, see make_a_map): per (phase*taps + tap)
   int tap_x[kMaxTapEntries], tap_dw[kMaxTapEntries], tap_p[kMaxTapEntries], tap_dh[kMaxTapEntries];
