@@ -88,6 +88,15 @@ constexpr int kWarpSlotBytes = 32 * 128;  // per-warp staging slot: 32 tile rows
 // clpk_debug_trace (debug builds only)
 __device__ long long g_trace[8192];
 __device__ int g_trace_n;
+#define CLPK_GTRACE(cond, tag)                                                       \
+  do {                                                                               \
+    if ((p.dbg & 128) && (cond)) {                                                   \
+      long long _t;                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                         \
+      const int _i = atomicAdd(&g_trace_n, 1);                                       \
+      if (_i < 4096) { g_trace[2 * _i] = (tag); g_trace[2 * _i + 1] = _t; }          \
+    }                                                                                \
+  } while (0)
 #define CLPK_TRACE(cond, tag)                                                        \
   do {                                                                               \
     if ((p.dbg & 64) && (cond)) {                                                    \
@@ -98,6 +107,7 @@ __device__ int g_trace_n;
 #else
 #define CLPK_DBG(bits) 0
 #define CLPK_TRACE(cond, tag) do { } while (0)
+#define CLPK_GTRACE(cond, tag) do { } while (0)
 #endif
 static inline int epi_vector_bytes(int block_n) { return 2 * 4 * block_n + kRedBytes; }
 
@@ -200,6 +210,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   constexpr int kABytes = kSlab ? kSlabABytes : kAAtomBytes * kAtoms;   // one A stage
   static_assert(!kSlab || BLOCK_K == 64, "slab mode stages 64-channel slabs");
   extern __shared__ uint8_t smem_raw[];
+  CLPK_GTRACE(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 300);  // kernel entry
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
   uint8_t* smem = smem_raw + pad;  // 1024-byte aligned (swizzle atoms)
@@ -247,6 +258,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   pdl_prologue_done();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  CLPK_GTRACE(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 301);  // setup done
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -350,6 +362,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&bars->full[stage], phase);  // TMA bytes (of both CTAs) have landed
           tc_fence_after();
+          CLPK_GTRACE(lane == 0 && it == 0 && kb == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 302);  // first operands landed
           if (elect_one()) {
             const uint64_t adesc = adesc0 + a_step * (uint64_t)stage;
             const uint64_t bdesc = bdesc0 + b_step * (uint64_t)stage;
@@ -387,6 +400,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (NCTA == 2) umma_commit_pair(&bars->empty[stage]); else umma_commit(&bars->empty[stage]);
             if (kb == k_blocks - 1) {
               if (NCTA == 2) umma_commit_pair(&bars->tmem_full[as]); else umma_commit(&bars->tmem_full[as]);
+              CLPK_GTRACE((blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 303);  // a tile's MMAs issued (last one = mainloop end)
             }
           }
           __syncwarp();
@@ -665,6 +679,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
     if (lane == 0 && st_tma) bulk_wait_group_all();  // all of this warp's stores retired before smem goes away
+    CLPK_GTRACE(lane == 0 && ew == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 304);  // epilogue done
   }
 
   tc_fence_before();
@@ -673,6 +688,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 1) {
     if (NCTA == 2) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  CLPK_GTRACE(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 305);  // kernel exit
 }
 
 // ------------------------------------------------------------------------------------------------ cross-check kernel
