@@ -789,7 +789,7 @@ static bool warp_subbox_ok(int wbox) { return wbox % 32 == 0 || 32 % wbox == 0; 
 int igemm_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg) {
   if (gn_cpg <= 0 || cout % gn_cpg != 0 || cout % 32 != 0) return 0;
   if (!(gn_cpg == 4 || gn_cpg == 8 || gn_cpg == 16 || gn_cpg % 32 == 0)) return 0;
-  if (cout / gn_cpg > 32) return 0;
+  if (cout / gn_cpg > 512) return 0;
   int gh, gw, wbox, hbox, phases;
   tile_geometry(kind, h_in, w_in, &gh, &gw, &wbox, &hbox, &phases);
   if (!warp_subbox_ok(wbox)) return 0;

@@ -210,7 +210,7 @@ __device__ __forceinline__ void gn_affine8(const float* __restrict__ gamma, cons
 template <bool kIn16, bool kHoist>
 __global__ void __launch_bounds__(kGnThreads, 4)
 gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float2* __restrict__ stats, const float2* __restrict__ partial, int slots, double n_per_group,
+                const float2* __restrict__ stats, const float2* __restrict__ partial, int slots, int pieces, double n_per_group,
                 float eps, uint16_t* __restrict__ y, int hw, int c, int groups, int silu, int op_f16) {
   __shared__ float2 st_s[32];
   pdl_prologue_done();
@@ -219,10 +219,15 @@ gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, c
   if (partial) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int g = warp; g < groups; g += kGnThreads / 32) {
-      const float2* pp = partial + (long long)b * slots * groups + g;
+      // partial[b][slot][piece]: `pieces` partial sums per slot, group g owns pieces [g*m, (g+1)*m), m = pieces / groups
+      // (m = 1: one partial per group; m > 1: group sizes such as 24 or 48 that the conv epilogue can only sum in 8- or
+      // 16-channel pieces)
+      const int m = pieces / groups;
+      const float2* pp = partial + (long long)b * slots * pieces + g * m;
       double S = 0.0, SS = 0.0;
-      for (int k = lane; k < slots; k += 32) {
-        const float2 v = __ldg(pp + (long long)k * groups);
+      for (int k = lane; k < slots * m; k += 32) {
+        const int slot = k / m, j = k - slot * m;
+        const float2 v = __ldg(pp + (long long)slot * pieces + j);
         S += (double)v.x; SS += (double)v.y;
       }
 #pragma unroll
@@ -306,7 +311,8 @@ int launch_gn_finalize(const float2* partial, float2* stats, int batch, int slot
 
 // x: fp32 NHWC (x_is_16 == 0) or 16-bit NHWC in the operand format.  Exactly one of stats / partial is used.
 int launch_gn_apply_ex(const void* x, int x_is_16, const float* gamma, const float* beta, const float2* stats,
-                       const float2* partial, int slots, double n_per_group, float eps, void* y_op, const GnShape& s,
+                       const float2* partial, int slots, int pieces, double n_per_group, float eps, void* y_op,
+                       const GnShape& s,
                        int silu, int op_dtype, cudaStream_t stream) {
   const long long octs = (long long)s.hw * (s.c / 8);
   CLPK_REQUIRE(s.c % 8 == 0 && s.c % s.groups == 0 && (s.c / s.groups) % 4 == 0,
@@ -320,7 +326,7 @@ int launch_gn_apply_ex(const void* x, int x_is_16, const float* gamma, const flo
   const bool f16 = op_dtype == CLPK_OP_F16;
 #define CLPK_GN_APPLY(IN16, HOIST)                                                                                    \
   launch_err = launch_kernel_pdl(gn_apply_kernel<IN16, HOIST>, agrid, dim3(kGnThreads), 0, stream, x, gamma, beta, stats,  \
-                                 partial, slots, n_per_group, eps, y, s.hw, s.c, s.groups, silu, (int)f16)
+                                 partial, slots, pieces, n_per_group, eps, y, s.hw, s.c, s.groups, silu, (int)f16)
   cudaError_t launch_err = cudaSuccess;
   if (x_is_16) { if (hoist) CLPK_GN_APPLY(true, true); else CLPK_GN_APPLY(true, false); }
   else { if (hoist) CLPK_GN_APPLY(false, true); else CLPK_GN_APPLY(false, false); }
@@ -332,7 +338,7 @@ int launch_gn_apply_ex(const void* x, int x_is_16, const float* gamma, const flo
 
 int launch_gn_apply(const float* x, const float* gamma, const float* beta, const float2* stats, void* y_op,
                     const GnShape& s, int silu, int op_dtype, cudaStream_t stream) {
-  return launch_gn_apply_ex(x, 0, gamma, beta, stats, nullptr, 0, 1.0, 0.f, y_op, s, silu, op_dtype, stream);
+  return launch_gn_apply_ex(x, 0, gamma, beta, stats, nullptr, 0, s.groups, 1.0, 0.f, y_op, s, silu, op_dtype, stream);
 }
 
 // statistics pass only: leaves (mean, rstd) in the stats area of ws (see layout above) and returns its address

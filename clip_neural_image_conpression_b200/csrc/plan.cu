@@ -38,6 +38,7 @@ struct GnPlan {
   float2* stats = nullptr;    // [B][groups] (mean, rstd)
   float2* partial = nullptr;  // [B][slots][groups] (sum, sumsq) written by the producer conv
   int slots = 0;
+  int piece = 0, pieces = 0;  // channels per partial sum the producer epilogue emits, and their number (C / piece)
   bool fused = false;
 };
 
@@ -229,9 +230,16 @@ int gn_groups_of(const clpk_plan* P, int level) { return std::min(P->cfg.groups,
 int setup_gn(clpk_plan* P, GnPlan* gn, int producer_kind, int prod_h_in, int prod_w_in) {
   const int c = P->lv_c[gn->level], groups = gn_groups_of(P, gn->level);
   CLPK_TRY(P->alloc(&gn->stats, (long long)P->B * groups));
-  gn->slots = (producer_kind >= 0) ? igemm_gn_slots(producer_kind, prod_h_in, prod_w_in, c, c / groups) : 0;
+  // The conv epilogue sums 4 / 8 / 16 channels or whole multiples of 32 at a time.  A group of another size (24, 48:
+  // base = 192) is summed in pieces of the largest of 16 / 8 / 4 that divides it; the apply kernel folds the pieces.
+  const int cpg = c / groups;
+  int piece = cpg;
+  if (!(cpg == 4 || cpg == 8 || cpg == 16 || cpg % 32 == 0)) piece = (cpg % 16 == 0) ? 16 : (cpg % 8 == 0) ? 8 : (cpg % 4 == 0) ? 4 : 0;
+  gn->piece = piece;
+  gn->pieces = piece > 0 ? c / piece : 0;
+  gn->slots = (producer_kind >= 0 && piece > 0) ? igemm_gn_slots(producer_kind, prod_h_in, prod_w_in, c, piece) : 0;
   gn->fused = gn->slots > 0;
-  if (gn->fused) CLPK_TRY(P->alloc(&gn->partial, (long long)P->B * gn->slots * groups));
+  if (gn->fused) CLPK_TRY(P->alloc(&gn->partial, (long long)P->B * gn->slots * gn->pieces));
   return CLPK_OK;
 }
 
@@ -243,13 +251,13 @@ int run_groupnorm(clpk_plan* P, const void* x, int x_is_16, const GnPlan& gn, cu
   int rc;
   if (gn.fused) {
     // statistics come from the producing conv's epilogue partials and are folded inside the apply kernel
-    rc = launch_gn_apply_ex(x, x_is_16, gn.gamma, gn.beta, nullptr, gn.partial, gn.slots, (double)hw * (c / groups), 1e-5f,
+    rc = launch_gn_apply_ex(x, x_is_16, gn.gamma, gn.beta, nullptr, gn.partial, gn.slots, gn.pieces, (double)hw * (c / groups), 1e-5f,
                             P->T, shp, gn.silu, P->cfg.op_dtype, s);
   } else {
     const float2* stats = nullptr;
     rc = x_is_16 ? CLPK_ERR_STATE : launch_gn_stats(reinterpret_cast<const float*>(x), P->gn_ws, shp, 1e-5f, &stats, s);
     if (rc == CLPK_OK)
-      rc = launch_gn_apply_ex(x, 0, gn.gamma, gn.beta, stats, nullptr, 0, 1.0, 0.f, P->T, shp, gn.silu, P->cfg.op_dtype, s);
+      rc = launch_gn_apply_ex(x, 0, gn.gamma, gn.beta, stats, nullptr, 0, groups, 1.0, 0.f, P->T, shp, gn.silu, P->cfg.op_dtype, s);
   }
   P->prof_mark(-1, s);
   return rc;
@@ -454,7 +462,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   auto wire_gn = [&](clpk_conv_epilogue* e, const GnPlan* gn) {
     if (gn && gn->fused) {
       e->gn_partial = gn->partial;
-      e->gn_cpg = P->lv_c[gn->level] / gn_groups_of(P, gn->level);
+      e->gn_cpg = gn->piece;  // channels per partial sum (== channels per group unless the group is summed in pieces)
     }
   };
   for (size_t i = 0; i < specs.size(); ++i) {
