@@ -132,14 +132,44 @@ def check(rc: int, what: str = "") -> None:
 
 
 def require_cuda(*tensors) -> None:
-    """The hot path is CUDA-only; refuse anything else loudly."""
+    """The hot path is CUDA-only; refuse anything else loudly.  All tensors of one call must share one device."""
     import torch
 
     if not torch.cuda.is_available():
         raise ClpkError("this code path needs an sm_100a CUDA device (no CPU fallback exists)")
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise ClpkError("expected CUDA tensors (no CPU fallback exists)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ClpkError(f"tensors of one call live on different devices ({dev} and {t.device})")
+
+
+def on_tensor_device(fn):
+    """Decorator: runs `fn` with the device of its first CUDA tensor argument made current, so that the stream handed to
+    libclpk, its allocations and its per-device state all belong to the tensors' GPU (not to whatever device happens to
+    be current in the caller)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrap(*args, **kwargs):
+        import torch
+
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrap
 
 
 def stream_ptr() -> int:

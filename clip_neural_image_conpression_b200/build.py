@@ -40,12 +40,28 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compiles the sources when libclpk.so is missing or older than them.  Safe under torchrun: an inter-process file
+    lock serialises the ranks (the first one builds, the others find a fresh library), objects go to a per-PID
+    directory and the library is replaced atomically."""
     if not force and not is_stale():
         return LIB
-    nvcc = find_nvcc()
-    objdir = CSRC / "build"
-    objdir.mkdir(exist_ok=True)
+    import fcntl
+    import tempfile
 
+    with open(CSRC / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():   # another rank built it while this one waited for the lock
+                return LIB
+            nvcc = find_nvcc()
+            (CSRC / "build").mkdir(exist_ok=True)
+            with tempfile.TemporaryDirectory(prefix=f"obj{os.getpid()}_", dir=CSRC / "build") as objdir:
+                return _compile_and_link(nvcc, Path(objdir), verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _compile_and_link(nvcc: str, objdir: Path, verbose: bool) -> Path:
     def compile_one(src: str) -> Path:
         obj = objdir / (src[:-3] + ".o")
         cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("CLPK_NVCC_EXTRA", "").split(), "-c", str(CSRC / src), "-o", str(obj)]
@@ -60,7 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB.with_suffix(".so.tmp")
+    tmp = LIB.with_suffix(f".so.tmp{os.getpid()}")
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *map(str, objs)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

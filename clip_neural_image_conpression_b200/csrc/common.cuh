@@ -329,16 +329,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// fp16 stores SATURATE (cvt.rn.satfinite: |x| > 65504 -> +-65504, NaN stays NaN): the 16-bit copies of un-normalised
+// tensors (conv1 + FiLM output Y, residual-stream copy X16) must not turn a large finite activation of a trained
+// checkpoint into inf -> NaN in the next GroupNorm.  Same single F2FP instruction as the non-saturating form.
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  __half2 v = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 // two fp32 -> two 16-bit operand values (fp16 when f16, else bf16), round to nearest even
 __device__ __forceinline__ uint32_t pack_op2(float lo, float hi, bool f16) {
   return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
 __device__ __forceinline__ uint16_t to_op(float v, bool f16) {
-  if (f16) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  if (f16) { uint16_t h; asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v)); return h; }
   __nv_bfloat16 b = __float2bfloat16_rn(v);
   return *reinterpret_cast<uint16_t*>(&b);
 }

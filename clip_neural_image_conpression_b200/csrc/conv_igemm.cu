@@ -71,13 +71,26 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int item,
 
 // per-tile epilogue vectors: y = acc * mul[n] + add[n]   (mul = 1 + FiLM scale or 1, add = bias * mul + FiLM shift)
 constexpr int kMaxGroupChunks = 4;  // 32-column chunks one epilogue group handles per tile (block_n <= 256, 2 groups)
-struct EpiVectors {       // laid out in smem as: float mul[block_n] | float add[block_n] | float2 red[...]
+// Fused GroupNorm statistics are SHIFTED sums (robust against |mean| >> std, like torch's Welford pass): every epilogue
+// warp takes K = the first value it sees of a group (lane 0's first channel, broadcast) and accumulates sum(x - K),
+// sum((x - K)^2) over its 32 rows; the per-tile fold re-bases the 4 warps' sums on warp 0's K and emits the tile's
+// (mean, M2 = sum((x - mean)^2), n) triple, which the consumer combines in fp64 (Chan et al.).
+struct EpiVectors {       // laid out in smem as: float mul[block_n] | float add[block_n] | red | redk | rows
   float* mul;
   float* add;
-  // fused GN statistics: [tile parity][epilogue group][chunk of the group][warp][group pair] partial (sum, sumsq)
-  float2 (*red)[kEpiGroups][kMaxGroupChunks][4][8];
+  float2* red;    // [tile parity][epilogue group][chunk of the group][warp][group pair] shifted (sum, sumsq)
+  float* redk;    // same indexing: the warp's shift K
+  int* rows;      // [tile parity][epilogue group][warp] valid rows of the warp in this tile
+  int nchg;       // chunks per epilogue group = ceil(block_n / 32 / kEpiGroups)
+  __device__ __forceinline__ int idx(int parity, int eg, int ci, int warp) const {
+    return (((parity * kEpiGroups + eg) * nchg + ci) * 4 + warp) * 8;
+  }
 };
-constexpr int kRedBytes = 2 * kEpiGroups * kMaxGroupChunks * 4 * 8 * (int)sizeof(float2);
+static __host__ __device__ inline int red_chunks_per_group(int block_n) { return (block_n / 32 + kEpiGroups - 1) / kEpiGroups; }
+static __host__ __device__ inline int red_bytes(int block_n) {
+  const int n = 2 * kEpiGroups * (red_chunks_per_group(block_n) > 0 ? red_chunks_per_group(block_n) : 1) * 4 * 8;
+  return n * (int)(sizeof(float2) + sizeof(float)) + 2 * kEpiGroups * 4 * (int)sizeof(int) + 32;
+}
 constexpr int kWarpSlotBytes = 32 * 128;  // per-warp staging slot: 32 tile rows x 128 B (fp32) or x 64 B (16-bit)
 
 // perf-debug switches (env CLPK_IGEMM_DBG) are compiled in only with -DCLPK_IGEMM_DEBUG: their uniform branches sit in
@@ -109,7 +122,7 @@ __device__ int g_trace_n;
 #define CLPK_TRACE(cond, tag) do { } while (0)
 #define CLPK_GTRACE(cond, tag) do { } while (0)
 #endif
-static inline int epi_vector_bytes(int block_n) { return 2 * 4 * block_n + kRedBytes; }
+static inline int epi_vector_bytes(int block_n) { return 2 * 4 * block_n + (red_bytes(block_n) + 63) / 64 * 64; }
 
 constexpr int kStagingBytes = kTileM * 128;
 
@@ -119,14 +132,16 @@ constexpr int kStagingBytes = kTileM * 128;
 // (NV/2 + NV/4 + ... shuffles instead of 5*NV); afterwards lane L holds the total of value index
 // bitreverse-ordered by the lane bits consumed, see `owner` below.  Fixed tree -> deterministic.
 template <int P>
-__device__ __forceinline__ void row_sums(const float (&v)[32], bool valid, float (&out)[2 * P]) {
+__device__ __forceinline__ void row_sums(const float (&v)[32], bool valid, float (&out)[2 * P], float (&kshift)[P]) {
   constexpr int per = 32 / P;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
+    const float k = __shfl_sync(0xffffffffu, v[i * per], 0);  // the warp's shift for this group (any finite value works)
+    kshift[i] = k;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < per; ++j) {
-      const float x = v[i * per + j];
+      const float x = v[i * per + j] - k;
       s1 += x;
       s2 = fmaf(x, x, s2);
     }
@@ -168,17 +183,20 @@ __device__ __forceinline__ int scatter_owner_index(int lane) {
   return idx;
 }
 
-// phase 1 (while the chunk's values are live): per-thread row sums into sums[0 .. 2P)
+// phase 1 (while the chunk's values are live): per-thread shifted row sums into sums[0 .. 2P), shifts into ks[0 .. P)
 template <int P>
-__device__ __forceinline__ void gn_row_sums(const float (&v)[32], bool valid, float (&sums)[16]) {
-  float vals[2 * P];
-  row_sums<P>(v, valid, vals);
+__device__ __forceinline__ void gn_row_sums(const float (&v)[32], bool valid, float (&sums)[16], float (&ks)[8]) {
+  float vals[2 * P], kk[P];
+  row_sums<P>(v, valid, vals, kk);
 #pragma unroll
   for (int i = 0; i < 2 * P; ++i) sums[i] = vals[i];
+#pragma unroll
+  for (int i = 0; i < P; ++i) ks[i] = kk[i];
 }
 // phase 2 (after the chunk's store has been issued): fold over the warp's 32 rows and park the warp's partials
 template <int P>
-__device__ __forceinline__ void gn_chunk_reduce(const float (&sums)[16], int lane, float2* redw) {
+__device__ __forceinline__ void gn_chunk_reduce(const float (&sums)[16], const float (&ks)[8], int lane, float2* redw,
+                                                float* redkw) {
   float vals[2 * P];
 #pragma unroll
   for (int i = 0; i < 2 * P; ++i) vals[i] = sums[i];
@@ -192,7 +210,11 @@ __device__ __forceinline__ void gn_chunk_reduce(const float (&sums)[16], int lan
     float* f = reinterpret_cast<float*>(redw);
     f[idx] = r;  // redw[i] = (sum_i, sumsq_i)  <->  flat index 2*i (+1)
   }
-}  // one staging buffer: 128 rows x 32 fp32 columns, 128B-swizzled
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < P; ++i) redkw[i] = ks[i];  // (uniform across the warp)
+  }
+}
 
 constexpr int kSlabABytes = 17 * 1024;  // (128 + 2) slab rows x 128 B = 16640, padded to the 1024-byte swizzle-atom pitch
 
@@ -226,9 +248,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   EpiVectors vec_s;
   vec_s.mul = reinterpret_cast<float*>(smem_s + (size_t)p.n_staging * kStagingBytes);
   vec_s.add = vec_s.mul + p.block_n;
-  vec_s.red = reinterpret_cast<float2(*)[kEpiGroups][kMaxGroupChunks][4][8]>(vec_s.add + p.block_n);
+  vec_s.nchg = red_chunks_per_group(p.block_n) > 0 ? red_chunks_per_group(p.block_n) : 1;
+  vec_s.red = reinterpret_cast<float2*>(vec_s.add + p.block_n);
+  vec_s.redk = reinterpret_cast<float*>(vec_s.red + 2 * kEpiGroups * vec_s.nchg * 4 * 8);
+  vec_s.rows = reinterpret_cast<int*>(vec_s.redk + 2 * kEpiGroups * vec_s.nchg * 4 * 8);
   const EpiVectors* vec = &vec_s;
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(reinterpret_cast<uint8_t*>(vec_s.red) + kRedBytes);
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(reinterpret_cast<uint8_t*>(vec_s.red) + (red_bytes(p.block_n) + 63) / 64 * 64);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -492,7 +517,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           named_bar_sync(kEpiGroups + 1, 128 * kEpiGroups);
           cached_key = key;
         }
-        float2 (*red_t)[4][8] = vec->red[it & 1][eg];  // [chunk of this group][warp][pair]
+        const int red_par = it & 1;
+        if (ep.gn_partial) {
+          const unsigned vm = __ballot_sync(0xffffffffu, valid);
+          if (lane == 0) vec->rows[(red_par * kEpiGroups + eg) * 4 + quarter] = __popc(vm);
+        }
         [[maybe_unused]] const bool tr = blockIdx.x == 0 && ew == 0 && lane == 0;  // traced warp (debug builds)
         CLPK_TRACE(tr, 100);
         mbar_wait(&bars->tmem_full[as], aphase);
@@ -502,7 +531,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int c = 32 * eg; c < p.block_n; c += cstep, ++ci) {
           uint8_t* sbuf = wslots + (size_t)slot * kWarpSlotBytes;
           uint32_t r[32];
-          float gsums[16];
+          float gsums[16], gks[8];
           __syncwarp();
           tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
           tmem_ld16(taddr + (uint32_t)c + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
@@ -552,10 +581,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (ep.gn_partial && !(CLPK_DBG(32))) {
               // per-thread (sum, sumsq) of this row's 32 values split by consumer-GroupNorm group; the cross-lane fold
               // happens after the chunk's store has been issued (it is off the store's critical path)
-              if (cpg >= 32) gn_row_sums<1>(v, valid, gsums);
-              else if (cpg == 16) gn_row_sums<2>(v, valid, gsums);
-              else if (cpg == 8) gn_row_sums<4>(v, valid, gsums);
-              else gn_row_sums<8>(v, valid, gsums);
+              if (cpg >= 32) gn_row_sums<1>(v, valid, gsums, gks);
+              else if (cpg == 16) gn_row_sums<2>(v, valid, gsums, gks);
+              else if (cpg == 8) gn_row_sums<4>(v, valid, gsums, gks);
+              else gn_row_sums<8>(v, valid, gsums, gks);
             }
             if (st_f32) {
 #pragma unroll
@@ -605,11 +634,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             // fold the row sums over the warp's 32 rows; the owning lanes park the warp's partials for the fixed-order
             // 4-warp fold at the end of the tile
             __syncwarp();
-            float2* redw = red_t[ci][quarter];
-            if (cpg >= 32) gn_chunk_reduce<1>(gsums, lane, redw);
-            else if (cpg == 16) gn_chunk_reduce<2>(gsums, lane, redw);
-            else if (cpg == 8) gn_chunk_reduce<4>(gsums, lane, redw);
-            else gn_chunk_reduce<8>(gsums, lane, redw);
+            const int ri = vec->idx(red_par, eg, ci, quarter);
+            float2* redw = vec->red + ri;
+            float* redkw = vec->redk + ri;
+            if (cpg >= 32) gn_chunk_reduce<1>(gsums, gks, lane, redw, redkw);
+            else if (cpg == 16) gn_chunk_reduce<2>(gsums, gks, lane, redw, redkw);
+            else if (cpg == 8) gn_chunk_reduce<4>(gsums, gks, lane, redw, redkw);
+            else gn_chunk_reduce<8>(gsums, gks, lane, redw, redkw);
           }
           CLPK_TRACE(tr, 108);
         }
@@ -629,15 +660,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const int nch = (p.block_n - 32 * eg + cstep - 1) / cstep;
           if (gtid < nch * npairs && tc.ok) {
             const int fci = gtid / npairs, pr = gtid - fci * npairs;
-            const float2* rr = &red_t[fci][0][pr];
-            float2 acc = rr[0];
+            // re-base the 4 warps' shifted sums on warp 0's K (exact algebra, fixed order), then the tile's triple
+            const int r0 = vec->idx(red_par, eg, fci, 0) + pr;
+            const int* rw = vec->rows + (red_par * kEpiGroups + eg) * 4;
+            const float cnt = (float)(cpg >= 32 ? 32 : cpg);  // channels behind one partial of this chunk
+            const float k0 = vec->redk[r0];
+            float s1 = 0.f, s2 = 0.f, n = 0.f;
 #pragma unroll
-            for (int wq = 1; wq < 4; ++wq) { acc.x += rr[wq * 8].x; acc.y += rr[wq * 8].y; }  // fixed order
+            for (int wq = 0; wq < 4; ++wq) {
+              const float2 a = vec->red[r0 + wq * 8];
+              const float d = vec->redk[r0 + wq * 8] - k0;
+              const float nw = (float)rw[wq] * cnt;
+              s1 += fmaf(nw, d, a.x);
+              s2 += fmaf(nw * d, d, fmaf(2.f * d, a.x, a.y));
+              n += nw;
+            }
+            const float inv_n = 1.0f / n;
+            const float mean = fmaf(s1, inv_n, k0);
+            const float m2 = fmaxf(fmaf(-s1 * inv_n, s1, s2), 0.f);
             const int ch = tc.n0 + 32 * eg + cstep * fci;
             const int g = (cpg >= 32) ? ch / cpg : ch / cpg + pr;
             const int mtile = (tc.phase * p.tiles_h + tc.h0 / p.hbox) * p.tiles_w + tc.w0 / p.wbox;
             const int slotg = mtile * p.gn_sub + ((cpg >= 32) ? (ch % cpg) / 32 : 0);
-            reinterpret_cast<float2*>(ep.gn_partial)[((long long)tc.b * p.gn_slots + slotg) * p.gn_groups + g] = acc;
+            reinterpret_cast<float4*>(ep.gn_partial)[((long long)tc.b * p.gn_slots + slotg) * p.gn_groups + g] =
+                make_float4(mean, m2, n, 0.f);
           }
         }
         CLPK_TRACE(tr, 109);
@@ -1049,20 +1095,25 @@ static cudaError_t set_smem_attr() {
   return cudaFuncSetAttribute(conv_igemm_kernel<BK, NC, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
 }
 
+// function attributes are per device (context): set them once for every device this process launches on
 int igemm_init() {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = set_smem_attr<64, 1>();
-    if (attr_err == cudaSuccess) attr_err = set_smem_attr<32, 1>();
-    if (attr_err == cudaSuccess) attr_err = set_smem_attr<128, 1>();
-    if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2>();
-    if (attr_err == cudaSuccess) attr_err = set_smem_attr<32, 2>();
-    if (attr_err == cudaSuccess) attr_err = set_smem_attr<128, 2>();
-    if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2, true>();
-    if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 1, true>();
-  });
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  CLPK_CHECK_CUDA(cudaGetDevice(&dev));
+  CLPK_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (done[dev]) return CLPK_OK;
+  cudaError_t attr_err = set_smem_attr<64, 1>();
+  if (attr_err == cudaSuccess) attr_err = set_smem_attr<32, 1>();
+  if (attr_err == cudaSuccess) attr_err = set_smem_attr<128, 1>();
+  if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2>();
+  if (attr_err == cudaSuccess) attr_err = set_smem_attr<32, 2>();
+  if (attr_err == cudaSuccess) attr_err = set_smem_attr<128, 2>();
+  if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2, true>();
+  if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 1, true>();
   CLPK_CHECK_CUDA(attr_err);
+  done[dev] = true;
   return CLPK_OK;
 }
 

@@ -28,12 +28,16 @@ bool pdl_enabled() {
   return on;
 }
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
 int num_sms() {
-  static int sms = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev < 0 || dev >= 64) dev = 0;
+  int sms = cache[dev].load(std::memory_order_relaxed);
   if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    cache[dev].store(sms, std::memory_order_relaxed);
   }
   return sms;
 }

@@ -52,9 +52,14 @@ gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float
 #pragma unroll
     for (int j = 0; j < J; ++j) q[j] = tid + j * T;
   }
-  float s[J], ss[J];
+  // SHIFTED sums (robust against |mean| >> std): every thread subtracts K[g] = the image's first element of its
+  // quad's group — one value per (image, group), identical in every block, so partials add up without re-basing
+  float s[J], ss[J], kq[J];
 #pragma unroll
-  for (int j = 0; j < J; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+  for (int j = 0; j < J; ++j) {
+    s[j] = 0.f; ss[j] = 0.f;
+    kq[j] = (q[j] < qc) ? __ldg(x + (long long)b * hw * c + ((q[j] * 4) / cpg) * cpg) : 0.f;
+  }
   const int p0 = chunk * pix_per_chunk;
   const int p1 = min(hw, p0 + pix_per_chunk);
   const float4* xb = reinterpret_cast<const float4*>(x) + (long long)b * hw * qc;
@@ -69,8 +74,9 @@ gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float
         for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + (long long)(p + u * ppb) * qc + q[j]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          s[j] += (v[u].x + v[u].y) + (v[u].z + v[u].w);
-          ss[j] += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w);
+          const float a0 = v[u].x - kq[j], a1 = v[u].y - kq[j], a2 = v[u].z - kq[j], a3 = v[u].w - kq[j];
+          s[j] += (a0 + a1) + (a2 + a3);
+          ss[j] += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
         }
       }
     }
@@ -80,8 +86,9 @@ gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float
     for (int j = 0; j < J; ++j) {
       if (q[j] < qc) {
         const float4 v = __ldg(xb + (long long)p * qc + q[j]);
-        s[j] += (v.x + v.y) + (v.z + v.w);
-        ss[j] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        const float a0 = v.x - kq[j], a1 = v.y - kq[j], a2 = v.z - kq[j], a3 = v.w - kq[j];
+        s[j] += (a0 + a1) + (a2 + a3);
+        ss[j] += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
       }
     }
   }
@@ -124,10 +131,11 @@ gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float
       }
       if (lane == 0) {
         const double n = (double)hw * (double)cpg;
-        const double mean = S / n;
-        double var = SS / n - mean * mean;
+        const double dm = S / n;  // mean - K
+        double var = SS / n - dm * dm;
         if (var < 0.0) var = 0.0;
-        stats[(long long)b * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+        const double k = (double)__ldg(x + (long long)b * hw * c + g * cpg);
+        stats[(long long)b * groups + g] = make_float2((float)(k + dm), (float)(1.0 / sqrt(var + (double)eps)));
       }
     }
     if (tid == 0) counter[b] = 0;  // ready for the next launch / graph replay
@@ -207,10 +215,40 @@ __device__ __forceinline__ void gn_affine8(const float* __restrict__ gamma, cons
   }
 }
 
+
+// Folds the per-tile (mean, M2, n) triples a conv epilogue wrote (conv_igemm.cu, "Fused GroupNorm statistics") into
+// (mean, rstd) of group g of image b; executed by one whole warp (lanes stride over the entries, fixed-order fp64 shuffle
+// tree -> deterministic).  partial[b][slot][piece]: `pieces` triples per slot, group g owns pieces [g*m, (g+1)*m),
+// m = pieces / groups (m > 1: group sizes such as 24 or 48 that the epilogue sums in 8- or 16-channel pieces).
+// Combination (Chan et al.): N = sum n, mean = sum(n*mean_i) / N, M2 = sum M2_i + sum n_i*mean_i^2 - N*mean^2, all fp64.
+__device__ __forceinline__ float2 gn_fold_partials(const float4* __restrict__ partial, int b, int g, int slots, int pieces,
+                                                   int groups, float eps, int lane) {
+  const int m = pieces / groups;
+  const float4* pp = partial + (long long)b * slots * pieces + g * m;
+  double A = 0.0, Q = 0.0, M = 0.0, N = 0.0;
+  for (int k = lane; k < slots * m; k += 32) {
+    const int slot = k / m, j = k - slot * m;
+    const float4 v = __ldg(pp + (long long)slot * pieces + j);
+    const double n = (double)v.z, mu = (double)v.x;
+    A += n * mu; Q += n * mu * mu; M += (double)v.y; N += n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    A += __shfl_xor_sync(0xffffffffu, A, o);
+    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+    M += __shfl_xor_sync(0xffffffffu, M, o);
+    N += __shfl_xor_sync(0xffffffffu, N, o);
+  }
+  const double mean = A / N;
+  double var = (M + (Q - N * mean * mean)) / N;
+  if (var < 0.0) var = 0.0;
+  return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
 template <bool kIn16, bool kHoist>
 __global__ void __launch_bounds__(kGnThreads, 4)
 gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float2* __restrict__ stats, const float2* __restrict__ partial, int slots, int pieces, double n_per_group,
+                const float2* __restrict__ stats, const float4* __restrict__ partial, int slots, int pieces, double n_per_group,
                 float eps, uint16_t* __restrict__ y, int hw, int c, int groups, int silu, int op_f16) {
   __shared__ float2 st_s[32];
   pdl_prologue_done();
@@ -219,28 +257,8 @@ gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, c
   if (partial) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int g = warp; g < groups; g += kGnThreads / 32) {
-      // partial[b][slot][piece]: `pieces` partial sums per slot, group g owns pieces [g*m, (g+1)*m), m = pieces / groups
-      // (m = 1: one partial per group; m > 1: group sizes such as 24 or 48 that the conv epilogue can only sum in 8- or
-      // 16-channel pieces)
-      const int m = pieces / groups;
-      const float2* pp = partial + (long long)b * slots * pieces + g * m;
-      double S = 0.0, SS = 0.0;
-      for (int k = lane; k < slots * m; k += 32) {
-        const int slot = k / m, j = k - slot * m;
-        const float2 v = __ldg(pp + (long long)slot * pieces + j);
-        S += (double)v.x; SS += (double)v.y;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        S += __shfl_xor_sync(0xffffffffu, S, o);
-        SS += __shfl_xor_sync(0xffffffffu, SS, o);
-      }
-      if (lane == 0) {
-        const double mean = S / n_per_group;
-        double var = SS / n_per_group - mean * mean;
-        if (var < 0.0) var = 0.0;
-        st_s[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
-      }
+      const float2 st = gn_fold_partials(partial, b, g, slots, pieces, groups, eps, lane);
+      if (lane == 0) st_s[g] = st;
     }
   } else {
     if (threadIdx.x < groups) st_s[threadIdx.x] = stats[(long long)b * groups + threadIdx.x];
@@ -277,41 +295,26 @@ gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, c
 
 // Folds per-tile partial sums produced by a conv epilogue: partial[b][slots][groups] (sum, sum of squares) ->
 // stats[b][g] = (mean, rstd).  One warp per (image, group); lanes stride over the slots, fp64 shuffle tree: deterministic.
-__global__ void gn_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stats, int slots, int groups,
-                                   double n_per_group, float eps) {
+__global__ void gn_finalize_kernel(const float4* __restrict__ partial, float2* __restrict__ stats, int slots, int groups,
+                                   float eps) {
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= groups) return;
-  const float2* pp = partial + (long long)b * slots * groups + g;
-  double S = 0.0, SS = 0.0;
-  for (int k = lane; k < slots; k += 32) {
-    const float2 v = __ldg(pp + (long long)k * groups);
-    S += (double)v.x; SS += (double)v.y;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    S += __shfl_xor_sync(0xffffffffu, S, o);
-    SS += __shfl_xor_sync(0xffffffffu, SS, o);
-  }
-  if (lane == 0) {
-    const double mean = S / n_per_group;
-    double var = SS / n_per_group - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[(long long)b * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
-  }
+  const float2 st = gn_fold_partials(partial, b, g, slots, groups, groups, eps, lane);
+  if (lane == 0) stats[(long long)b * groups + g] = st;
 }
 
-int launch_gn_finalize(const float2* partial, float2* stats, int batch, int slots, int groups, double n_per_group,
-                       float eps, cudaStream_t stream) {
+int launch_gn_finalize(const float4* partial, float2* stats, int batch, int slots, int groups, float eps,
+                       cudaStream_t stream) {
   CLPK_REQUIRE(groups <= 32, "GroupNorm finalize supports <= 32 groups");
-  gn_finalize_kernel<<<batch, 32 * groups, 0, stream>>>(partial, stats, slots, groups, n_per_group, eps);
+  gn_finalize_kernel<<<batch, 32 * groups, 0, stream>>>(partial, stats, slots, groups, eps);
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }
 
 // x: fp32 NHWC (x_is_16 == 0) or 16-bit NHWC in the operand format.  Exactly one of stats / partial is used.
 int launch_gn_apply_ex(const void* x, int x_is_16, const float* gamma, const float* beta, const float2* stats,
-                       const float2* partial, int slots, int pieces, double n_per_group, float eps, void* y_op,
+                       const float4* partial, int slots, int pieces, double n_per_group, float eps, void* y_op,
                        const GnShape& s,
                        int silu, int op_dtype, cudaStream_t stream) {
   const long long octs = (long long)s.hw * (s.c / 8);
@@ -408,8 +411,8 @@ extern "C" int clpk_groupnorm_finalize(const void* partial, void* stats, int bat
                                        double n_per_group, float eps, void* stream) {
   CLPK_REQUIRE(partial && stats && batch > 0 && slots > 0 && groups > 0 && n_per_group > 0,
                "clpk_groupnorm_finalize: bad arguments");
-  return launch_gn_finalize(reinterpret_cast<const float2*>(partial), reinterpret_cast<float2*>(stats), batch, slots,
-                            groups, n_per_group, eps, (cudaStream_t)stream);
+  return launch_gn_finalize(reinterpret_cast<const float4*>(partial), reinterpret_cast<float2*>(stats), batch, slots,
+                            groups, eps, (cudaStream_t)stream);
 }
 
 extern "C" int clpk_groupnorm_apply(const float* x, const float* gamma, const float* beta, const void* stats, void* y,

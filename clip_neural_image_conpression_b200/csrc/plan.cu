@@ -36,7 +36,7 @@ struct GnPlan {
   int level = 0, silu = 1;
   float *gamma = nullptr, *beta = nullptr;
   float2* stats = nullptr;    // [B][groups] (mean, rstd)
-  float2* partial = nullptr;  // [B][slots][groups] (sum, sumsq) written by the producer conv
+  float4* partial = nullptr;  // [B][slots][pieces] (mean, M2, n, -) per tile, written by the producer conv
   int slots = 0;
   int piece = 0, pieces = 0;  // channels per partial sum the producer epilogue emits, and their number (C / piece)
   bool fused = false;
@@ -55,8 +55,19 @@ struct ResBlockPlan {
 
 using namespace clpk;
 
+// makes `dev` current for the lifetime of the guard (plan calls run on the plan's device whatever the caller's is)
+struct DevGuard {
+  int prev = -1;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct clpk_plan {
   clpk_unet_config cfg;
+  int device = 0;            // CUDA device the plan's memory, tensor maps and graph belong to
   int B = 0, H = 0, W = 0;
   int n_levels = 0;
   std::vector<int> lv_c, lv_h, lv_w;  // size n_levels + 1
@@ -88,6 +99,7 @@ struct clpk_plan {
   int launches_fwd = 0;
   // DDIM state
   int steps = 0;
+  int tab_cap = 0;           // steps ht_tab / coef_tab are sized for
   float *ht_tab = nullptr, *coef_tab = nullptr;
   DdimRun* run_dev = nullptr;
   bool any_sigma = false;
@@ -314,11 +326,14 @@ int film_from_h(clpk_plan* P, cudaStream_t s) {
 
 extern "C" void clpk_plan_destroy(clpk_plan* P) {
   if (!P) return;
+  DevGuard dg(P->device);
   if (P->graph_exec) cudaGraphExecDestroy(P->graph_exec);
   if (P->graph) cudaGraphDestroy(P->graph);
   if (P->cap_stream) cudaStreamDestroy(P->cap_stream);
   for (cudaEvent_t e : P->prof_ev) cudaEventDestroy(e);
   for (void* q : P->allocs) cudaFree(q);
+  if (P->ht_tab) cudaFree(P->ht_tab);
+  if (P->coef_tab) cudaFree(P->coef_tab);
   delete P;
 }
 
@@ -346,6 +361,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     ~Guard() { if (p) clpk_plan_destroy(p); }
   } guard{P};
   P->cfg = *cfg;
+  CLPK_CHECK_CUDA(cudaGetDevice(&P->device));
   P->B = batch; P->H = height; P->W = width;
   P->n_levels = cfg->n_levels;
   const int td = cfg->time_dim, L = cfg->n_levels;
@@ -402,7 +418,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     CLPK_TRY(P->alloc(&x16, n));
     P->X16.push_back(x16);
   }
-  P->x16_gn = getenv("CLPK_X16") != nullptr;
+  { const char* e = getenv("CLPK_X16"); P->x16_gn = e && atoi(e) != 0; }
   CLPK_TRY(P->alloc(&P->Y, max_act));
   CLPK_TRY(P->alloc(&P->Yf, max_act));
   CLPK_TRY(P->alloc(&P->T, max_act));
@@ -472,7 +488,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     e1.film_scale1p = P->film + rb.film_off;
     e1.film_shift = P->film + rb.film_off + rb.c;
     e1.film_stride = film_n;
-    rb.y16 = rb.gn2.fused && !getenv("CLPK_Y_FP32");
+    { const char* e = getenv("CLPK_Y_FP32"); rb.y16 = rb.gn2.fused && !(e && atoi(e) != 0); }
     if (rb.y16) e1.out_op = P->Y; else e1.out_f32 = P->Yf;
     e1.cout_valid = rb.c;
     wire_gn(&e1, &rb.gn2);
@@ -572,6 +588,7 @@ extern "C" int clpk_plan_launches_per_forward(const clpk_plan* P) { return P ? P
 extern "C" int clpk_unet_forward(clpk_plan* P, const float* x, const float* z, const int64_t* t, float* eps,
                                  void* stream) {
   CLPK_REQUIRE(P && x && z && t && eps, "clpk_unet_forward: null argument");
+  DevGuard dg(P->device);
   cudaStream_t s = (cudaStream_t)stream;
   const clpk_unet_config& c = P->cfg;
   const int td = c.time_dim;
@@ -600,25 +617,40 @@ static int ddim_step_body(clpk_plan* P, cudaStream_t s) {
 extern "C" int clpk_plan_prepare_ddim(clpk_plan* P, int steps, const int64_t* ts_host, const float* coef_host,
                                       int use_graph, void* stream) {
   CLPK_REQUIRE(P && steps > 0 && ts_host && coef_host, "clpk_plan_prepare_ddim: bad arguments");
+  DevGuard dg(P->device);
   cudaStream_t s = (cudaStream_t)stream;
   const int td = P->cfg.time_dim;
   if (P->graph_exec) { cudaGraphExecDestroy(P->graph_exec); P->graph_exec = nullptr; }
   if (P->graph) { cudaGraphDestroy(P->graph); P->graph = nullptr; }
-  // per-step tables (the time half of the conditioning is batch invariant: ddim.py:32 uses one t for the whole batch)
-  int64_t* ts_dev = nullptr;
-  float *temb = nullptr, *h1 = nullptr;
-  CLPK_TRY(P->alloc(&ts_dev, steps));
-  CLPK_TRY(P->alloc(&temb, (long long)steps * td));
-  CLPK_TRY(P->alloc(&h1, (long long)steps * 4 * td));
-  CLPK_TRY(P->alloc(&P->ht_tab, (long long)steps * td));
-  CLPK_TRY(P->alloc(&P->coef_tab, (long long)steps * 5));
+  P->steps = 0;  // not prepared until everything below (tables, capture, instantiate) has succeeded
+  // per-step tables (the time half of the conditioning is batch invariant: ddim.py:32 uses one t for the whole batch).
+  // ht_tab / coef_tab live in dedicated members and are re-allocated only when a run needs more steps; the
+  // temporaries are freed before returning.
+  struct Tmp {
+    void* p[3] = {nullptr, nullptr, nullptr};
+    ~Tmp() { for (void* q : p) if (q) cudaFree(q); }
+  } tmp;
+  CLPK_CHECK_CUDA(cudaMalloc(&tmp.p[0], (size_t)steps * sizeof(int64_t)));
+  CLPK_CHECK_CUDA(cudaMalloc(&tmp.p[1], (size_t)steps * td * sizeof(float)));
+  CLPK_CHECK_CUDA(cudaMalloc(&tmp.p[2], (size_t)steps * 4 * td * sizeof(float)));
+  int64_t* ts_dev = reinterpret_cast<int64_t*>(tmp.p[0]);
+  float* temb = reinterpret_cast<float*>(tmp.p[1]);
+  float* h1 = reinterpret_cast<float*>(tmp.p[2]);
+  if (steps > P->tab_cap) {
+    if (P->ht_tab) { cudaFree(P->ht_tab); P->ht_tab = nullptr; P->bytes -= (long long)P->tab_cap * td * 4; }
+    if (P->coef_tab) { cudaFree(P->coef_tab); P->coef_tab = nullptr; P->bytes -= (long long)P->tab_cap * 5 * 4; }
+    P->tab_cap = 0;
+    CLPK_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&P->ht_tab), (size_t)steps * td * sizeof(float)));
+    CLPK_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&P->coef_tab), (size_t)steps * 5 * sizeof(float)));
+    P->tab_cap = steps;
+    P->bytes += (long long)steps * (td + 5) * 4;
+  }
   CLPK_CHECK_CUDA(cudaMemcpyAsync(ts_dev, ts_host, (size_t)steps * sizeof(int64_t), cudaMemcpyHostToDevice, s));
   CLPK_CHECK_CUDA(cudaMemcpyAsync(P->coef_tab, coef_host, (size_t)steps * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
   CLPK_TRY(launch_timestep_embedding(ts_dev, temb, steps, td, 10000.f, s));
   CLPK_TRY(launch_linear(temb, P->tp0_w, P->tp0_b, nullptr, 0, h1, steps, 4 * td, td, 1, s));
   CLPK_TRY(launch_linear(h1, P->tp2_w, P->tp2_b, nullptr, 0, P->ht_tab, steps, td, 4 * td, 0, s));
   CLPK_CHECK_CUDA(cudaStreamSynchronize(s));
-  P->steps = steps;
   P->any_sigma = false;
   for (int i = 0; i < steps; ++i) P->any_sigma = P->any_sigma || (coef_host[i * 5 + 4] > 0.f);
   if (use_graph) {
@@ -634,6 +666,7 @@ extern "C" int clpk_plan_prepare_ddim(clpk_plan* P, int steps, const int64_t* ts
     P->graph = g;
     CLPK_CHECK_CUDA(cudaGraphInstantiate(&P->graph_exec, P->graph, 0));
   }
+  P->steps = steps;
   return CLPK_OK;
 }
 
@@ -644,6 +677,7 @@ extern "C" int clpk_ddim_sample(clpk_plan* P, const float* z, float* x, const fl
     set_error("clpk_ddim_sample: call clpk_plan_prepare_ddim first");
     return CLPK_ERR_STATE;
   }
+  DevGuard dg(P->device);
   cudaStream_t s = (cudaStream_t)stream;
   const clpk_unet_config& c = P->cfg;
   const long long n = (long long)P->B * c.img_ch * P->H * P->W;
@@ -687,6 +721,7 @@ extern "C" int clpk_plan_profile_steps(clpk_plan* P, int iters, float* ms_out6, 
     set_error("clpk_plan_profile_steps: call clpk_plan_prepare_ddim first");
     return CLPK_ERR_STATE;
   }
+  DevGuard dg(P->device);
   cudaStream_t s = (cudaStream_t)stream;
   for (int k = 0; k < 6; ++k) { ms_out6[k] = 0.f; count_out6[k] = 0; }
   DdimRun run{};

@@ -52,7 +52,11 @@ class DDIMSampler:
         self.sch = scheduler
         self.eta = eta
         self.use_graph = True      # CUDA-graph replay of the step (set False to launch kernels one by one)
-        self.seed = 0              # Philox seed of the in-kernel eta > 0 noise
+        # Philox key of the in-kernel eta > 0 noise.  None (default): every sample() call draws a fresh 63-bit key from
+        # torch's default generator, so the noise follows torch.manual_seed / --seed and differs between calls,
+        # micro-batches and ranks like the reference's torch.randn_like draws (ddim.py:44-45).  An int pins the key
+        # (reproducible tests).
+        self.seed = None
 
     @torch.no_grad()
     def sample(self, model, z_clip: torch.Tensor, shape: tuple, steps: int = 50, cfg_scale: float = 1.0,
@@ -79,8 +83,9 @@ class DDIMSampler:
             ts_arr = (C.c_int64 * steps)(*ts.tolist())
             cf = coef.reshape(-1).tolist()
             cf_arr = (C.c_float * len(cf))(*cf)
-            check(plan.lib.clpk_plan_prepare_ddim(plan.handle, steps, ts_arr, cf_arr, int(self.use_graph), stream_ptr()),
-                  "clpk_plan_prepare_ddim")
+            with torch.cuda.device(x.device):
+                check(plan.lib.clpk_plan_prepare_ddim(plan.handle, steps, ts_arr, cf_arr, int(self.use_graph), stream_ptr()),
+                      "clpk_plan_prepare_ddim")
             plan.ddim_key = key
         x = x.contiguous().clone()
         z = z_clip.contiguous().float()
@@ -89,8 +94,12 @@ class DDIMSampler:
         if trace is not None:
             eps_tr = torch.empty((steps,) + tuple(x.shape), dtype=torch.float32, device=x.device)
             x_tr = torch.empty_like(eps_tr)
-        check(plan.lib.clpk_ddim_sample(plan.handle, ptr(z), ptr(x), ptr(nz), int(self.seed) & (2 ** 64 - 1), ptr(eps_tr),
-                                        ptr(x_tr), stream_ptr()), "clpk_ddim_sample")
+        seed = self.seed
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 63 - 1, (1,), dtype=torch.int64).item()) if float(self.eta) > 0 else 0
+        with torch.cuda.device(x.device):
+            check(plan.lib.clpk_ddim_sample(plan.handle, ptr(z), ptr(x), ptr(nz), int(seed) & (2 ** 64 - 1), ptr(eps_tr),
+                                            ptr(x_tr), stream_ptr()), "clpk_ddim_sample")
         if trace is not None:
             trace["eps"], trace["x"] = eps_tr, x_tr
         return x

@@ -3,7 +3,7 @@
 Interface mirror of the reference's PKG/models/unet.py:22-106: `timestep_embedding(t, dim, max_period)`,
 `CLIPCondUNet(z_dim, base, ch_mult, time_dim, img_ch)` with the reference's parameter tree and
 `forward(x_t, z_clip, t) -> eps`.  The nn.Modules own the fp32 parameters; on the first CUDA call for a given
-(batch, H, W) a *plan* is built in C++ (bf16 K-major weight repack, NHWC workspaces, TMA descriptors, launch
+(batch, H, W) a *plan* is built in C++ (16-bit — fp16 default, bf16 selectable — K-major weight repack, NHWC workspaces, TMA descriptors, launch
 sequence) and cached.  CPU tensors are rejected: there is no fallback path.
 """
 from __future__ import annotations
@@ -37,13 +37,18 @@ class _Plan:
         cfg.time_dim, cfg.img_ch, cfg.groups = net.time_dim, net.img_ch, 8
         cfg.op_dtype = op_code(net.operand_dtype)
         sd = {k: v.detach().float().contiguous() for k, v in net.state_dict().items()}
+        devs = {v.device for v in sd.values()}
+        if len(devs) != 1 or next(iter(devs)).type != "cuda":
+            raise _lib.ClpkError("CLIPCondUNet parameters must live on ONE CUDA device")
+        self.device = next(iter(devs))
         names = (C.c_char_p * len(sd))(*[k.encode() for k in sd])
         ptrs = (C.c_void_p * len(sd))(*[v.data_ptr() for v in sd.values()])
         numels = (C.c_int64 * len(sd))(*[v.numel() for v in sd.values()])
         handle = C.c_void_p()
-        torch.cuda.current_stream().synchronize()
-        check(lib.clpk_plan_create(C.byref(cfg), batch, height, width, len(sd), names, ptrs, numels, C.byref(handle)),
-              "clpk_plan_create")
+        with torch.cuda.device(self.device):   # the plan's memory, tensor maps and graph belong to the weights' GPU
+            torch.cuda.current_stream().synchronize()
+            check(lib.clpk_plan_create(C.byref(cfg), batch, height, width, len(sd), names, ptrs, numels, C.byref(handle)),
+                  "clpk_plan_create")
         self.lib, self.handle = lib, handle
         self.batch, self.height, self.width = batch, height, width
         self.ddim_key = None
@@ -140,6 +145,7 @@ class CLIPCondUNet(nn.Module):
         z = z_clip.contiguous().float()
         tt = t.contiguous().to(torch.int64)
         eps = torch.empty_like(x)
-        check(plan.lib.clpk_unet_forward(plan.handle, ptr(x), ptr(z), ptr(tt), ptr(eps), stream_ptr()),
-              "clpk_unet_forward")
+        with torch.cuda.device(x.device):
+            check(plan.lib.clpk_unet_forward(plan.handle, ptr(x), ptr(z), ptr(tt), ptr(eps), stream_ptr()),
+                  "clpk_unet_forward")
         return eps

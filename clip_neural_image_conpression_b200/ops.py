@@ -11,7 +11,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import CONV_3X3_S1, CONV_3X3_S2, CONVT_4X4_S2, ConvEpilogue, check, op_code, ptr, require_cuda, stream_ptr
+from ._lib import (CONV_3X3_S1, CONV_3X3_S2, CONVT_4X4_S2, ConvEpilogue, check, on_tensor_device, op_code, ptr,
+                   require_cuda, stream_ptr)
 
 __all__ = [
     "dequant_l2norm", "quant_encode", "quant_fit", "ddim_step", "timestep_embedding", "linear", "film_apply",
@@ -24,6 +25,7 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous().float() if (t.dtype != torch.float32 or not t.is_contiguous()) else t
 
 
+@on_tensor_device
 def dequant_l2norm(q: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor, l2norm: bool = True,
                    return_raw: bool = False):
     """uint8 [B,D] -> fp32 [B,D]: q*scale+zero, then row L2 normalisation (reconstruct_diffusion.py:43-44)."""
@@ -38,6 +40,7 @@ def dequant_l2norm(q: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor, l2n
     return (z, raw) if return_raw else z
 
 
+@on_tensor_device
 def quant_encode(x: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor) -> torch.Tensor:
     require_cuda(x, scale, zero)
     x2 = _f32c(x).reshape(-1, x.shape[-1])
@@ -47,6 +50,7 @@ def quant_encode(x: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor) -> to
     return q.reshape(x.shape)
 
 
+@on_tensor_device
 def quant_fit(x: torch.Tensor):
     require_cuda(x)
     x = _f32c(x)
@@ -57,6 +61,7 @@ def quant_fit(x: torch.Tensor):
     return scale, zero
 
 
+@on_tensor_device
 def ddim_step(x: torch.Tensor, eps: torch.Tensor, coef, noise: torch.Tensor | None = None,
               out: torch.Tensor | None = None) -> torch.Tensor:
     """One DDIM update (ddim.py:36-45); coef = (sqrt(1-a_t), sqrt(a_t), sqrt(a_s), sqrt(a_s-sigma^2), sigma)."""
@@ -70,6 +75,7 @@ def ddim_step(x: torch.Tensor, eps: torch.Tensor, coef, noise: torch.Tensor | No
     return out
 
 
+@on_tensor_device
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     require_cuda(t)
     t = t.contiguous().to(torch.int64)
@@ -79,6 +85,7 @@ def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -
     return out
 
 
+@on_tensor_device
 def linear(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, act: int = 0,
            add: torch.Tensor | None = None) -> torch.Tensor:
     require_cuda(x, w)
@@ -93,6 +100,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, act: int = 
     return y
 
 
+@on_tensor_device
 def film_apply(x_nchw: torch.Tensor, scale1p: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
     require_cuda(x_nchw, scale1p, shift)
     x = _f32c(x_nchw)
@@ -104,6 +112,7 @@ def film_apply(x_nchw: torch.Tensor, scale1p: torch.Tensor, shift: torch.Tensor)
     return y
 
 
+@on_tensor_device
 def groupnorm_silu(x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float = 1e-5,
                    silu: bool = True, dtype: torch.dtype = torch.float16) -> torch.Tensor:
     """fp32 NHWC [B,H,W,C] -> 16-bit (fp16 default / bf16) NHWC GroupNorm(+SiLU) = the conv A operand."""
@@ -119,6 +128,7 @@ def groupnorm_silu(x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor
     return y
 
 
+@on_tensor_device
 def pack_conv_weight(w: torch.Tensor, kind: int, dtype: torch.dtype = torch.float16) -> torch.Tensor:
     """Reference-layout fp32 conv weight -> 16-bit K-major GEMM layout (see include/clpk.h)."""
     require_cuda(w)
@@ -169,6 +179,7 @@ def _conv_out_hw(kind: int, h: int, w: int):
     return h, w
 
 
+@on_tensor_device
 def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, bias: torch.Tensor, *,
                film_scale1p=None, film_shift=None, resid=None, want_f32=True, want_op=False, want_nchw=False,
                gn_groups: int = 0, impl: str = "igemm"):
@@ -192,7 +203,7 @@ def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout:
         slots = int(_lib.load().clpk_conv_gn_slots(kind, h, w, cout, cpg))
         if slots <= 0:
             raise ValueError(f"fused GroupNorm statistics unsupported for cout={cout}, groups={gn_groups}")
-        partial = torch.zeros((b, slots, gn_groups, 2), dtype=torch.float32, device=dev)
+        partial = torch.zeros((b, slots, gn_groups, 4), dtype=torch.float32, device=dev)
     _conv("clpk_conv_igemm" if impl == "igemm" else "clpk_conv_direct", x_nhwc_op, w_packed, kind, cout, bias,
           film_scale1p, film_shift, _f32c(resid) if resid is not None else None, outs.get("f32"), outs.get("op"),
           outs.get("nchw"), partial, cpg)
@@ -204,6 +215,7 @@ def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout:
     return outs
 
 
+@on_tensor_device
 def groupnorm_apply(x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, stats: torch.Tensor, groups: int,
                     silu: bool = True, dtype: torch.dtype = torch.float16) -> torch.Tensor:
     """Second half of GroupNorm(+SiLU) given (mean, rstd) [B, groups, 2] (e.g. from conv_igemm(gn_groups=...))."""
@@ -222,6 +234,7 @@ def conv_direct(*args, **kwargs):
     return conv_igemm(*args, impl="direct", **kwargs)
 
 
+@on_tensor_device
 def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """Stem conv (unet.py:55): fp32 NCHW -> fp32 NHWC."""
     require_cuda(x_nchw, w, b)
@@ -234,6 +247,7 @@ def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Ten
     return y
 
 
+@on_tensor_device
 def to_uint8_hwc(x_nchw: torch.Tensor) -> torch.Tensor:
     """clamp(-1,1) -> ((x+1)*127.5) truncated to uint8, HWC (reconstruct_diffusion.py:55-56)."""
     require_cuda(x_nchw)
@@ -244,6 +258,7 @@ def to_uint8_hwc(x_nchw: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@on_tensor_device
 def psnr_sqerr_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """Per-image sum of squared uint8-domain differences (metrics.py:16-26) as int64 [B]."""
     require_cuda(a, b)
@@ -256,6 +271,7 @@ def psnr_sqerr_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@on_tensor_device
 def ssim_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """Per-image SSIM (metrics.py:32-46, scikit-image defaults: 7x7 uniform window, uint8 domain, data_range 255) of two
     fp32 NCHW [B,C,H,W] tensors in [-1,1], as fp64 [B]."""
@@ -275,6 +291,7 @@ def ssim_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@on_tensor_device
 def ddpm_combine(x: torch.Tensor, y: torch.Tensor, ca: torch.Tensor, cb: torch.Tensor, cdiv: torch.Tensor | None = None,
                  clamp: bool = False) -> torch.Tensor:
     """out[b] = (ca[b]*x[b] + cb[b]*y[b]) [/ cdiv[b]] [clamp(-1, 1)] with every operation individually rounded — the DDPM

@@ -93,9 +93,11 @@ int clpk_groupnorm_silu(const float* x_nhwc_dev, const float* gamma_dev, const f
                         void* ws_dev, int batch, int hw, int c, int groups, float eps, int silu, int op_dtype,
                         void* stream);
 
-/* The two halves of clpk_groupnorm_silu for producers that already emitted partial sums (conv epilogue):
- * finalize: partial[b][slots][groups] float2 (sum, sumsq) -> stats[b][groups] float2 (mean, rstd), biased variance over
- * n_per_group elements; apply: y = (x - mean) * rstd * gamma + beta [SiLU] in the 16-bit operand format. */
+/* The two halves of clpk_groupnorm_silu for producers that already emitted per-tile statistics (conv epilogue):
+ * finalize: partial[b][slots][groups] float4 (tile mean, tile M2 = sum (x - mean)^2, tile element count n, unused) ->
+ * stats[b][groups] float2 (mean, rstd), biased variance, combined in fp64 with the parallel-variance formula (robust for
+ * |mean| >> std like torch's Welford pass; n_per_group is informational, the counts come from the triples);
+ * apply: y = (x - mean) * rstd * gamma + beta [SiLU] in the 16-bit operand format. */
 int clpk_groupnorm_finalize(const void* partial_dev, void* stats_dev, int batch, int slots, int groups,
                             double n_per_group, float eps, void* stream);
 int clpk_groupnorm_apply(const float* x_nhwc_dev, const float* gamma_dev, const float* beta_dev, const void* stats_dev,
@@ -129,9 +131,10 @@ typedef struct clpk_conv_epilogue {
   void* out_op;               /* dev NHWC 16-bit (op_dtype) or NULL */
   float* out_nchw;            /* dev NCHW fp32 or NULL            */
   int cout_valid;             /* channels really present (<= cout_pad) */
-  /* Fused GroupNorm statistics of the FINAL output values (after bias / FiLM / residual): per-tile partial sums
-   * gn_partial[b][slot][g] = (sum, sum of squares) as float2, slots = clpk_conv_gn_slots(...), g < cout / gn_cpg.
-   * Fold them with clpk_groupnorm_finalize.  NULL = off.  Needs out_f32 and gn_cpg in {4, 8, 16} or a multiple of 32. */
+  /* Fused GroupNorm statistics of the FINAL output values (after bias / FiLM / residual): per-tile triples
+   * gn_partial[b][slot][g] = float4 (mean, M2, n, -) accumulated as shifted sums in the epilogue, slots =
+   * clpk_conv_gn_slots(...), g < cout / gn_cpg.  Fold them with clpk_groupnorm_finalize.  NULL = off.
+   * Needs an NHWC output and gn_cpg in {4, 8, 16} or a multiple of 32. */
   void* gn_partial;
   int gn_cpg;
 } clpk_conv_epilogue;

@@ -168,8 +168,8 @@ def timestep_embedding(t: torch.Tensor, dim: int, max_period: int = 10000) -> to
     return emb
 
 
-def _resblock(sd, p: str, x: torch.Tensor, h: torch.Tensor, groups: int = 8) -> torch.Tensor:
-    """PKG/models/blocks.py:40-44 (+ FiLM :22-25)."""
+def _resblock(sd, p: str, x: torch.Tensor, h: torch.Tensor, groups: int = 8, taps: Optional[dict] = None) -> torch.Tensor:
+    """PKG/models/blocks.py:40-44 (+ FiLM :22-25).  `taps` (tests only) receives the conv1 + FiLM output as "<p>.y"."""
     c = x.shape[1]
     g = min(groups, c)
     y = F.conv2d(F.silu(F.group_norm(x, g, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], 1e-5)),
@@ -177,6 +177,8 @@ def _resblock(sd, p: str, x: torch.Tensor, h: torch.Tensor, groups: int = 8) -> 
     s = F.linear(h, sd[p + ".film.to_scale.weight"], sd[p + ".film.to_scale.bias"])[:, :, None, None]
     b = F.linear(h, sd[p + ".film.to_shift.weight"], sd[p + ".film.to_shift.bias"])[:, :, None, None]
     y = y * (1 + s) + b
+    if taps is not None:
+        taps[p + ".y"] = y
     y = F.conv2d(F.silu(F.group_norm(y, g, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], 1e-5)),
                  sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)
     return x + y
@@ -195,8 +197,8 @@ def unet_forward(sd: Dict[str, torch.Tensor], ch_mult: Sequence[int], x_t: torch
     skips = []
     n = len(ch_mult)
     for i in range(n):
-        x = _resblock(sd, f"down.{3 * i}", x, h)
-        x = _resblock(sd, f"down.{3 * i + 1}", x, h)
+        x = _resblock(sd, f"down.{3 * i}", x, h, taps=taps)
+        x = _resblock(sd, f"down.{3 * i + 1}", x, h, taps=taps)
         skips.append(x)
         x = F.conv2d(x, sd[f"down.{3 * i + 2}.weight"], sd[f"down.{3 * i + 2}.bias"], stride=2, padding=1)
     x = _resblock(sd, "mid1", x, h)

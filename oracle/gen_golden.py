@@ -85,8 +85,64 @@ def write_ddpm(R, out) -> None:
     np.savez_compressed(out / "ddpm.npz", **dd)
 
 
+DEFAULT = dict(z_dim=512, base=128, ch_mult=(1, 2, 2))          # BASELINE.json configs[1-3] architecture
+WIDE = dict(z_dim=768, base=192, ch_mult=(1, 2, 2, 4))          # BASELINE.json configs[4] architecture
+FULL_KEEP = (0, 1, 2, 25, 49)                                    # DDIM-50 steps recorded: t = 999, 978, 958, 489, 0
+
+
+def write_fullsize(R, out) -> None:
+    """Reference-CPU fixtures at the REAL sizes (tests/golden/fullsize_default.npz, fullsize_wide.npz):
+      * default UNet (base 128, (1,2,2)), 256 px, B = 1: the unmodified reference DDIMSampler.sample (ddim.py:21-46)
+        over all 50 steps with contractive `out.*` (x0.1); the model callable records (x_t, eps) at steps FULL_KEEP
+        (teacher-forced per-step parity at t = 999 / 978 / 958 / 489 / 0) and the final x (closed-loop >= 40 dB bar).
+        x_T and z are regenerated from their seeds by the tests, not stored.
+      * wide UNet (base 192, (1,2,2,4), z = 768), 128 px, B = 1: two forwards (t = 999, 123) of unet.py:81-106.
+    Weights: oracle.make_state_dict(seed) loaded into the reference module (strict)."""
+    torch.set_num_threads(8)
+    sch = R.sched.NoiseScheduler(1000, "cosine", "cpu")
+    net = ref_net(R, DEFAULT, seed=0, out_gain=0.1)
+    g = torch.Generator().manual_seed(5)
+    z = torch.nn.functional.normalize(torch.randn(1, 512, generator=g), dim=-1)
+    x_T = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(6))
+    rec, calls = {}, [0]
+
+    def model(x, zc, t):
+        i = calls[0]
+        calls[0] += 1
+        eps = net(x, zc, t)
+        if i in FULL_KEEP:
+            if i > 0:
+                rec[f"x{i}"] = x.detach().clone().numpy()
+            rec[f"eps{i}"] = eps.detach().clone().numpy()
+            rec[f"t{i}"] = t.numpy().copy()
+        return eps
+
+    xf = R.ddim.DDIMSampler(sch, 0.0).sample(model, z, (1, 3, 256, 256), steps=50, x_T=x_T)
+    assert calls[0] == 50
+    rec["x_final"] = xf.numpy()
+    rec["z_check"], rec["x_T_check"] = z.numpy(), x_T.numpy()[:, :, :2, :8]   # guards the seeds, not the payload
+    np.savez_compressed(out / "fullsize_default.npz", **rec)
+    del net
+
+    net = ref_net(R, WIDE, seed=31, out_gain=0.1)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 3, 128, 128, generator=g)
+    zw = torch.nn.functional.normalize(torch.randn(1, 768, generator=g), dim=-1)
+    wd = {}
+    with torch.no_grad():
+        for t in (999, 123):
+            wd[f"eps_t{t}"] = net(x, zw, torch.tensor([t])).numpy()
+    wd["z_check"], wd["x_check"] = zw.numpy(), x.numpy()[:, :, :2, :8]
+    np.savez_compressed(out / "fullsize_wide.npz", **wd)
+    for f in ("fullsize_default.npz", "fullsize_wide.npz"):
+        print(f, (out / f).stat().st_size // 1024, "KiB")
+
+
 def main() -> None:
     R = import_reference()
+    if "--only-fullsize" in sys.argv:   # adds the full-size fixtures without rewriting the others
+        write_fullsize(R, ROOT / "tests" / "golden")
+        return
     if "--only-ddpm" in sys.argv:   # adds the ddpm fixture without rewriting the others
         write_ddpm(R, ROOT / "tests" / "golden")
         return

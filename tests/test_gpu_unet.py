@@ -115,13 +115,22 @@ def test_ddim_stochastic_path_and_nan_pattern(oracle, golden):
     # eta = 1.0: the reference's sqrt(a_s - sigma^2) is NaN from step 0 on -> all-NaN output
     xn = _sampler(1.0).sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T, noise=noise)
     assert float(torch.isnan(xn).float().mean()) == float(g["pg.eta1.nan_fraction"]) == 1.0
-    # in-kernel Philox noise: finite, seed-reproducible, seed-sensitive
+    # in-kernel Philox noise.  Pinned key: finite, reproducible, key-sensitive.
     s = _sampler(1e-3)
+    s.seed = 0
     a = s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T)
     b = s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T)
     s.seed = 1
     c = s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T)
     assert torch.isfinite(a).all() and torch.equal(a, b) and not torch.equal(a, c)
+    # Default (seed None): a fresh key per call from torch's generator, like the reference's torch.randn_like draws
+    # (ddim.py:44-45) — calls differ, torch.manual_seed makes the sequence reproducible.
+    s = _sampler(1e-3)
+    torch.manual_seed(123)
+    d1, d2 = s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T), s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T)
+    torch.manual_seed(123)
+    d3 = s.sample(net, z, (2, 3, 64, 64), steps=10, x_T=x_T)
+    assert not torch.equal(d1, d2) and torch.equal(d1, d3)
 
 
 def test_ddim_teacher_forced_epsilon(oracle, golden):
