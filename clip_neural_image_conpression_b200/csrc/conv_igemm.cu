@@ -664,16 +664,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int r0 = vec->idx(red_par, eg, fci, 0) + pr;
             const int* rw = vec->rows + (red_par * kEpiGroups + eg) * 4;
             const float cnt = (float)(cpg >= 32 ? 32 : cpg);  // channels behind one partial of this chunk
-            const float k0 = vec->redk[r0];
-            float s1 = 0.f, s2 = 0.f, n = 0.f;
+            // (a warp without valid rows — tile rows beyond the TMA box — is skipped: its accumulator rows, hence its K,
+            //  are whatever the uninitialised part of the A stage produced)
+            float k0 = 0.f, s1 = 0.f, s2 = 0.f, n = 0.f;
+            bool have = false;
 #pragma unroll
             for (int wq = 0; wq < 4; ++wq) {
-              const float2 a = vec->red[r0 + wq * 8];
-              const float d = vec->redk[r0 + wq * 8] - k0;
-              const float nw = (float)rw[wq] * cnt;
-              s1 += fmaf(nw, d, a.x);
-              s2 += fmaf(nw * d, d, fmaf(2.f * d, a.x, a.y));
-              n += nw;
+              if (rw[wq] > 0) {
+                const float2 a = vec->red[r0 + wq * 8];
+                const float kw = vec->redk[r0 + wq * 8];
+                if (!have) { k0 = kw; have = true; }
+                const float d = kw - k0;
+                const float nw = (float)rw[wq] * cnt;
+                s1 += fmaf(nw, d, a.x);
+                s2 += fmaf(nw * d, d, fmaf(2.f * d, a.x, a.y));
+                n += nw;
+              }
             }
             const float inv_n = 1.0f / n;
             const float mean = fmaf(s1, inv_n, k0);

@@ -217,20 +217,24 @@ __device__ __forceinline__ void gn_affine8(const float* __restrict__ gamma, cons
 
 
 // Folds the per-tile (mean, M2, n) triples a conv epilogue wrote (conv_igemm.cu, "Fused GroupNorm statistics") into
-// (mean, rstd) of group g of image b; executed by one whole warp (lanes stride over the entries, fixed-order fp64 shuffle
+// (mean, rstd) of group g of image b; executed by one whole warp (lanes stride over the entries, fixed-order shuffle
 // tree -> deterministic).  partial[b][slot][piece]: `pieces` triples per slot, group g owns pieces [g*m, (g+1)*m),
 // m = pieces / groups (m > 1: group sizes such as 24 or 48 that the epilogue sums in 8- or 16-channel pieces).
-// Combination (Chan et al.): N = sum n, mean = sum(n*mean_i) / N, M2 = sum M2_i + sum n_i*mean_i^2 - N*mean^2, all fp64.
+// Combination (Chan et al.) relative to the FIRST triple's mean m0, so every accumulated term is of the order of the
+// spread of the tile means (fp32 is ample; fp64 would cost ~7 DFMA-class ops per entry in every block's prologue):
+//   N = sum n, A = sum n (mean_i - m0), Q = sum n (mean_i - m0)^2, M = sum M2_i
+//   mean = m0 + A / N,   var = (M + Q - A^2 / N) / N      (final scalar arithmetic in fp64)
 __device__ __forceinline__ float2 gn_fold_partials(const float4* __restrict__ partial, int b, int g, int slots, int pieces,
                                                    int groups, float eps, int lane) {
   const int m = pieces / groups;
   const float4* pp = partial + (long long)b * slots * pieces + g * m;
-  double A = 0.0, Q = 0.0, M = 0.0, N = 0.0;
+  const float m0 = __ldg(pp).x;
+  float A = 0.f, Q = 0.f, M = 0.f, N = 0.f;
   for (int k = lane; k < slots * m; k += 32) {
     const int slot = k / m, j = k - slot * m;
     const float4 v = __ldg(pp + (long long)slot * pieces + j);
-    const double n = (double)v.z, mu = (double)v.x;
-    A += n * mu; Q += n * mu * mu; M += (double)v.y; N += n;
+    const float d = v.x - m0, nd = v.z * d;
+    A += nd; Q = fmaf(nd, d, Q); M += v.y; N += v.z;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -239,8 +243,9 @@ __device__ __forceinline__ float2 gn_fold_partials(const float4* __restrict__ pa
     M += __shfl_xor_sync(0xffffffffu, M, o);
     N += __shfl_xor_sync(0xffffffffu, N, o);
   }
-  const double mean = A / N;
-  double var = (M + (Q - N * mean * mean)) / N;
+  const double n = (double)N, a = (double)A;
+  const double mean = (double)m0 + a / n;
+  double var = ((double)M + ((double)Q - a * a / n)) / n;
   if (var < 0.0) var = 0.0;
   return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
 }
