@@ -39,6 +39,9 @@ class ConvEpilogue(C.Structure):
         ("cout_valid", C.c_int),
         ("gn_partial", C.c_void_p),
         ("gn_cpg", C.c_int),
+        ("in_scale", C.c_void_p),
+        ("in_shift", C.c_void_p),
+        ("in_silu", C.c_int),
     ]
 
 
@@ -74,6 +77,8 @@ SIGNATURES = {
     "clpk_groupnorm_finalize": (_i, [_vp, _vp, _i, _i, _i, C.c_double, _f, _vp]),
     "clpk_groupnorm_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "clpk_conv_gn_slots": (_i, [_i, _i, _i, _i, _i]),
+    "clpk_conv_in_affine_supported": (_i, [_i, _i, _i, _i, _i]),
+    "clpk_groupnorm_affine": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "clpk_pack_conv_weight": (_i64, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "clpk_conv_igemm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
     "clpk_conv_direct": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
@@ -112,8 +117,10 @@ def load() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
+        import os
+        override = os.environ.get("CLPK_LIB")   # A/B experiments only: another build of the SAME library (tools/ab/)
         try:
-            path = _build.build()
+            path = Path(override) if override else _build.build()
         except Exception as e:  # noqa: BLE001 — surfaced verbatim: there is nothing to fall back to
             raise ClpkError(f"libclpk.so is unavailable and could not be built: {e}") from e
         lib = C.CDLL(str(path))

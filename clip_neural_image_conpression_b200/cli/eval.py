@@ -61,7 +61,7 @@ def main(argv=None) -> None:
     device = torch.device(args.device if world == 1 else f"cuda:{local}")
     if device.type != "cuda":
         raise SystemExit("this decoder runs on CUDA (sm_100a) only; there is no CPU path")
-    torch.cuda.set_device(device)   # --device cuda:N is honoured (single process); under torchrun: cuda:LOCAL_RANK
+    torch.cuda.set_device(device if device.index is not None else torch.cuda.current_device())   # --device cuda:N is honoured (single process); under torchrun: cuda:LOCAL_RANK
     if args.seed is not None:
         torch.manual_seed(args.seed + rank)
     store = Path(args.store_dir)

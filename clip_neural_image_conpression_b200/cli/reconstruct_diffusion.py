@@ -54,7 +54,7 @@ def main(argv=None) -> None:
     device = torch.device(args.device)
     if device.type != "cuda":
         raise SystemExit("this decoder runs on CUDA (sm_100a) only; there is no CPU path")
-    torch.cuda.set_device(device)   # --device cuda:N: streams, plan memory and kernels all on that GPU
+    torch.cuda.set_device(device if device.index is not None else torch.cuda.current_device())   # --device cuda:N: streams, plan memory and kernels all on that GPU
     if args.seed is not None:
         torch.manual_seed(args.seed)
     scale, zero = load_store_meta(Path(args.store_dir), device)

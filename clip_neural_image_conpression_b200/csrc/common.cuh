@@ -197,6 +197,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Release at cluster scope: publishes this thread's (fenced) shared-memory writes to the waiter in the peer CTA.
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // CTA-pair TMA loads: data lands in the issuing CTA's smem, the transaction bytes are signalled on `mbar_cluster_addr`
 // (the pair leader's barrier)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0,
@@ -322,6 +326,32 @@ __host__ __device__ inline uint32_t make_idesc_16bit(int m, int n, bool f16) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 — two fp32 lanes per instruction, each rounded like the scalar op) --
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // ---- misc math ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
@@ -349,6 +379,33 @@ __device__ __forceinline__ uint16_t to_op(float v, bool f16) {
 __device__ __forceinline__ float from_op(uint16_t raw, bool f16) {
   if (f16) return __half2float(*reinterpret_cast<const __half*>(&raw));
   return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&raw));
+}
+
+// GroupNorm apply [+ SiLU] of 8 packed 16-bit values: r = v * sc + sh (one FMA, (scale, shift) = (rstd*gamma,
+// beta - mean*rstd*gamma)), SiLU as ONE MUFU op per element: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+__device__ __forceinline__ uint4 affine_act8(const uint4& a, const float (&sc)[8], const float (&sh)[8], bool silu, bool f16) {
+  const uint32_t w4[4] = {a.x, a.y, a.z, a.w};
+  float r[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    r[2 * k] = fmaf(from_op((uint16_t)(w4[k] & 0xffffu), f16), sc[2 * k], sh[2 * k]);
+    r[2 * k + 1] = fmaf(from_op((uint16_t)(w4[k] >> 16), f16), sc[2 * k + 1], sh[2 * k + 1]);
+  }
+  if (silu) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = silu_tanh(r[k]);
+  }
+  return make_uint4(pack_op2(r[0], r[1], f16), pack_op2(r[2], r[3], f16), pack_op2(r[4], r[5], f16),
+                    pack_op2(r[6], r[7], f16));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -31,6 +31,7 @@ namespace clpk {
 
 constexpr int kEpiGroups = 2;                       // epilogue warp groups (4 warps each) alternating 32-column chunks
 constexpr int kNumThreads = 64 + 128 * kEpiGroups;   // warp 0 TMA, warp 1 MMA, then the epilogue groups
+constexpr int kXformThreads = 128;                    // + 4 transform warps in the kXform variants (input GroupNorm fused)
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 232448;  // 227 KB
@@ -38,6 +39,7 @@ constexpr int kSmemBudget = 232448;  // 227 KB
 struct __align__(8) PipeBarriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
+  uint64_t ready[kMaxStages];   // kXform: the stage's A slab has been normalised in place (leader CTA's copy is waited on)
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t res_full[4 * kEpiGroups][4];  // per epilogue warp: residual sub-box landed in the warp's staging slot s
@@ -81,6 +83,7 @@ struct EpiVectors {       // laid out in smem as: float mul[block_n] | float add
   float2* red;    // [tile parity][epilogue group][chunk of the group][warp][group pair] shifted (sum, sumsq)
   float* redk;    // same indexing: the warp's shift K
   int* rows;      // [tile parity][epilogue group][warp] valid rows of the warp in this tile
+  float* xf_tab;  // kXform: (scale[cin] | shift[cin]) of the current image's input transform
   int nchg;       // chunks per epilogue group = ceil(block_n / 32 / kEpiGroups)
   __device__ __forceinline__ int idx(int parity, int eg, int ci, int warp) const {
     return (((parity * kEpiGroups + eg) * nchg + ci) * 4 + warp) * 8;
@@ -122,7 +125,9 @@ __device__ int g_trace_n;
 #define CLPK_TRACE(cond, tag) do { } while (0)
 #define CLPK_GTRACE(cond, tag) do { } while (0)
 #endif
-static inline int epi_vector_bytes(int block_n) { return 2 * 4 * block_n + (red_bytes(block_n) + 63) / 64 * 64; }
+static inline int epi_vector_bytes(int block_n, int xf_cin) {
+  return 2 * 4 * block_n + (red_bytes(block_n) + 63) / 64 * 64 + (2 * 4 * xf_cin + 63) / 64 * 64;
+}
 
 constexpr int kStagingBytes = kTileM * 128;
 
@@ -133,20 +138,24 @@ constexpr int kStagingBytes = kTileM * 128;
 // bitreverse-ordered by the lane bits consumed, see `owner` below.  Fixed tree -> deterministic.
 template <int P>
 __device__ __forceinline__ void row_sums(const float (&v)[32], bool valid, float (&out)[2 * P], float (&kshift)[P]) {
-  constexpr int per = 32 / P;
+  constexpr int per = 32 / P;  // >= 4: consecutive value pairs always belong to one group -> packed fp32x2 accumulators
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     const float k = __shfl_sync(0xffffffffu, v[i * per], 0);  // the warp's shift for this group (any finite value works)
     kshift[i] = k;
-    float s1 = 0.f, s2 = 0.f;
+    const f32x2 kk = pack2(k, k);
+    f32x2 s1 = pack2(0.f, 0.f), s2 = s1;
 #pragma unroll
-    for (int j = 0; j < per; ++j) {
-      const float x = v[i * per + j] - k;
-      s1 += x;
-      s2 = fmaf(x, x, s2);
+    for (int j = 0; j < per; j += 2) {
+      const f32x2 d = sub2(pack2(v[i * per + j], v[i * per + j + 1]), kk);
+      s1 = add2(s1, d);
+      s2 = fma2(d, d, s2);
     }
-    out[2 * i] = valid ? s1 : 0.f;
-    out[2 * i + 1] = valid ? s2 : 0.f;
+    float a0, a1, b0, b1;
+    unpack2(s1, a0, a1);
+    unpack2(s2, b0, b1);
+    out[2 * i] = valid ? a0 + a1 : 0.f;
+    out[2 * i + 1] = valid ? b0 + b1 : 0.f;
   }
 }
 
@@ -218,8 +227,8 @@ __device__ __forceinline__ void gn_chunk_reduce(const float (&sums)[16], const f
 
 constexpr int kSlabABytes = 17 * 1024;  // (128 + 2) slab rows x 128 B = 16640, padded to the 1024-byte swizzle-atom pitch
 
-template <int BLOCK_K, int NCTA, bool kSlab>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int BLOCK_K, int NCTA, bool kSlab, bool kXform>
+__global__ void __launch_bounds__(kNumThreads + (kXform ? kXformThreads : 0), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ OutMaps maps_out, const __grid_constant__ OutMaps maps_res,
                   const __grid_constant__ IgemmParams p) {
@@ -231,7 +240,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   constexpr int kAAtomBytes = kTileM * kAtomK * 2;
   constexpr int kABytes = kSlab ? kSlabABytes : kAAtomBytes * kAtoms;   // one A stage
   static_assert(!kSlab || BLOCK_K == 64, "slab mode stages 64-channel slabs");
-  extern __shared__ uint8_t smem_raw[];
+  static_assert(!kXform || kSlab, "the input transform works on row slabs");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   CLPK_GTRACE(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 300);  // kernel entry
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -252,8 +262,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   vec_s.red = reinterpret_cast<float2*>(vec_s.add + p.block_n);
   vec_s.redk = reinterpret_cast<float*>(vec_s.red + 2 * kEpiGroups * vec_s.nchg * 4 * 8);
   vec_s.rows = reinterpret_cast<int*>(vec_s.redk + 2 * kEpiGroups * vec_s.nchg * 4 * 8);
+  vec_s.xf_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(vec_s.red) + (red_bytes(p.block_n) + 63) / 64 * 64);
   const EpiVectors* vec = &vec_s;
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(reinterpret_cast<uint8_t*>(vec_s.red) + (red_bytes(p.block_n) + 63) / 64 * 64);
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(reinterpret_cast<uint8_t*>(vec_s.xf_tab) +
+                                                       (kXform ? (2 * 4 * p.cin + 63) / 64 * 64 : 0));
+  if (p.smem_slack == 0 && pad != 0) {  // the launch reserved no alignment slack: the 1024-byte alignment must hold
+    if (threadIdx.x == 0) printf("clpk: dynamic shared memory is not 1024-byte aligned (0x%x)\n", raw_addr);
+    __trap();
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -265,6 +281,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->ready[s], 4 * NCTA);  // one arrive per transform warp (of both CTAs of a pair)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
@@ -319,7 +336,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (CLPK_DBG(8)) tx -= (uint32_t)b_bytes;
             uint8_t* a_dst = smem_a + (size_t)stage * kABytes;
             uint8_t* b_dst = smem_b + (size_t)stage * b_bytes;
-            if (kSlab) {
+            if (kSlab && kXform) {
+              // input transform on: every CTA signals its OWN full barrier (its transform warps wait there, locally); the
+              // MMA issuer waits on `ready`, which those warps arrive on after normalising the slab
+              mbar_arrive_expect_tx(&bars->full[stage], tx);
+              tma_load_5d(a_dst, &map_a, &bars->full[stage], kc * 64, tc.w0 - 1, 0, tc.h0 + tap - 1, tc.b);
+#pragma unroll
+              for (int s3 = 0; s3 < 3; ++s3) {
+                const int kcol = (tap * 3 + s3) * p.cin + kc * 64;
+                tma_load_2d(b_dst + s3 * b_atom_bytes, &map_w, &bars->full[stage], kcol, w_row);
+              }
+            } else if (kSlab) {
               // stage kb = (kernel row r = tap, channel block kc): slab = input row h0 + r - 1, pixels w0 - 1 .. w0 + wbox
               // (TMA zero-fills what lies outside the image), weights = taps (r, 0..2) of that channel block
               const uint32_t lead_full = (NCTA == 2) ? mapa_u32(smem_u32(&bars->full[stage]), 0u) : smem_u32(&bars->full[stage]);
@@ -385,7 +412,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         CLPK_TRACE(blockIdx.x == 0 && lane == 0, 201);
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&bars->full[stage], phase);  // TMA bytes (of both CTAs) have landed
+          mbar_wait(kXform ? &bars->ready[stage] : &bars->full[stage], phase);  // operands (of both CTAs) are in place
           tc_fence_after();
           CLPK_GTRACE(lane == 0 && it == 0 && kb == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 302);  // first operands landed
           if (elect_one()) {
@@ -431,6 +458,62 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+      }
+    }
+  } else if (kXform && warp >= 2 + 4 * kEpiGroups) {
+    // ===================================================== transform warps (kXform): GroupNorm apply [+ SiLU] of the
+    // consumer side, in place on the freshly landed A slab: a <- act(a * scale[b, c] + shift[b, c]) (fp32 math, 16-bit
+    // in/out), i.e. blocks.py:41,43 / unet.py:105 without the stand-alone normalisation pass over HBM.  Pixels outside
+    // the image (TMA zero fill = the conv's padding of the NORMALISED tensor) are left untouched.
+    // Thread (row i0 + 16 k, 16-byte piece j): the 128B TMA swizzle puts logical piece j of slab row i at physical piece
+    // j ^ (i & 7) (stages are 1024-byte aligned) -> a quarter warp covers one 128-byte row: conflict-free.
+    const int xt = threadIdx.x - kNumThreads;
+    const int j = xt & 7, i0 = xt >> 3;
+    const bool f16 = p.op_f16 != 0, act = p.ep.in_silu != 0;
+    float* tab = vec->xf_tab;
+    const uint32_t ready0 = (NCTA == 2) ? mapa_u32(smem_u32(&bars->ready[0]), 0u) : 0u;
+    int cur_b = -1, stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      const TileCoord tc = decode_tile(p, tile, (int)rank);
+      const int vb = tc.ok ? tc.b : 0;
+      if (vb != cur_b) {  // new image: refresh the (scale | shift) table — every ~(tiles per image / CTAs) tiles
+        named_bar_sync(kEpiGroups + 2, kXformThreads);
+        for (int c = xt; c < p.cin; c += kXformThreads) {
+          tab[c] = __ldg(p.ep.in_scale + (long long)vb * p.cin + c);
+          tab[p.cin + c] = __ldg(p.ep.in_shift + (long long)vb * p.cin + c);
+        }
+        named_bar_sync(kEpiGroups + 2, kXformThreads);
+        cur_b = vb;
+      }
+      int tap = 0, kc = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&bars->full[stage], phase);  // this CTA's slab (and weight blocks) have landed
+        const int hin = tc.h0 + tap - 1;
+        if (tc.ok && hin >= 0 && hin < p.grid_h) {
+          float sc[8], sh[8];
+          const float4 s0 = *reinterpret_cast<const float4*>(tab + kc * 64 + 8 * j);
+          const float4 s1 = *reinterpret_cast<const float4*>(tab + kc * 64 + 8 * j + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(tab + p.cin + kc * 64 + 8 * j);
+          const float4 h1 = *reinterpret_cast<const float4*>(tab + p.cin + kc * 64 + 8 * j + 4);
+          sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+          sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+          uint8_t* a = smem_a + (size_t)stage * kABytes;
+          for (int i = i0; i < p.wbox + 2; i += kXformThreads / 8) {
+            const int w = tc.w0 - 1 + i;
+            if (w < 0 || w >= p.grid_w) continue;
+            uint4* q = reinterpret_cast<uint4*>(a + i * 128 + ((j ^ (i & 7)) << 4));
+            *q = affine_act8(*q, sc, sh, act, f16);
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_release_cluster(ready0 + (uint32_t)stage * 8u);
+          else mbar_arrive(&bars->ready[stage]);
+        }
+        if (++kc == p.kpt) { kc = 0; ++tap; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -555,15 +638,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           tmem_ld_wait();
           CLPK_TRACE(tr, 102);
           if (!(CLPK_DBG(1))) {
-            float v[32];
+            float v[32];  // (all epilogue arithmetic as packed fp32x2: half the issue slots of the scalar form)
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 m4 = *reinterpret_cast<const float4*>(&vec->mul[c + 4 * j4]);  // smem broadcast
               const float4 a4 = *reinterpret_cast<const float4*>(&vec->add[c + 4 * j4]);
-              v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), m4.x, a4.x);
-              v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), m4.y, a4.y);
-              v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), m4.z, a4.z);
-              v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), m4.w, a4.w);
+              unpack2(fma2(pack2(__uint_as_float(r[4 * j4 + 0]), __uint_as_float(r[4 * j4 + 1])), pack2(m4.x, m4.y),
+                           pack2(a4.x, a4.y)), v[4 * j4 + 0], v[4 * j4 + 1]);
+              unpack2(fma2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(m4.z, m4.w),
+                           pack2(a4.z, a4.w)), v[4 * j4 + 2], v[4 * j4 + 3]);
             }
             // staging row = lane (row of the warp's sub-box); 16-byte piece j4 lives at piece (j4 ^ (lane & 7)) — the
             // 128B TMA swizzle (slots are 1024-byte aligned)
@@ -575,7 +658,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 q = *reinterpret_cast<const float4*>(srow + ((j4 ^ (lane & 7)) << 4));
-                v[4 * j4 + 0] += q.x; v[4 * j4 + 1] += q.y; v[4 * j4 + 2] += q.z; v[4 * j4 + 3] += q.w;
+                unpack2(add2(pack2(v[4 * j4 + 0], v[4 * j4 + 1]), pack2(q.x, q.y)), v[4 * j4 + 0], v[4 * j4 + 1]);
+                unpack2(add2(pack2(v[4 * j4 + 2], v[4 * j4 + 3]), pack2(q.z, q.w)), v[4 * j4 + 2], v[4 * j4 + 3]);
               }
             }
             if (ep.gn_partial && !(CLPK_DBG(32))) {
@@ -607,6 +691,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               }
               if (st_16) {
                 // 16-byte piece j (channels 8j .. 8j+7) of row `lane` lives at piece (j ^ ((lane >> 1) & 3)): 64B swizzle
+                // (with a residual the slot still holds the fp32 sub-box other lanes may be reading: reconverge first)
+                if (res_tma) __syncwarp();
                 uint8_t* srow16 = sbuf + lane * 64;
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) *reinterpret_cast<uint4*>(srow16 + ((j8 ^ ((lane >> 1) & 3)) << 4)) = pk[j8];
@@ -848,6 +934,15 @@ int igemm_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg) {
   const int sub = gn_cpg >= 32 ? gn_cpg / 32 : 1;
   return phases * ((gh + hbox - 1) / hbox) * ((gw + wbox - 1) / wbox) * sub;
 }
+static bool slab_geometry_ok(int kind, int w_in, int cin, int block_n) {
+  const bool slab_pair = block_n % 32 == 0 && block_n <= 128;
+  return kind == CLPK_CONV_3X3_S1 && cin % 64 == 0 && w_in >= kTileM && (slab_pair || block_n <= 64);
+}
+bool igemm_xform_ok(int kind, int h_in, int w_in, int cin, int cout) {
+  (void)h_in;
+  { const char* e = getenv("CLPK_IGEMM_SLAB"); if (e && atoi(e) == 0) return false; }
+  return slab_geometry_ok(kind, w_in, cin, igemm_block_n(igemm_cout_pad(cout))) && cin <= 1024;
+}
 int igemm_block_n(int cout_pad) {
   int best = 16;
   for (int n = 16; n <= 256 && n <= cout_pad; n += 16)
@@ -932,11 +1027,18 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   // A stage holds the 3 weight blocks of a kernel row, so the per-CTA share of N must stay <= 64 rows: CTA pairs for
   // N <= 128, a single CTA for narrow N (the 3-channel `out` conv, N padded to 16).
   const bool slab_pair = p.block_n % 32 == 0 && p.block_n <= 128;
-  if (kind == CLPK_CONV_3X3_S1 && cin % 64 == 0 && w_in >= kTileM && (slab_pair || p.block_n <= 64)) {
+  if (slab_geometry_ok(kind, w_in, cin, p.block_n)) {
     const char* e = getenv("CLPK_IGEMM_SLAB");
     p.slab = (e && atoi(e) == 0) ? 0 : 1;
   }
   if (p.slab) { p.ncta = slab_pair ? 2 : 1; p.block_k = 64; }
+  p.xform = 0;
+  if (ep->in_scale || ep->in_shift) {
+    CLPK_REQUIRE(ep->in_scale && ep->in_shift, "in_scale and in_shift must be given together");
+    CLPK_REQUIRE(p.slab && igemm_xform_ok(kind, h_in, w_in, cin, cout),
+                 "the fused input transform needs the row-slab mainloop (3x3 s1, W >= 128, cout <= 128, cin %% 64 == 0)");
+    p.xform = 1;
+  }
   p.n_tiles_n = p.cout_pad / p.block_n;
   p.kpt = cin / p.block_k;
   p.ep = *ep;
@@ -1009,11 +1111,14 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   const bool f32_ok = p.ep.out_f32 != nullptr && (reinterpret_cast<uintptr_t>(p.ep.out_f32) & 15) == 0;
   p.chunked = (p.block_n % 32 == 0 && cout % 32 == 0 && (f32_ok || (p.ep.out_op && !p.ep.out_f32)) && !p.ep.out_nchw &&
                warp_subbox_ok(p.wbox)) ? 1 : 0;
-  const int fixed = 1024 /*alignment slack*/ + epi_vector_bytes(p.block_n) + (int)sizeof(PipeBarriers) + 16;
+  // The dynamic shared memory is declared __align__(1024) and is the kernel's only shared memory, so its base is
+  // 1024-aligned and no slack is reserved (the kernel traps if that ever fails to hold); CLPK_IGEMM_SLACK=1 restores it.
+  { const char* e = getenv("CLPK_IGEMM_SLACK"); p.smem_slack = (e && atoi(e) != 0) ? 1024 : 0; }
+  const int fixed = p.smem_slack + epi_vector_bytes(p.block_n, p.xform ? cin : 0) + (int)sizeof(PipeBarriers) + 16;
   p.n_staging = 0;
   const bool op16_ok = p.ep.out_op != nullptr && (reinterpret_cast<uintptr_t>(p.ep.out_op) & 15) == 0;
   if (p.chunked && (p.ep.out_f32 || p.ep.resid || op16_ok)) {
-    CLPK_REQUIRE(p.ep.out_f32 != nullptr || !p.ep.resid, "a residual input needs the fp32 output");
+    CLPK_REQUIRE(p.ep.out_f32 != nullptr || !p.ep.resid || op16_ok, "a residual input needs an NHWC output");
     // as many staging slots per epilogue group (<= 3) as the smem ring can spare without losing depth; a residual
     // epilogue keeps (slots - 1) chunk loads in flight per group, so its throughput hangs on this
     // (measured: the 256-wide CTA-pair tiles of the 64x64 / 32x32 layers prefer a 5-deep ring over a second staging slot)
@@ -1073,18 +1178,20 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
       if (rc) return rc;
     }
   }
-  if (p.chunked && p.ep.out_f32) {
+  memset(&out->maps_res, 0, sizeof(out->maps_res));
+  if (p.chunked && (p.ep.out_f32 || p.ep.resid)) {
     const long long CO = cout, OW = p.out_w, OH = p.out_h, sc = p.out_scale;
     cuuint64_t odims[5] = {(cuuint64_t)CO, (cuuint64_t)p.grid_w, 1, (cuuint64_t)p.grid_h, (cuuint64_t)batch};
     cuuint64_t ostr[4] = {(cuuint64_t)(sc * CO * 4), (cuuint64_t)(sc * OW * CO * 4), (cuuint64_t)(sc * OW * CO * 4),
                           (cuuint64_t)(OH * OW * CO * 4)};
     cuuint32_t obox[5] = {32, (cuuint32_t)wsub, 1, (cuuint32_t)(32 / wsub), 1};  // one epilogue warp's 32 tile rows
-    memset(&out->maps_res, 0, sizeof(out->maps_res));
     for (int phase = 0; phase < p.phases; ++phase) {
       const long long off = ((long long)(phase >> 1) * OW + (phase & 1)) * CO;
-      rc = encode_map(&out->maps_out.m[phase], p.ep.out_f32 + off, 5, odims, ostr, obox, 128,
-                      CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
-      if (rc) return rc;
+      if (p.ep.out_f32) {
+        rc = encode_map(&out->maps_out.m[phase], p.ep.out_f32 + off, 5, odims, ostr, obox, 128,
+                        CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+        if (rc) return rc;
+      }
       if (p.ep.resid) {
         CLPK_REQUIRE((reinterpret_cast<uintptr_t>(p.ep.resid) & 15) == 0, "residual tensor must be 16-byte aligned");
         rc = encode_map(&out->maps_res.m[phase], const_cast<float*>(p.ep.resid) + off, 5, odims, ostr, obox, 128,
@@ -1096,9 +1203,9 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   return rc;
 }
 
-template <int BK, int NC, bool SLAB = false>
+template <int BK, int NC, bool SLAB = false, bool XF = false>
 static cudaError_t set_smem_attr() {
-  return cudaFuncSetAttribute(conv_igemm_kernel<BK, NC, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  return cudaFuncSetAttribute(conv_igemm_kernel<BK, NC, SLAB, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
 }
 
 // function attributes are per device (context): set them once for every device this process launches on
@@ -1118,16 +1225,18 @@ int igemm_init() {
   if (attr_err == cudaSuccess) attr_err = set_smem_attr<128, 2>();
   if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2, true>();
   if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 1, true>();
+  if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2, true, true>();
+  if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 1, true, true>();
   CLPK_CHECK_CUDA(attr_err);
   done[dev] = true;
   return CLPK_OK;
 }
 
-template <int BK, int NC, bool SLAB = false>
+template <int BK, int NC, bool SLAB = false, bool XF = false>
 static cudaError_t launch_variant(const IgemmLaunch& L, cudaStream_t stream) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)L.grid);
-  cfg.blockDim = dim3(kNumThreads);
+  cfg.blockDim = dim3(kNumThreads + (XF ? kXformThreads : 0));
   cfg.dynamicSmemBytes = (size_t)L.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -1146,14 +1255,15 @@ static cudaError_t launch_variant(const IgemmLaunch& L, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BK, NC, SLAB>, L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
+  return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BK, NC, SLAB, XF>, L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
 }
 
 int igemm_launch(const IgemmLaunch& L, cudaStream_t stream) {
   int irc = igemm_init();
   if (irc) return irc;
   cudaError_t e;
-  if (L.p.slab) e = (L.p.ncta == 2) ? launch_variant<64, 2, true>(L, stream) : launch_variant<64, 1, true>(L, stream);
+  if (L.p.slab && L.p.xform) e = (L.p.ncta == 2) ? launch_variant<64, 2, true, true>(L, stream) : launch_variant<64, 1, true, true>(L, stream);
+  else if (L.p.slab) e = (L.p.ncta == 2) ? launch_variant<64, 2, true>(L, stream) : launch_variant<64, 1, true>(L, stream);
   else if (L.p.block_k == 128) e = (L.p.ncta == 2) ? launch_variant<128, 2>(L, stream) : launch_variant<128, 1>(L, stream);
   else if (L.p.block_k == 64) e = (L.p.ncta == 2) ? launch_variant<64, 2>(L, stream) : launch_variant<64, 1>(L, stream);
   else e = (L.p.ncta == 2) ? launch_variant<32, 2>(L, stream) : launch_variant<32, 1>(L, stream);
@@ -1196,6 +1306,11 @@ extern "C" int64_t clpk_pack_conv_weight(const float* w_dev, void* out_bf16_dev,
   }
   count_launch();
   return total;
+}
+
+extern "C" int clpk_conv_in_affine_supported(int kind, int h_in, int w_in, int cin, int cout) {
+  if (kind < 0 || kind > 3 || h_in <= 0 || w_in <= 0 || cin <= 0 || cout <= 0) return 0;
+  return igemm_xform_ok(kind, h_in, w_in, cin, cout) ? 1 : 0;
 }
 
 extern "C" int clpk_conv_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg) {

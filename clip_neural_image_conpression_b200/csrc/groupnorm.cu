@@ -153,16 +153,6 @@ gn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, float
 // of the octets per pixel (kHoist) each thread owns one channel octet, so its 8 (scale, shift) pairs live in registers.
 constexpr int kGnUnroll = 4;
 
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float silu_tanh(float x) {
-  const float h = 0.5f * x;
-  return fmaf(h, tanh_approx(h), h);
-}
-
 template <bool kIn16>
 __device__ __forceinline__ void gn_load8(const void* __restrict__ xin, long long idx, uint4& a, uint4& b) {
   if (kIn16) {
@@ -309,6 +299,34 @@ __global__ void gn_finalize_kernel(const float4* __restrict__ partial, float2* _
   if (lane == 0) stats[(long long)b * groups + g] = st;
 }
 
+// partial -> per-(image, channel) affine form of GroupNorm for convs that normalise their own A operand
+// (clpk_conv_epilogue.in_scale / in_shift): one block per image, one warp per group.
+__global__ void gn_affine_kernel(const float4* __restrict__ partial, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
+                                 int slots, int pieces, int groups, int c, float eps) {
+  pdl_prologue_done();
+  const int b = blockIdx.x;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (g >= groups) return;
+  const float2 st = gn_fold_partials(partial, b, g, slots, pieces, groups, eps, lane);
+  const int cpg = c / groups;
+  for (int k = lane; k < cpg; k += 32) {
+    const int ch = g * cpg + k;
+    const float sc = st.y * __ldg(gamma + ch);
+    scale[(long long)b * c + ch] = sc;
+    shift[(long long)b * c + ch] = fmaf(-st.x, sc, __ldg(beta + ch));
+  }
+}
+
+int launch_gn_affine(const float4* partial, const float* gamma, const float* beta, float* scale, float* shift, int batch,
+                     int slots, int pieces, int groups, int c, float eps, cudaStream_t stream) {
+  CLPK_REQUIRE(groups > 0 && groups <= 32 && c % groups == 0 && pieces % groups == 0, "GroupNorm affine: bad group layout");
+  CLPK_CHECK_CUDA(launch_kernel_pdl(gn_affine_kernel, dim3(batch), dim3(32 * groups), 0, stream, partial, gamma, beta, scale,
+                                    shift, slots, pieces, groups, c, eps));
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
 int launch_gn_finalize(const float4* partial, float2* stats, int batch, int slots, int groups, float eps,
                        cudaStream_t stream) {
   CLPK_REQUIRE(groups <= 32, "GroupNorm finalize supports <= 32 groups");
@@ -418,6 +436,14 @@ extern "C" int clpk_groupnorm_finalize(const void* partial, void* stats, int bat
                "clpk_groupnorm_finalize: bad arguments");
   return launch_gn_finalize(reinterpret_cast<const float4*>(partial), reinterpret_cast<float2*>(stats), batch, slots,
                             groups, eps, (cudaStream_t)stream);
+}
+
+extern "C" int clpk_groupnorm_affine(const void* partial, const float* gamma, const float* beta, float* scale, float* shift,
+                                     int batch, int slots, int pieces, int groups, int c, float eps, void* stream) {
+  CLPK_REQUIRE(partial && gamma && beta && scale && shift && batch > 0 && slots > 0 && pieces > 0 && groups > 0 && c > 0,
+               "clpk_groupnorm_affine: bad arguments");
+  return launch_gn_affine(reinterpret_cast<const float4*>(partial), gamma, beta, scale, shift, batch, slots, pieces, groups,
+                          c, eps, (cudaStream_t)stream);
 }
 
 extern "C" int clpk_groupnorm_apply(const float* x, const float* gamma, const float* beta, const void* stats, void* y,

@@ -40,6 +40,11 @@ struct GnPlan {
   int slots = 0;
   int piece = 0, pieces = 0;  // channels per partial sum the producer epilogue emits, and their number (C / piece)
   bool fused = false;
+  // `in_consumer`: the normalisation (+ SiLU) is applied by the consuming conv to its own A operand in shared memory
+  // (clpk_conv_epilogue.in_scale / in_shift); the stand-alone apply pass is replaced by a tiny partial -> (scale, shift)
+  // fold (gn_affine_kernel)
+  bool in_consumer = false;
+  float *scale = nullptr, *shift = nullptr;  // [B][C]
 };
 
 struct ResBlockPlan {
@@ -50,6 +55,13 @@ struct ResBlockPlan {
   bool emit16 = false;   // conv2 also writes the 16-bit copy X16[level] (feeds the next resampling conv)
   bool y16 = false;        // conv1 output kept in the 16-bit operand format (needs fused GroupNorm statistics)
 };
+
+// GroupNorm fusion switches (env CLPK_FUSE_GN, bit mask, default 3): 1 = norm2 + SiLU of a ResBlock applied inside conv2
+// (row-slab levels), 2 = out_norm applied inside the `out` conv, fed by a 16-bit-only transposed-conv output.
+static int fuse_gn_mask() {
+  const char* e = getenv("CLPK_FUSE_GN");
+  return e ? atoi(e) : 3;
+}
 
 }  // namespace clpk
 
@@ -88,6 +100,7 @@ struct clpk_plan {
   uint16_t* Y = nullptr;     // conv1 output of the current ResBlock, stored in the 16-bit operand format
   uint16_t* T = nullptr;     // GroupNorm+SiLU output = conv A operand (fp16 or bf16, cfg.op_dtype)
   std::vector<uint16_t*> X16;  // per level: 16-bit copy of X[l]
+  bool fuse_head = false;    // out_norm applied inside the `out` conv (see fuse_gn_mask)
   bool x16_gn = false;       // env CLPK_X16=1: GroupNorms on the residual stream read X16 instead of fp32 X
   float* Yf = nullptr;       // fp32 conv1 output, only for ResBlocks whose GroupNorm statistics cannot be fused
   void* gn_ws = nullptr;
@@ -258,6 +271,13 @@ int setup_gn(clpk_plan* P, GnPlan* gn, int producer_kind, int prod_h_in, int pro
 int run_groupnorm(clpk_plan* P, const void* x, int x_is_16, const GnPlan& gn, cudaStream_t s) {
   const int level = gn.level, groups = gn_groups_of(P, level);
   const int hw = P->lv_h[level] * P->lv_w[level], c = P->lv_c[level];
+  if (gn.in_consumer) {  // statistics -> (scale, shift) table; the consuming conv normalises its own operand
+    P->prof_mark(kProfCond, s);
+    const int rc = launch_gn_affine(gn.partial, gn.gamma, gn.beta, gn.scale, gn.shift, P->B, gn.slots, gn.pieces, groups, c,
+                                    1e-5f, s);
+    P->prof_mark(-1, s);
+    return rc;
+  }
   const GnShape shp = gn_shape(P->B, hw, c, groups);
   P->prof_mark(kProfGroupNorm, s);
   int rc;
@@ -475,6 +495,13 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   }
   CLPK_TRY(setup_gn(P, &P->out_gn, CLPK_CONVT_4X4_S2, P->lv_h[1], P->lv_w[1]));
   gn_after_up[0] = &P->out_gn;
+  P->fuse_head = (fuse_gn_mask() & 2) && P->out_gn.fused && !P->x16_gn &&
+                 igemm_xform_ok(CLPK_CONV_3X3_S1, height, width, cfg->base, cfg->img_ch);
+  if (P->fuse_head) {
+    P->out_gn.in_consumer = true;
+    CLPK_TRY(P->alloc(&P->out_gn.scale, (long long)batch * cfg->base));
+    CLPK_TRY(P->alloc(&P->out_gn.shift, (long long)batch * cfg->base));
+  }
   auto wire_gn = [&](clpk_conv_epilogue* e, const GnPlan* gn) {
     if (gn && gn->fused) {
       e->gn_partial = gn->partial;
@@ -500,7 +527,18 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     e2.out_op = rb.emit16 ? P->X16[rb.level] : nullptr;
     e2.cout_valid = rb.c;
     wire_gn(&e2, gn_after_conv2[i]);
-    CLPK_TRY(bind_conv(P, &rb.conv2, P->T, e2));
+    const void* a2 = P->T;
+    if ((fuse_gn_mask() & 1) && rb.y16 && rb.gn2.fused && igemm_xform_ok(CLPK_CONV_3X3_S1, rb.h, rb.w, rb.c, rb.c)) {
+      // blocks.py:43 act(norm2(y)) happens inside conv2: A operand = the raw conv1 + FiLM output Y
+      rb.gn2.in_consumer = true;
+      CLPK_TRY(P->alloc(&rb.gn2.scale, (long long)batch * rb.c));
+      CLPK_TRY(P->alloc(&rb.gn2.shift, (long long)batch * rb.c));
+      e2.in_scale = rb.gn2.scale;
+      e2.in_shift = rb.gn2.shift;
+      e2.in_silu = 1;
+      a2 = P->Y;
+    }
+    CLPK_TRY(bind_conv(P, &rb.conv2, a2, e2));
     P->flops_fwd += rb.conv1.flops + rb.conv2.flops;
   }
   // ---- resampling convs
@@ -528,6 +566,12 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     eu.resid = P->X[l];  // skip connection, added in place
     eu.out_f32 = P->X[l];
     eu.out_op = P->x16_gn ? P->X16[l] : nullptr;
+    if (l == 0 && P->fuse_head) {
+      // the last transposed conv's result is read by out_norm only: keep just the 16-bit copy (its GroupNorm statistics
+      // still come from the fp32 accumulators), which the `out` conv normalises in shared memory
+      eu.out_f32 = nullptr;
+      eu.out_op = P->X16[0];
+    }
     eu.cout_valid = P->lv_c[l];
     wire_gn(&eu, gn_after_up[l]);
     CLPK_TRY(bind_conv(P, &up, P->X16[l + 1], eu));
@@ -566,7 +610,12 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     eo.bias = P->out_conv.bias;
     eo.out_nchw = P->eps_buf;
     eo.cout_valid = cfg->img_ch;
-    CLPK_TRY(bind_conv(P, &P->out_conv, P->T, eo));
+    if (P->fuse_head) {  // unet.py:105 out(out_norm(x)): no activation
+      eo.in_scale = P->out_gn.scale;
+      eo.in_shift = P->out_gn.shift;
+      eo.in_silu = 0;
+    }
+    CLPK_TRY(bind_conv(P, &P->out_conv, P->fuse_head ? (const void*)P->X16[0] : (const void*)P->T, eo));
     P->flops_fwd += P->out_conv.flops;
   }
   P->flops_fwd += 2.0 * batch * (double)height * width * cfg->base * cfg->img_ch * 9;  // in_conv
@@ -769,12 +818,12 @@ extern "C" int clpk_plan_work_breakdown(const clpk_plan* P, double* conv_res_flo
   double a = 0, b = 0, g = 0;
   for (const ResBlockPlan& rb : P->rbs) {
     a += rb.conv1.flops + rb.conv2.flops;
-    g += 2.0 * P->B * (double)rb.h * rb.w * rb.c;
+    g += ((rb.gn1.in_consumer ? 0.0 : 1.0) + (rb.gn2.in_consumer ? 0.0 : 1.0)) * P->B * (double)rb.h * rb.w * rb.c;
   }
   for (const ConvPlan& c : P->downs) b += c.flops;
   for (const ConvPlan& c : P->ups) b += c.flops;
   b += P->out_conv.flops;
-  g += (double)P->B * P->H * P->W * P->cfg.base;  // out_norm
+  if (!P->out_gn.in_consumer) g += (double)P->B * P->H * P->W * P->cfg.base;  // out_norm
   *conv_res_flops = a; *conv_other_flops = b; *gn_elements = g;
   return CLPK_OK;
 }
@@ -785,11 +834,12 @@ extern "C" int clpk_plan_groupnorm_bytes(const clpk_plan* P, double* bytes) {
   CLPK_REQUIRE(P && bytes, "clpk_plan_groupnorm_bytes: null argument");
   double tot = 0;
   auto in_bytes_x = [&](const GnPlan& gn) { return (gn.fused && P->x16_gn) ? 2.0 : 4.0; };
-  for (const ResBlockPlan& rb : P->rbs) {
+  for (const ResBlockPlan& rb : P->rbs) {  // (GroupNorms applied inside their consumer conv have no stand-alone pass)
     const double n = (double)P->B * rb.h * rb.w * rb.c;
-    tot += n * (in_bytes_x(rb.gn1) + 2.0) + n * ((rb.y16 ? 2.0 : 4.0) + 2.0);
+    if (!rb.gn1.in_consumer) tot += n * (in_bytes_x(rb.gn1) + 2.0);
+    if (!rb.gn2.in_consumer) tot += n * ((rb.y16 ? 2.0 : 4.0) + 2.0);
   }
-  tot += (double)P->B * P->H * P->W * P->cfg.base * (in_bytes_x(P->out_gn) + 2.0);
+  if (!P->out_gn.in_consumer) tot += (double)P->B * P->H * P->W * P->cfg.base * (in_bytes_x(P->out_gn) + 2.0);
   *bytes = tot;
   return CLPK_OK;
 }

@@ -16,7 +16,7 @@ from ._lib import (CONV_3X3_S1, CONV_3X3_S2, CONVT_4X4_S2, ConvEpilogue, check, 
 
 __all__ = [
     "dequant_l2norm", "quant_encode", "quant_fit", "ddim_step", "timestep_embedding", "linear", "film_apply",
-    "groupnorm_silu", "pack_conv_weight", "conv_igemm", "conv_direct", "conv_in", "to_uint8_hwc", "psnr_sqerr_u8", "ssim_u8", "ddpm_combine",
+    "groupnorm_silu", "groupnorm_affine", "conv_in_affine_supported", "pack_conv_weight", "conv_igemm", "conv_direct", "conv_in", "to_uint8_hwc", "psnr_sqerr_u8", "ssim_u8", "ddpm_combine",
     "CONV_3X3_S1", "CONV_3X3_S2", "CONVT_4X4_S2",
 ]
 
@@ -148,7 +148,7 @@ def pack_conv_weight(w: torch.Tensor, kind: int, dtype: torch.dtype = torch.floa
 
 
 def _conv(fn_name: str, x_nhwc_op, w_packed, kind, cout, bias, film_scale1p, film_shift, resid, out_f32, out_op,
-          out_nchw, gn_partial=None, gn_cpg=0):
+          out_nchw, gn_partial=None, gn_cpg=0, in_affine=None):
     require_cuda(x_nhwc_op, w_packed, bias)
     assert x_nhwc_op.is_contiguous() and x_nhwc_op.dtype == w_packed.dtype, "operands must share one 16-bit dtype"
     b, h, w, cin = x_nhwc_op.shape
@@ -166,6 +166,12 @@ def _conv(fn_name: str, x_nhwc_op, w_packed, kind, cout, bias, film_scale1p, fil
     ep.cout_valid = cout
     ep.gn_partial = ptr(gn_partial)
     ep.gn_cpg = int(gn_cpg)
+    if in_affine is not None:
+        isc, ish, act = in_affine
+        isc, ish = _f32c(isc), _f32c(ish)
+        assert isc.shape == (b, cin) and ish.shape == (b, cin)
+        keep += [isc, ish]
+        ep.in_scale, ep.in_shift, ep.in_silu = ptr(isc), ptr(ish), int(bool(act))
     fn = getattr(_lib.load(), fn_name)
     check(fn(ptr(x_nhwc_op), ptr(w_packed), kind, b, h, w, cin, cout, op_code(x_nhwc_op.dtype), C.byref(ep), stream_ptr()),
           fn_name)
@@ -182,11 +188,14 @@ def _conv_out_hw(kind: int, h: int, w: int):
 @on_tensor_device
 def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, bias: torch.Tensor, *,
                film_scale1p=None, film_shift=None, resid=None, want_f32=True, want_op=False, want_nchw=False,
-               gn_groups: int = 0, impl: str = "igemm"):
+               gn_groups: int = 0, impl: str = "igemm", in_affine=None, return_partial: bool = False):
     """Implicit-GEMM conv on the tensor cores (x and w_packed in the same 16-bit dtype).  Returns a dict of the
     requested outputs: "f32" NHWC fp32, "op" NHWC in the operand dtype, "nchw" fp32 NCHW.  gn_groups > 0 additionally
     returns "gn_stats" [B, gn_groups, 2] = (mean, rstd) of a GroupNorm(gn_groups) over the output, accumulated by the
-    conv epilogue (no extra pass over the tensor)."""
+    conv epilogue (no extra pass over the tensor).  in_affine = (scale [B, Cin], shift [B, Cin], silu) applies
+    a <- act(x * scale + shift) to the A operand inside the kernel (clpk_conv_epilogue.in_scale; geometries with
+    conv_in_affine_supported(...) only).  return_partial additionally returns the raw per-tile statistics ("gn_partial",
+    "gn_slots") for groupnorm_affine."""
     b, h, w, _ = x_nhwc_op.shape
     oh, ow = _conv_out_hw(kind, h, w)
     dev = x_nhwc_op.device
@@ -206,13 +215,32 @@ def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout:
         partial = torch.zeros((b, slots, gn_groups, 4), dtype=torch.float32, device=dev)
     _conv("clpk_conv_igemm" if impl == "igemm" else "clpk_conv_direct", x_nhwc_op, w_packed, kind, cout, bias,
           film_scale1p, film_shift, _f32c(resid) if resid is not None else None, outs.get("f32"), outs.get("op"),
-          outs.get("nchw"), partial, cpg)
+          outs.get("nchw"), partial, cpg, in_affine)
+    if gn_groups > 0 and return_partial:
+        outs["gn_partial"], outs["gn_slots"] = partial, slots
     if gn_groups > 0:
         stats = torch.empty((b, gn_groups, 2), dtype=torch.float32, device=dev)
         check(_lib.load().clpk_groupnorm_finalize(ptr(partial), ptr(stats), b, slots, gn_groups, float(oh * ow * cpg), 1e-5,
                                                   stream_ptr()), "clpk_groupnorm_finalize")
         outs["gn_stats"] = stats
     return outs
+
+
+def conv_in_affine_supported(kind: int, h: int, w: int, cin: int, cout: int) -> bool:
+    return bool(_lib.load().clpk_conv_in_affine_supported(kind, h, w, cin, cout))
+
+
+@on_tensor_device
+def groupnorm_affine(partial: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float = 1e-5):
+    """Per-tile conv statistics [B, slots, pieces, 4] -> (scale, shift) [B, C] of GroupNorm(groups) in affine form."""
+    require_cuda(partial, gamma, beta)
+    b, slots, pieces, _ = partial.shape
+    c = gamma.numel()
+    scale = torch.empty((b, c), dtype=torch.float32, device=partial.device)
+    shift = torch.empty_like(scale)
+    check(_lib.load().clpk_groupnorm_affine(ptr(partial), ptr(_f32c(gamma)), ptr(_f32c(beta)), ptr(scale), ptr(shift), b, slots,
+                                            pieces, groups, c, eps, stream_ptr()), "clpk_groupnorm_affine")
+    return scale, shift
 
 
 @on_tensor_device

@@ -137,7 +137,25 @@ typedef struct clpk_conv_epilogue {
    * Needs an NHWC output and gn_cpg in {4, 8, 16} or a multiple of 32. */
   void* gn_partial;
   int gn_cpg;
+  /* Input transform fused into the A-operand path — the consumer-side half of GroupNorm [+ SiLU] (blocks.py:41,43;
+   * unet.py:105) without a stand-alone normalisation pass over HBM:
+   *   a[b,h,w,c] <- act(x[b,h,w,c] * in_scale[b*cin + c] + in_shift[b*cin + c]),  act = SiLU when in_silu != 0,
+   * applied in shared memory (fp32 math) to every operand slab before the tensor cores read it; the conv's zero padding
+   * stays zero.  Tables from clpk_groupnorm_affine.  Only for geometries with clpk_conv_in_affine_supported(...) == 1
+   * (3x3 stride-1 convs on rows of >= 128 pixels, cout <= 128, cin % 64 == 0).  NULL = off. */
+  const float* in_scale;
+  const float* in_shift;
+  int in_silu;
 } clpk_conv_epilogue;
+
+/* 1 when clpk_conv_igemm accepts in_scale / in_shift for this geometry, else 0. */
+int clpk_conv_in_affine_supported(int kind, int h_in, int w_in, int cin, int cout);
+
+/* Folds the per-tile statistics a conv epilogue wrote (gn_partial, `pieces` triples per slot: pieces = c / gn_cpg) into
+ * the per-(image, channel) affine form of GroupNorm: scale[b*c + ch] = rstd * gamma[ch],
+ * shift[b*c + ch] = beta[ch] - mean * rstd * gamma[ch]  (biased variance, eps inside the sqrt; blocks.py:33,35). */
+int clpk_groupnorm_affine(const void* partial_dev, const float* gamma_dev, const float* beta_dev, float* scale_dev,
+                          float* shift_dev, int batch, int slots, int pieces, int groups, int c, float eps, void* stream);
 
 /* Number of partial-sum slots per image a conv of this geometry writes for a consumer GroupNorm with gn_cpg channels
  * per group (<= 0: the fused statistics are not available for this shape). */

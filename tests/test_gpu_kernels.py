@@ -283,6 +283,69 @@ def test_conv_fused_groupnorm_statistics(ops, kind, b, h, w, cin, cout, resid):
     assert float((a.float() - ref.float()).abs().max()) <= 4e-3 * max(1.0, float(ref.float().abs().max()))
 
 
+@pytest.mark.parametrize("b,h,w,cin,cout,silu,resid", [
+    (1, 4, 256, 128, 128, True, False),    # CTA-pair slab mainloop, two channel blocks
+    (3, 5, 192, 64, 64, True, True),       # ragged W (clipped second tile), odd tile count (masked pair half), residual
+    (2, 6, 320, 128, 3, False, False),     # single-CTA slab, narrow N: the head (out_norm has no activation)
+    (1, 3, 128, 192, 128, True, True),     # three channel blocks, W == one tile
+    (8, 16, 128, 128, 128, True, True),    # many tiles per CTA: image changes inside a CTA's tile walk (table refresh)
+])
+def test_conv_fused_input_groupnorm(ops, b, h, w, cin, cout, silu, resid):
+    """clpk_conv_epilogue.in_scale / in_shift: the conv applies act(x * scale[b,c] + shift[b,c]) to its own A operand in
+    shared memory (GroupNorm apply + SiLU of the consumer side).  Reference: the same kernel WITHOUT the transform, fed
+    with the transformed tensor computed by torch and rounded to fp16 — identical up to the 1-ulp disagreements between
+    tanh.approx-based SiLU and torch's; and the fp64 convolution of that tensor.  Zero padding must stay zero."""
+    g = torch.Generator().manual_seed(11 + cin + cout + w)
+    x16 = (torch.randn(b, h, w, cin, generator=g) * 2 + 0.5).to(torch.float16).cuda()
+    sc = (1 + 0.3 * torch.randn(b, cin, generator=g)).cuda()
+    sh = (0.5 * torch.randn(b, cin, generator=g) + 0.7).cuda()      # non-zero shift: padding would show up as act(shift)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    assert ops.conv_in_affine_supported(0, h, w, cin, cout)
+    t = x16.float() * sc[:, None, None, :] + sh[:, None, None, :]
+    t16 = (F.silu(t) if silu else t).to(torch.float16)
+    kw = {"resid": torch.randn(b, h, w, cout, generator=g).cuda()} if resid else {}
+    nchw = cout % 16 != 0
+    wp = ops.pack_conv_weight(wt, 0)
+    args = dict(want_f32=not nchw, want_op=False, want_nchw=nchw, **kw)
+    fused = ops.conv_igemm(x16, wp, 0, cout, bias, in_affine=(sc, sh, silu), **args)
+    plain = ops.conv_igemm(t16, wp, 0, cout, bias, **args)
+    y = fused["nchw"] if nchw else fused["f32"].permute(0, 3, 1, 2)
+    yp = plain["nchw"] if nchw else plain["f32"].permute(0, 3, 1, 2)
+    ref = F.conv2d(t16.float().permute(0, 3, 1, 2).double(), wt.to(torch.float16).double(), bias.double(), padding=1)
+    if resid:
+        ref = ref + kw["resid"].permute(0, 3, 1, 2).double()
+    scale = max(1.0, float(ref.abs().max()))
+    assert float(torch.linalg.norm(y.double() - ref) / torch.linalg.norm(ref)) < 1e-3
+    assert float((y - yp).abs().max()) < 5e-3 * scale
+    assert float((y.double() - ref).abs().max()) < 5e-3 * scale
+    again = ops.conv_igemm(x16, wp, 0, cout, bias, in_affine=(sc, sh, silu), **args)
+    assert torch.equal(again["nchw"] if nchw else again["f32"], fused["nchw"] if nchw else fused["f32"])   # deterministic
+    assert not ops.conv_in_affine_supported(0, 32, 32, 128, 128) and not ops.conv_in_affine_supported(1, 256, 256, 128, 128)
+
+
+def test_groupnorm_affine_from_conv_statistics(ops):
+    """conv (fused statistics) -> clpk_groupnorm_affine -> next conv normalising its own operand  ==  conv -> GroupNorm+SiLU
+    pass -> conv: the two-kernel ResBlock tail (blocks.py:43) without the stand-alone normalisation pass."""
+    g = torch.Generator().manual_seed(21)
+    b, h, w, c = 2, 6, 256, 128
+    x16 = torch.randn(b, h, w, c, generator=g).to(torch.float16).cuda()
+    w1 = (torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5).cuda()
+    w2 = (torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5).cuda()
+    b1, b2 = (torch.randn(c, generator=g) + 3.0).cuda(), torch.randn(c, generator=g).cuda()
+    gamma, beta = (1 + 0.1 * torch.randn(c, generator=g)).cuda(), (0.1 * torch.randn(c, generator=g)).cuda()
+    o1 = ops.conv_igemm(x16, ops.pack_conv_weight(w1, 0), 0, c, b1, want_f32=True, want_op=True, gn_groups=8, return_partial=True)
+    sc, sh = ops.groupnorm_affine(o1["gn_partial"], gamma, beta, 8)
+    mean, rstd = o1["gn_stats"][..., 0], o1["gn_stats"][..., 1]
+    np.testing.assert_allclose(sc.cpu().numpy(), (rstd.repeat_interleave(c // 8, dim=1) * gamma).cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(sh.cpu().numpy(), (beta - mean.repeat_interleave(c // 8, dim=1) * rstd.repeat_interleave(c // 8, dim=1) * gamma).cpu().numpy(),
+                               rtol=1e-5, atol=1e-6)
+    fused = ops.conv_igemm(o1["op"], ops.pack_conv_weight(w2, 0), 0, c, b2, in_affine=(sc, sh, True))["f32"]
+    t16 = ops.groupnorm_apply(o1["op"].float(), gamma, beta, o1["gn_stats"], 8, silu=True)
+    plain = ops.conv_igemm(t16, ops.pack_conv_weight(w2, 0), 0, c, b2)["f32"]
+    assert float(torch.linalg.norm(fused - plain) / torch.linalg.norm(plain)) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ blocks, post-process
 def test_film_and_resblock_match_reference(ops, golden):
     from clip_neural_image_conpression_b200.models import FiLM, ResBlock
