@@ -125,6 +125,8 @@ def load() -> C.CDLL:
             raise ClpkError(f"libclpk.so is unavailable and could not be built: {e}") from e
         lib = C.CDLL(str(path))
         for name, (res, args) in SIGNATURES.items():
+            if override and not hasattr(lib, name):
+                continue             # A/B against an older build: entry points it lacks stay unbound
             fn = getattr(lib, name)  # AttributeError here means the .so does not match include/clpk.h
             fn.restype = res
             fn.argtypes = args

@@ -408,6 +408,27 @@ __device__ __forceinline__ uint4 affine_act8(const uint4& a, const float (&sc)[8
                     pack_op2(r[6], r[7], f16));
 }
 
+// Same transform with the SiLU evaluated on packed halves (fp16 operands only): the affine part stays fp32 (a large
+// |shift| against a small result must not cancel in half precision), then h = y/2, h + h*tanh(h) as HMUL2 +
+// MUFU.TANH.F16x2 + HFMA2 — ONE MUFU op per PAIR (the SFU pipe, 16 ops/clk/SM, is what bounds the in-kernel transform).
+__device__ __forceinline__ uint32_t silu_h2(uint32_t y2) {
+  uint32_t h, t, r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h) : "r"(y2), "r"(0x38003800u));  // * 0.5
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(h), "r"(t));
+  return r;
+}
+__device__ __forceinline__ uint4 affine_silu8_h2(const uint4& a, const float (&sc)[8], const float (&sh)[8]) {
+  const uint32_t w4[4] = {a.x, a.y, a.z, a.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[k]));
+    o[k] = silu_h2(pack_f16x2(fmaf(f.x, sc[2 * k], sh[2 * k]), fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1])));
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

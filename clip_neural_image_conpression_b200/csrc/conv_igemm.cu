@@ -48,6 +48,7 @@ struct __align__(8) PipeBarriers {
 
 struct TileCoord {
   int phase, b, h0, w0, n0;
+  int th, tw;  // tile indices (h0 / hbox, w0 / wbox)
   bool ok;  // false: the odd CTA of a pair past the last spatial tile (loads hit TMA out-of-bounds zeros, nothing stored)
 };
 
@@ -65,6 +66,8 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int item,
   r = msp / p.tiles_w;
   const int th = r % p.tiles_h;
   c.b = r / p.tiles_h;
+  c.th = th;
+  c.tw = tw;
   c.h0 = th * p.hbox;
   c.w0 = tw * p.wbox;
   c.n0 = nt * p.block_n;
@@ -77,12 +80,12 @@ constexpr int kMaxGroupChunks = 4;  // 32-column chunks one epilogue group handl
 // warp takes K = the first value it sees of a group (lane 0's first channel, broadcast) and accumulates sum(x - K),
 // sum((x - K)^2) over its 32 rows; the per-tile fold re-bases the 4 warps' sums on warp 0's K and emits the tile's
 // (mean, M2 = sum((x - mean)^2), n) triple, which the consumer combines in fp64 (Chan et al.).
-struct EpiVectors {       // laid out in smem as: float mul[block_n] | float add[block_n] | red | redk | rows
+struct EpiVectors {       // laid out in smem as: float mul[block_n] | float add[block_n] | red | xf_tab
   float* mul;
   float* add;
-  float2* red;    // [tile parity][epilogue group][chunk of the group][warp][group pair] shifted (sum, sumsq)
-  float* redk;    // same indexing: the warp's shift K
-  int* rows;      // [tile parity][epilogue group][warp] valid rows of the warp in this tile
+  // [tile parity][epilogue group][chunk of the group][warp][group pair]: the warp's shifted (sum, sumsq), its shift K and
+  // its number of valid rows — one 16-byte entry, so the per-tile fold reads one LDS.128 per warp
+  float4* red;
   float* xf_tab;  // kXform: (scale[cin] | shift[cin]) of the current image's input transform
   int nchg;       // chunks per epilogue group = ceil(block_n / 32 / kEpiGroups)
   __device__ __forceinline__ int idx(int parity, int eg, int ci, int warp) const {
@@ -92,7 +95,7 @@ struct EpiVectors {       // laid out in smem as: float mul[block_n] | float add
 static __host__ __device__ inline int red_chunks_per_group(int block_n) { return (block_n / 32 + kEpiGroups - 1) / kEpiGroups; }
 static __host__ __device__ inline int red_bytes(int block_n) {
   const int n = 2 * kEpiGroups * (red_chunks_per_group(block_n) > 0 ? red_chunks_per_group(block_n) : 1) * 4 * 8;
-  return n * (int)(sizeof(float2) + sizeof(float)) + 2 * kEpiGroups * 4 * (int)sizeof(int) + 32;
+  return n * (int)sizeof(float4);
 }
 constexpr int kWarpSlotBytes = 32 * 128;  // per-warp staging slot: 32 tile rows x 128 B (fp32) or x 64 B (16-bit)
 
@@ -136,13 +139,20 @@ constexpr int kStagingBytes = kTileM * 128;
 // 32 FADD + 32 FFMA, all indices static.  warp_reduce_scatter: folds NV values over the 32 lanes with a halving butterfly
 // (NV/2 + NV/4 + ... shuffles instead of 5*NV); afterwards lane L holds the total of value index
 // bitreverse-ordered by the lane bits consumed, see `owner` below.  Fixed tree -> deterministic.
+// redw: the warp's red entries of this chunk (one float4 per group pair); lane 0 parks the shift K and the warp's valid-row
+// count right away (nothing but the row sums is carried across the chunk's store)
 template <int P>
-__device__ __forceinline__ void row_sums(const float (&v)[32], bool valid, float (&out)[2 * P], float (&kshift)[P]) {
+__device__ __forceinline__ void row_sums(const float (&v)[32], bool valid, float nrows, int lane, float (&out)[2 * P],
+                                         float4* redw) {
   constexpr int per = 32 / P;  // >= 4: consecutive value pairs always belong to one group -> packed fp32x2 accumulators
 #pragma unroll
   for (int i = 0; i < P; ++i) {
+#ifdef CLPK_STATS_NOSHIFT   // experiment: cost of the shift itself
+    const float k = 0.f;
+#else
     const float k = __shfl_sync(0xffffffffu, v[i * per], 0);  // the warp's shift for this group (any finite value works)
-    kshift[i] = k;
+#endif
+    if (lane == 0) *reinterpret_cast<float2*>(reinterpret_cast<float*>(redw + i) + 2) = make_float2(k, nrows);
     const f32x2 kk = pack2(k, k);
     f32x2 s1 = pack2(0.f, 0.f), s2 = s1;
 #pragma unroll
@@ -192,20 +202,18 @@ __device__ __forceinline__ int scatter_owner_index(int lane) {
   return idx;
 }
 
-// phase 1 (while the chunk's values are live): per-thread shifted row sums into sums[0 .. 2P), shifts into ks[0 .. P)
+// phase 1 (while the chunk's values are live): per-thread shifted row sums into sums[0 .. 2P)
 template <int P>
-__device__ __forceinline__ void gn_row_sums(const float (&v)[32], bool valid, float (&sums)[16], float (&ks)[8]) {
-  float vals[2 * P], kk[P];
-  row_sums<P>(v, valid, vals, kk);
+__device__ __forceinline__ void gn_row_sums(const float (&v)[32], bool valid, float nrows, int lane, float (&sums)[16],
+                                            float4* redw) {
+  float vals[2 * P];
+  row_sums<P>(v, valid, nrows, lane, vals, redw);
 #pragma unroll
   for (int i = 0; i < 2 * P; ++i) sums[i] = vals[i];
-#pragma unroll
-  for (int i = 0; i < P; ++i) ks[i] = kk[i];
 }
 // phase 2 (after the chunk's store has been issued): fold over the warp's 32 rows and park the warp's partials
 template <int P>
-__device__ __forceinline__ void gn_chunk_reduce(const float (&sums)[16], const float (&ks)[8], int lane, float2* redw,
-                                                float* redkw) {
+__device__ __forceinline__ void gn_chunk_reduce(const float (&sums)[16], int lane, float4* redw) {
   float vals[2 * P];
 #pragma unroll
   for (int i = 0; i < 2 * P; ++i) vals[i] = sums[i];
@@ -215,14 +223,7 @@ __device__ __forceinline__ void gn_chunk_reduce(const float (&sums)[16], const f
   constexpr int kSteps = (P == 1) ? 1 : (P == 2) ? 2 : (P == 4) ? 3 : 4;
   const int idx = scatter_owner_index<2 * P>(lane);
   const int low_mask = (32 >> kSteps) - 1;  // lanes differing only in the untouched low bits hold duplicates
-  if ((lane & low_mask) == 0) {
-    float* f = reinterpret_cast<float*>(redw);
-    f[idx] = r;  // redw[i] = (sum_i, sumsq_i)  <->  flat index 2*i (+1)
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < P; ++i) redkw[i] = ks[i];  // (uniform across the warp)
-  }
+  if ((lane & low_mask) == 0) reinterpret_cast<float*>(redw)[4 * (idx >> 1) + (idx & 1)] = r;  // .x = sum, .y = sumsq of pair idx/2
 }
 
 constexpr int kSlabABytes = 17 * 1024;  // (128 + 2) slab rows x 128 B = 16640, padded to the 1024-byte swizzle-atom pitch
@@ -259,9 +260,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   vec_s.mul = reinterpret_cast<float*>(smem_s + (size_t)p.n_staging * kStagingBytes);
   vec_s.add = vec_s.mul + p.block_n;
   vec_s.nchg = red_chunks_per_group(p.block_n) > 0 ? red_chunks_per_group(p.block_n) : 1;
-  vec_s.red = reinterpret_cast<float2*>(vec_s.add + p.block_n);
-  vec_s.redk = reinterpret_cast<float*>(vec_s.red + 2 * kEpiGroups * vec_s.nchg * 4 * 8);
-  vec_s.rows = reinterpret_cast<int*>(vec_s.redk + 2 * kEpiGroups * vec_s.nchg * 4 * 8);
+  vec_s.red = reinterpret_cast<float4*>(vec_s.add + p.block_n);
   vec_s.xf_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(vec_s.red) + (red_bytes(p.block_n) + 63) / 64 * 64);
   const EpiVectors* vec = &vec_s;
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(reinterpret_cast<uint8_t*>(vec_s.xf_tab) +
@@ -470,6 +469,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int xt = threadIdx.x - kNumThreads;
     const int j = xt & 7, i0 = xt >> 3;
     const bool f16 = p.op_f16 != 0, act = p.ep.in_silu != 0;
+    const bool h2 = f16 && act && p.xform_h2 != 0;  // SiLU on packed halves (one MUFU op per pair)
     float* tab = vec->xf_tab;
     const uint32_t ready0 = (NCTA == 2) ? mapa_u32(smem_u32(&bars->ready[0]), 0u) : 0u;
     int cur_b = -1, stage = 0;
@@ -499,11 +499,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
           sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
           uint8_t* a = smem_a + (size_t)stage * kABytes;
-          for (int i = i0; i < p.wbox + 2; i += kXformThreads / 8) {
+          // all of the thread's rows are loaded before the first one is transformed: 9 independent LDS -> math -> STS
+          // chains in flight (a serial row loop is latency-bound at ~2x the stage's MMA time)
+          constexpr int kRowsPerThread = (kTileM + 2 + kXformThreads / 8 - 1) / (kXformThreads / 8);
+          uint4 q[kRowsPerThread];
+#pragma unroll
+          for (int r = 0; r < kRowsPerThread; ++r) {
+            const int i = i0 + r * (kXformThreads / 8);
             const int w = tc.w0 - 1 + i;
-            if (w < 0 || w >= p.grid_w) continue;
-            uint4* q = reinterpret_cast<uint4*>(a + i * 128 + ((j ^ (i & 7)) << 4));
-            *q = affine_act8(*q, sc, sh, act, f16);
+            if (i < kTileM + 2 && w >= 0 && w < p.grid_w)
+              q[r] = *reinterpret_cast<const uint4*>(a + i * 128 + ((j ^ (i & 7)) << 4));
+          }
+#pragma unroll
+          for (int r = 0; r < kRowsPerThread; ++r) {
+            const int i = i0 + r * (kXformThreads / 8);
+            const int w = tc.w0 - 1 + i;
+            if (i < kTileM + 2 && w >= 0 && w < p.grid_w)
+              *reinterpret_cast<uint4*>(a + i * 128 + ((j ^ (i & 7)) << 4)) =
+                  h2 ? affine_silu8_h2(q[r], sc, sh) : affine_act8(q[r], sc, sh, act, f16);
           }
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -601,10 +614,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           cached_key = key;
         }
         const int red_par = it & 1;
-        if (ep.gn_partial) {
-          const unsigned vm = __ballot_sync(0xffffffffu, valid);
-          if (lane == 0) vec->rows[(red_par * kEpiGroups + eg) * 4 + quarter] = __popc(vm);
-        }
+        const float nrows = ep.gn_partial ? (float)__popc(__ballot_sync(0xffffffffu, valid)) : 0.f;  // valid rows of this warp
         [[maybe_unused]] const bool tr = blockIdx.x == 0 && ew == 0 && lane == 0;  // traced warp (debug builds)
         CLPK_TRACE(tr, 100);
         mbar_wait(&bars->tmem_full[as], aphase);
@@ -614,7 +624,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int c = 32 * eg; c < p.block_n; c += cstep, ++ci) {
           uint8_t* sbuf = wslots + (size_t)slot * kWarpSlotBytes;
           uint32_t r[32];
-          float gsums[16], gks[8];
+          float gsums[16];
+          float4* redw = vec->red + vec->idx(red_par, eg, ci, quarter);
           __syncwarp();
           tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
           tmem_ld16(taddr + (uint32_t)c + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
@@ -665,10 +676,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (ep.gn_partial && !(CLPK_DBG(32))) {
               // per-thread (sum, sumsq) of this row's 32 values split by consumer-GroupNorm group; the cross-lane fold
               // happens after the chunk's store has been issued (it is off the store's critical path)
-              if (cpg >= 32) gn_row_sums<1>(v, valid, gsums, gks);
-              else if (cpg == 16) gn_row_sums<2>(v, valid, gsums, gks);
-              else if (cpg == 8) gn_row_sums<4>(v, valid, gsums, gks);
-              else gn_row_sums<8>(v, valid, gsums, gks);
+              if (cpg >= 32) gn_row_sums<1>(v, valid, nrows, lane, gsums, redw);
+              else if (cpg == 16) gn_row_sums<2>(v, valid, nrows, lane, gsums, redw);
+              else if (cpg == 8) gn_row_sums<4>(v, valid, nrows, lane, gsums, redw);
+              else gn_row_sums<8>(v, valid, nrows, lane, gsums, redw);
             }
             if (st_f32) {
 #pragma unroll
@@ -720,13 +731,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             // fold the row sums over the warp's 32 rows; the owning lanes park the warp's partials for the fixed-order
             // 4-warp fold at the end of the tile
             __syncwarp();
-            const int ri = vec->idx(red_par, eg, ci, quarter);
-            float2* redw = vec->red + ri;
-            float* redkw = vec->redk + ri;
-            if (cpg >= 32) gn_chunk_reduce<1>(gsums, gks, lane, redw, redkw);
-            else if (cpg == 16) gn_chunk_reduce<2>(gsums, gks, lane, redw, redkw);
-            else if (cpg == 8) gn_chunk_reduce<4>(gsums, gks, lane, redw, redkw);
-            else gn_chunk_reduce<8>(gsums, gks, lane, redw, redkw);
+            if (cpg >= 32) gn_chunk_reduce<1>(gsums, lane, redw);
+            else if (cpg == 16) gn_chunk_reduce<2>(gsums, lane, redw);
+            else if (cpg == 8) gn_chunk_reduce<4>(gsums, lane, redw);
+            else gn_chunk_reduce<8>(gsums, lane, redw);
           }
           CLPK_TRACE(tr, 108);
         }
@@ -744,38 +752,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           // reach after their fold.
           named_bar_sync(bar_id, 128);
           const int nch = (p.block_n - 32 * eg + cstep - 1) / cstep;
-          if (gtid < nch * npairs && tc.ok) {
-            const int fci = gtid / npairs, pr = gtid - fci * npairs;
-            // re-base the 4 warps' shifted sums on warp 0's K (exact algebra, fixed order), then the tile's triple
-            const int r0 = vec->idx(red_par, eg, fci, 0) + pr;
-            const int* rw = vec->rows + (red_par * kEpiGroups + eg) * 4;
+          // The fold duty ROTATES over the group's 4 warps (tile it -> warp it % 4): its ~200 clk of dependent latency would
+          // otherwise always delay the same warp, and the accumulator is only released when the slowest warp is done.
+          if (quarter == (it & 3) && lane < nch * npairs && tc.ok) {
+            const int fci = lane / npairs, pr = lane - fci * npairs;
+            const float4* rr = vec->red + vec->idx(red_par, eg, fci, 0) + pr;
             const float cnt = (float)(cpg >= 32 ? 32 : cpg);  // channels behind one partial of this chunk
-            // (a warp without valid rows — tile rows beyond the TMA box — is skipped: its accumulator rows, hence its K,
-            //  are whatever the uninitialised part of the A stage produced)
+            // re-base the 4 warps' shifted sums on the first valid warp's K (exact algebra, fixed order).  A warp without
+            // valid rows — tile rows beyond the TMA box — is skipped: its accumulator rows, hence its K, are whatever the
+            // uninitialised part of the A stage produced.
             float k0 = 0.f, s1 = 0.f, s2 = 0.f, n = 0.f;
             bool have = false;
 #pragma unroll
             for (int wq = 0; wq < 4; ++wq) {
-              if (rw[wq] > 0) {
-                const float2 a = vec->red[r0 + wq * 8];
-                const float kw = vec->redk[r0 + wq * 8];
-                if (!have) { k0 = kw; have = true; }
-                const float d = kw - k0;
-                const float nw = (float)rw[wq] * cnt;
+              const float4 a = rr[wq * 8];   // (sum, sumsq, K, valid rows) of warp wq
+              if (a.w > 0.f) {
+                if (!have) { k0 = a.z; have = true; }
+                const float d = a.z - k0;
+                const float nw = a.w * cnt;
                 s1 += fmaf(nw, d, a.x);
                 s2 += fmaf(nw * d, d, fmaf(2.f * d, a.x, a.y));
                 n += nw;
               }
             }
-            const float inv_n = 1.0f / n;
+            const float inv_n = __fdividef(1.0f, n);  // n is a small integer: the approximate reciprocal is within 1 ulp
             const float mean = fmaf(s1, inv_n, k0);
             const float m2 = fmaxf(fmaf(-s1 * inv_n, s1, s2), 0.f);
             const int ch = tc.n0 + 32 * eg + cstep * fci;
-            const int g = (cpg >= 32) ? ch / cpg : ch / cpg + pr;
-            const int mtile = (tc.phase * p.tiles_h + tc.h0 / p.hbox) * p.tiles_w + tc.w0 / p.wbox;
-            const int slotg = mtile * p.gn_sub + ((cpg >= 32) ? (ch % cpg) / 32 : 0);
-            reinterpret_cast<float4*>(ep.gn_partial)[((long long)tc.b * p.gn_slots + slotg) * p.gn_groups + g] =
-                make_float4(mean, m2, n, 0.f);
+            int g, sub;
+            if (cpg >= 32) {
+              if (p.gn_cpg_shift >= 0) { g = ch >> p.gn_cpg_shift; sub = (ch & (cpg - 1)) >> 5; }
+              else { g = ch / cpg; sub = (ch - g * cpg) >> 5; }
+            } else {
+              g = (ch >> p.gn_cpg_shift) + pr;   // cpg in {4, 8, 16}
+              sub = 0;
+            }
+            const int mtile = (tc.phase * p.tiles_h + tc.th) * p.tiles_w + tc.tw;
+            const int slotg = mtile * p.gn_sub + sub;
+            float2* part = reinterpret_cast<float2*>(ep.gn_partial);
+            part[((long long)tc.b * p.gn_slots + slotg) * p.gn_groups + g] = make_float2(mean, m2);
+            // element count behind every triple of this slot: geometry only, so image 0's tiles publish it for all images
+            if (tc.b == 0)
+              reinterpret_cast<float*>(part + (long long)p.batch * p.gn_slots * p.gn_groups)[slotg] = n;
           }
         }
         CLPK_TRACE(tr, 109);
@@ -1038,6 +1056,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     CLPK_REQUIRE(p.slab && igemm_xform_ok(kind, h_in, w_in, cin, cout),
                  "the fused input transform needs the row-slab mainloop (3x3 s1, W >= 128, cout <= 128, cin %% 64 == 0)");
     p.xform = 1;
+    { const char* e = getenv("CLPK_XF_H2"); p.xform_h2 = (e && atoi(e) == 0) ? 0 : 1; }
   }
   p.n_tiles_n = p.cout_pad / p.block_n;
   p.kpt = cin / p.block_k;
@@ -1122,7 +1141,9 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     // as many staging slots per epilogue group (<= 3) as the smem ring can spare without losing depth; a residual
     // epilogue keeps (slots - 1) chunk loads in flight per group, so its throughput hangs on this
     // (measured: the 256-wide CTA-pair tiles of the 64x64 / 32x32 layers prefer a 5-deep ring over a second staging slot)
-    const int want_stages = (p.block_k == 128 || p.slab) ? 3 : (p.ncta == 2 && p.block_n >= 256) ? 5 : 4;
+    int want_stages = (p.block_k == 128 || p.slab) ? 3 : (p.ncta == 2 && p.block_n >= 256) ? 5 : 4;
+    // the in-smem transform adds a third phase (fill -> normalise -> MMA) to every stage's life: one more stage in flight
+    if (p.xform) { const char* e = getenv("CLPK_XF_STAGES"); want_stages = e ? atoi(e) : 3; }
     int per_group = p.ep.resid ? 3 : 2;
     while (per_group > 1 && (kSmemBudget - fixed - kEpiGroups * per_group * kStagingBytes) / stage_bytes < want_stages) --per_group;
     { const char* e = getenv("CLPK_IGEMM_SLOTS"); if (e && atoi(e) >= 1 && atoi(e) <= 3) per_group = atoi(e); }
@@ -1140,6 +1161,9 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
                  "fused GroupNorm statistics unsupported for this conv (cout=%d cpg=%d)", cout, p.ep.gn_cpg);
     p.gn_groups = cout / p.ep.gn_cpg;
     p.gn_sub = p.ep.gn_cpg >= 32 ? p.ep.gn_cpg / 32 : 1;
+    p.gn_cpg_shift = -1;
+    for (int sft = 2; sft < 16; ++sft)
+      if ((1 << sft) == p.ep.gn_cpg) p.gn_cpg_shift = sft;
   }
   // residual sub-boxes (of 4 per chunk) the producer prefetches into L2 per tile: measured neutral-to-harmful for the
   // 3x3 convs (their per-warp look-ahead loads cover the latency), a small win for the short-K transposed conv

@@ -28,10 +28,12 @@ struct IgemmParams {
   int n_staging;            // epilogue staging buffers (128 rows x 128 B each) for the TMA-store path, 0 = direct stores
   int res_ahead;            // residual chunks the epilogue leader keeps in flight ahead of the one being processed
   int gn_groups, gn_slots, gn_sub;  // fused GroupNorm statistics: groups, partial slots per image, chunks per group slot
+  int gn_cpg_shift;         // log2(channels per partial) when that is a power of two, else -1
   int reverse;              // 1 (default; env CLPK_IGEMM_REVERSE=0 turns it off): tiles are walked from the END of the tensor —
                             // the tail of the operand is what the preceding kernel wrote last and is the likeliest L2 resident
   int xform;                // 1: input transform fused into the A path (ep.in_scale / in_shift; slab mainloop only): 4 extra
                             // warps normalise every landed slab in place before the tensor cores read it
+  int xform_h2;             // 1 (default; env CLPK_XF_H2=0 turns it off): the transform's SiLU runs on packed halves (fp16 operands)
   int smem_slack;           // bytes reserved for aligning the dynamic shared memory to 1024 (0: the base is trusted)
   int dbg;                  // perf-debug switches (env CLPK_IGEMM_DBG): 1 no epilogue memory ops, 2 no MMA, 4 no A loads, 8 no B loads
   // A-operand coordinates (5-D view of the NHWC input, see make_a_map): per (phase*taps + tap)
@@ -67,6 +69,8 @@ int direct_launch(const IgemmLaunch& L, const void* x_bf16, const void* w_packed
 
 // padded GEMM-N of a conv with `cout` output channels, and the UMMA N tile chosen for it
 int igemm_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg);  // <= 0: unsupported
+// floats of a gn_partial buffer: batch * slots * pieces (mean, M2) pairs followed by `slots` element counts
+inline long long igemm_gn_partial_floats(int batch, int slots, int pieces) { return 2ll * batch * slots * pieces + slots; }
 int igemm_cout_pad(int cout);
 // can a conv of this geometry apply ep.in_scale / in_shift to its A operand in shared memory (row-slab mainloop)?
 bool igemm_xform_ok(int kind, int h_in, int w_in, int cin, int cout);

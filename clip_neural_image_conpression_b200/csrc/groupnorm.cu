@@ -206,25 +206,28 @@ __device__ __forceinline__ void gn_affine8(const float* __restrict__ gamma, cons
 }
 
 
-// Folds the per-tile (mean, M2, n) triples a conv epilogue wrote (conv_igemm.cu, "Fused GroupNorm statistics") into
-// (mean, rstd) of group g of image b; executed by one whole warp (lanes stride over the entries, fixed-order shuffle
-// tree -> deterministic).  partial[b][slot][piece]: `pieces` triples per slot, group g owns pieces [g*m, (g+1)*m),
-// m = pieces / groups (m > 1: group sizes such as 24 or 48 that the epilogue sums in 8- or 16-channel pieces).
-// Combination (Chan et al.) relative to the FIRST triple's mean m0, so every accumulated term is of the order of the
-// spread of the tile means (fp32 is ample; fp64 would cost ~7 DFMA-class ops per entry in every block's prologue):
+// Folds the per-tile statistics a conv epilogue wrote (conv_igemm.cu, "Fused GroupNorm statistics") into (mean, rstd)
+// of group g of image b; executed by one whole warp (lanes stride over the entries, fixed-order shuffle tree ->
+// deterministic).  partial[b][slot][piece] = (tile mean, tile M2): `pieces` pairs per slot, group g owns pieces
+// [g*m, (g+1)*m), m = pieces / groups (m > 1: group sizes such as 24 or 48 that the epilogue sums in 8- or 16-channel
+// pieces); counts[slot] = elements behind every pair of that slot (geometry only, shared by all images).
+// Combination (Chan et al.) relative to the FIRST pair's mean m0, so every accumulated term is of the order of the spread
+// of the tile means (fp32 is ample):
 //   N = sum n, A = sum n (mean_i - m0), Q = sum n (mean_i - m0)^2, M = sum M2_i
-//   mean = m0 + A / N,   var = (M + Q - A^2 / N) / N      (final scalar arithmetic in fp64)
-__device__ __forceinline__ float2 gn_fold_partials(const float4* __restrict__ partial, int b, int g, int slots, int pieces,
-                                                   int groups, float eps, int lane) {
+//   mean = m0 + A / N,   var = (M + Q - A^2 / N) / N
+__device__ __forceinline__ float2 gn_fold_partials(const float2* __restrict__ partial, const float* __restrict__ counts,
+                                                   int b, int g, int slots, int pieces, int groups, float eps, int lane) {
   const int m = pieces / groups;
-  const float4* pp = partial + (long long)b * slots * pieces + g * m;
+  const float2* pp = partial + (long long)b * slots * pieces + g * m;
   const float m0 = __ldg(pp).x;
   float A = 0.f, Q = 0.f, M = 0.f, N = 0.f;
+#pragma unroll 4
   for (int k = lane; k < slots * m; k += 32) {
     const int slot = k / m, j = k - slot * m;
-    const float4 v = __ldg(pp + (long long)slot * pieces + j);
-    const float d = v.x - m0, nd = v.z * d;
-    A += nd; Q = fmaf(nd, d, Q); M += v.y; N += v.z;
+    const float2 v = __ldg(pp + (long long)slot * pieces + j);
+    const float n = __ldg(counts + slot);
+    const float d = v.x - m0, nd = n * d;
+    A += nd; Q = fmaf(nd, d, Q); M += v.y; N += n;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -233,17 +236,15 @@ __device__ __forceinline__ float2 gn_fold_partials(const float4* __restrict__ pa
     M += __shfl_xor_sync(0xffffffffu, M, o);
     N += __shfl_xor_sync(0xffffffffu, N, o);
   }
-  const double n = (double)N, a = (double)A;
-  const double mean = (double)m0 + a / n;
-  double var = ((double)M + ((double)Q - a * a / n)) / n;
-  if (var < 0.0) var = 0.0;
-  return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  const float inv_n = 1.0f / N, dm = A * inv_n;
+  const float var = fmaxf((M + fmaf(-A, dm, Q)) * inv_n, 0.f);
+  return make_float2(m0 + dm, 1.0f / sqrtf(var + eps));
 }
 
 template <bool kIn16, bool kHoist>
 __global__ void __launch_bounds__(kGnThreads, 4)
 gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float2* __restrict__ stats, const float4* __restrict__ partial, int slots, int pieces, double n_per_group,
+                const float2* __restrict__ stats, const float2* __restrict__ partial, int slots, int pieces, double n_per_group,
                 float eps, uint16_t* __restrict__ y, int hw, int c, int groups, int silu, int op_f16) {
   __shared__ float2 st_s[32];
   pdl_prologue_done();
@@ -252,7 +253,8 @@ gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, c
   if (partial) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int g = warp; g < groups; g += kGnThreads / 32) {
-      const float2 st = gn_fold_partials(partial, b, g, slots, pieces, groups, eps, lane);
+      const float* counts = reinterpret_cast<const float*>(partial + (long long)gridDim.y * slots * pieces);
+      const float2 st = gn_fold_partials(partial, counts, b, g, slots, pieces, groups, eps, lane);
       if (lane == 0) st_s[g] = st;
     }
   } else {
@@ -290,25 +292,27 @@ gn_apply_kernel(const void* __restrict__ xin, const float* __restrict__ gamma, c
 
 // Folds per-tile partial sums produced by a conv epilogue: partial[b][slots][groups] (sum, sum of squares) ->
 // stats[b][g] = (mean, rstd).  One warp per (image, group); lanes stride over the slots, fp64 shuffle tree: deterministic.
-__global__ void gn_finalize_kernel(const float4* __restrict__ partial, float2* __restrict__ stats, int slots, int groups,
+__global__ void gn_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stats, int slots, int groups,
                                    float eps) {
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= groups) return;
-  const float2 st = gn_fold_partials(partial, b, g, slots, groups, groups, eps, lane);
+  const float* counts = reinterpret_cast<const float*>(partial + (long long)gridDim.x * slots * groups);
+  const float2 st = gn_fold_partials(partial, counts, b, g, slots, groups, groups, eps, lane);
   if (lane == 0) stats[(long long)b * groups + g] = st;
 }
 
 // partial -> per-(image, channel) affine form of GroupNorm for convs that normalise their own A operand
 // (clpk_conv_epilogue.in_scale / in_shift): one block per image, one warp per group.
-__global__ void gn_affine_kernel(const float4* __restrict__ partial, const float* __restrict__ gamma,
+__global__ void gn_affine_kernel(const float2* __restrict__ partial, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
                                  int slots, int pieces, int groups, int c, float eps) {
   pdl_prologue_done();
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= groups) return;
-  const float2 st = gn_fold_partials(partial, b, g, slots, pieces, groups, eps, lane);
+  const float* counts = reinterpret_cast<const float*>(partial + (long long)gridDim.x * slots * pieces);
+  const float2 st = gn_fold_partials(partial, counts, b, g, slots, pieces, groups, eps, lane);
   const int cpg = c / groups;
   for (int k = lane; k < cpg; k += 32) {
     const int ch = g * cpg + k;
@@ -318,7 +322,7 @@ __global__ void gn_affine_kernel(const float4* __restrict__ partial, const float
   }
 }
 
-int launch_gn_affine(const float4* partial, const float* gamma, const float* beta, float* scale, float* shift, int batch,
+int launch_gn_affine(const float2* partial, const float* gamma, const float* beta, float* scale, float* shift, int batch,
                      int slots, int pieces, int groups, int c, float eps, cudaStream_t stream) {
   CLPK_REQUIRE(groups > 0 && groups <= 32 && c % groups == 0 && pieces % groups == 0, "GroupNorm affine: bad group layout");
   CLPK_CHECK_CUDA(launch_kernel_pdl(gn_affine_kernel, dim3(batch), dim3(32 * groups), 0, stream, partial, gamma, beta, scale,
@@ -327,7 +331,7 @@ int launch_gn_affine(const float4* partial, const float* gamma, const float* bet
   return CLPK_OK;
 }
 
-int launch_gn_finalize(const float4* partial, float2* stats, int batch, int slots, int groups, float eps,
+int launch_gn_finalize(const float2* partial, float2* stats, int batch, int slots, int groups, float eps,
                        cudaStream_t stream) {
   CLPK_REQUIRE(groups <= 32, "GroupNorm finalize supports <= 32 groups");
   gn_finalize_kernel<<<batch, 32 * groups, 0, stream>>>(partial, stats, slots, groups, eps);
@@ -337,7 +341,7 @@ int launch_gn_finalize(const float4* partial, float2* stats, int batch, int slot
 
 // x: fp32 NHWC (x_is_16 == 0) or 16-bit NHWC in the operand format.  Exactly one of stats / partial is used.
 int launch_gn_apply_ex(const void* x, int x_is_16, const float* gamma, const float* beta, const float2* stats,
-                       const float4* partial, int slots, int pieces, double n_per_group, float eps, void* y_op,
+                       const float2* partial, int slots, int pieces, double n_per_group, float eps, void* y_op,
                        const GnShape& s,
                        int silu, int op_dtype, cudaStream_t stream) {
   const long long octs = (long long)s.hw * (s.c / 8);
@@ -434,7 +438,7 @@ extern "C" int clpk_groupnorm_finalize(const void* partial, void* stats, int bat
                                        double n_per_group, float eps, void* stream) {
   CLPK_REQUIRE(partial && stats && batch > 0 && slots > 0 && groups > 0 && n_per_group > 0,
                "clpk_groupnorm_finalize: bad arguments");
-  return launch_gn_finalize(reinterpret_cast<const float4*>(partial), reinterpret_cast<float2*>(stats), batch, slots,
+  return launch_gn_finalize(reinterpret_cast<const float2*>(partial), reinterpret_cast<float2*>(stats), batch, slots,
                             groups, eps, (cudaStream_t)stream);
 }
 
@@ -442,7 +446,7 @@ extern "C" int clpk_groupnorm_affine(const void* partial, const float* gamma, co
                                      int batch, int slots, int pieces, int groups, int c, float eps, void* stream) {
   CLPK_REQUIRE(partial && gamma && beta && scale && shift && batch > 0 && slots > 0 && pieces > 0 && groups > 0 && c > 0,
                "clpk_groupnorm_affine: bad arguments");
-  return launch_gn_affine(reinterpret_cast<const float4*>(partial), gamma, beta, scale, shift, batch, slots, pieces, groups,
+  return launch_gn_affine(reinterpret_cast<const float2*>(partial), gamma, beta, scale, shift, batch, slots, pieces, groups,
                           c, eps, (cudaStream_t)stream);
 }
 

@@ -37,12 +37,12 @@ long long gn_ws_bytes(const GnShape& s);
 int launch_groupnorm(const float* x, const float* gamma, const float* beta, void* y_op, void* ws, const GnShape& s,
                      float eps, int silu, int op_dtype, cudaStream_t stream);
 int launch_gn_stats(const float* x, void* ws, const GnShape& s, float eps, const float2** stats_out, cudaStream_t stream);
-int launch_gn_finalize(const float4* partial, float2* stats, int batch, int slots, int groups, float eps,
+int launch_gn_finalize(const float2* partial, float2* stats, int batch, int slots, int groups, float eps,
                        cudaStream_t stream);
-int launch_gn_affine(const float4* partial, const float* gamma, const float* beta, float* scale, float* shift, int batch,
+int launch_gn_affine(const float2* partial, const float* gamma, const float* beta, float* scale, float* shift, int batch,
                      int slots, int pieces, int groups, int c, float eps, cudaStream_t stream);
 int launch_gn_apply_ex(const void* x, int x_is_16, const float* gamma, const float* beta, const float2* stats,
-                       const float4* partial, int slots, int pieces, double n_per_group, float eps, void* y_op,
+                       const float2* partial, int slots, int pieces, double n_per_group, float eps, void* y_op,
                        const GnShape& s, int silu, int op_dtype, cudaStream_t stream);
 int launch_gn_apply(const float* x, const float* gamma, const float* beta, const float2* stats, void* y_op,
                     const GnShape& s, int silu, int op_dtype, cudaStream_t stream);

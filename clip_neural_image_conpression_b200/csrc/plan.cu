@@ -36,7 +36,7 @@ struct GnPlan {
   int level = 0, silu = 1;
   float *gamma = nullptr, *beta = nullptr;
   float2* stats = nullptr;    // [B][groups] (mean, rstd)
-  float4* partial = nullptr;  // [B][slots][pieces] (mean, M2, n, -) per tile, written by the producer conv
+  float2* partial = nullptr;  // [B][slots][pieces] (mean, M2) per tile + [slots] element counts, written by the producer conv
   int slots = 0;
   int piece = 0, pieces = 0;  // channels per partial sum the producer epilogue emits, and their number (C / piece)
   bool fused = false;
@@ -56,11 +56,21 @@ struct ResBlockPlan {
   bool y16 = false;        // conv1 output kept in the 16-bit operand format (needs fused GroupNorm statistics)
 };
 
-// GroupNorm fusion switches (env CLPK_FUSE_GN, bit mask, default 3): 1 = norm2 + SiLU of a ResBlock applied inside conv2
-// (row-slab levels), 2 = out_norm applied inside the `out` conv, fed by a 16-bit-only transposed-conv output.
+// GroupNorm-in-consumer switches (env CLPK_FUSE_GN, bit mask, default 0): 1 = norm2 + SiLU of a ResBlock applied inside
+// conv2 (row-slab levels), 2 = out_norm applied inside the `out` conv.  Correct (tests/test_gpu_unet.py,
+// test_gpu_kernels.py) but OFF by default: measured on B200 the in-smem transform costs more than the stand-alone
+// GroupNorm pass it removes — the slab mainloop already spends ~3/4 of the shared-memory bandwidth on operand reads
+// (every A byte is read by 3 taps), and the extra read + write of each slab stretches a stage from ~770 to ~2400 clk
+// (DESIGN.md section 9).
 static int fuse_gn_mask() {
   const char* e = getenv("CLPK_FUSE_GN");
-  return e ? atoi(e) : 3;
+  return e ? atoi(e) : 0;
+}
+// env CLPK_HEAD16 (default 1): the last transposed conv, whose result only out_norm reads, stores just the 16-bit copy
+// (statistics still come from its fp32 accumulators) and out_norm reads 2 B instead of 4 B per element.
+static bool head16_on() {
+  const char* e = getenv("CLPK_HEAD16");
+  return !(e && atoi(e) == 0);
 }
 
 }  // namespace clpk
@@ -101,6 +111,7 @@ struct clpk_plan {
   uint16_t* T = nullptr;     // GroupNorm+SiLU output = conv A operand (fp16 or bf16, cfg.op_dtype)
   std::vector<uint16_t*> X16;  // per level: 16-bit copy of X[l]
   bool fuse_head = false;    // out_norm applied inside the `out` conv (see fuse_gn_mask)
+  bool head16 = false;       // the last transposed conv writes only the 16-bit copy X16[0] (see head16_on)
   bool x16_gn = false;       // env CLPK_X16=1: GroupNorms on the residual stream read X16 instead of fp32 X
   float* Yf = nullptr;       // fp32 conv1 output, only for ResBlocks whose GroupNorm statistics cannot be fused
   void* gn_ws = nullptr;
@@ -264,7 +275,11 @@ int setup_gn(clpk_plan* P, GnPlan* gn, int producer_kind, int prod_h_in, int pro
   gn->pieces = piece > 0 ? c / piece : 0;
   gn->slots = (producer_kind >= 0 && piece > 0) ? igemm_gn_slots(producer_kind, prod_h_in, prod_w_in, c, piece) : 0;
   gn->fused = gn->slots > 0;
-  if (gn->fused) CLPK_TRY(P->alloc(&gn->partial, (long long)P->B * gn->slots * gn->pieces));
+  if (gn->fused) {
+    float* buf = nullptr;
+    CLPK_TRY(P->alloc(&buf, igemm_gn_partial_floats(P->B, gn->slots, gn->pieces) + 2));
+    gn->partial = reinterpret_cast<float2*>(buf);
+  }
   return CLPK_OK;
 }
 
@@ -330,7 +345,8 @@ int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s) {
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
     CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->ups[l].L, s));  // X16[l+1] -> X[l] += convT (unet.py:102-104)
   }
-  CLPK_TRY(run_groupnorm_x(P, 0, P->out_gn, s));                   // out_norm, no activation (unet.py:105)
+  if (P->head16) CLPK_TRY(run_groupnorm(P, P->X16[0], 1, P->out_gn, s));  // out_norm on the 16-bit transposed-conv output
+  else CLPK_TRY(run_groupnorm_x(P, 0, P->out_gn, s));              // out_norm, no activation (unet.py:105)
   CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->out_conv.L, s));  // -> eps_buf (NCHW)
   return CLPK_OK;
 }
@@ -497,6 +513,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   gn_after_up[0] = &P->out_gn;
   P->fuse_head = (fuse_gn_mask() & 2) && P->out_gn.fused && !P->x16_gn &&
                  igemm_xform_ok(CLPK_CONV_3X3_S1, height, width, cfg->base, cfg->img_ch);
+  P->head16 = P->fuse_head || (head16_on() && P->out_gn.fused && !P->x16_gn && cfg->base % 32 == 0);
   if (P->fuse_head) {
     P->out_gn.in_consumer = true;
     CLPK_TRY(P->alloc(&P->out_gn.scale, (long long)batch * cfg->base));
@@ -566,7 +583,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     eu.resid = P->X[l];  // skip connection, added in place
     eu.out_f32 = P->X[l];
     eu.out_op = P->x16_gn ? P->X16[l] : nullptr;
-    if (l == 0 && P->fuse_head) {
+    if (l == 0 && P->head16) {
       // the last transposed conv's result is read by out_norm only: keep just the 16-bit copy (its GroupNorm statistics
       // still come from the fp32 accumulators), which the `out` conv normalises in shared memory
       eu.out_f32 = nullptr;
@@ -839,7 +856,7 @@ extern "C" int clpk_plan_groupnorm_bytes(const clpk_plan* P, double* bytes) {
     if (!rb.gn1.in_consumer) tot += n * (in_bytes_x(rb.gn1) + 2.0);
     if (!rb.gn2.in_consumer) tot += n * ((rb.y16 ? 2.0 : 4.0) + 2.0);
   }
-  if (!P->out_gn.in_consumer) tot += (double)P->B * P->H * P->W * P->cfg.base * (in_bytes_x(P->out_gn) + 2.0);
+  if (!P->out_gn.in_consumer) tot += (double)P->B * P->H * P->W * P->cfg.base * ((P->head16 ? 2.0 : in_bytes_x(P->out_gn)) + 2.0);
   *bytes = tot;
   return CLPK_OK;
 }

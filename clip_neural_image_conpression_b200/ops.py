@@ -212,7 +212,8 @@ def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout:
         slots = int(_lib.load().clpk_conv_gn_slots(kind, h, w, cout, cpg))
         if slots <= 0:
             raise ValueError(f"fused GroupNorm statistics unsupported for cout={cout}, groups={gn_groups}")
-        partial = torch.zeros((b, slots, gn_groups, 4), dtype=torch.float32, device=dev)
+        # [b][slots][groups] (tile mean, tile M2) pairs followed by [slots] element counts (see include/clpk.h)
+        partial = torch.zeros(2 * b * slots * gn_groups + slots, dtype=torch.float32, device=dev)
     _conv("clpk_conv_igemm" if impl == "igemm" else "clpk_conv_direct", x_nhwc_op, w_packed, kind, cout, bias,
           film_scale1p, film_shift, _f32c(resid) if resid is not None else None, outs.get("f32"), outs.get("op"),
           outs.get("nchw"), partial, cpg, in_affine)
@@ -231,15 +232,17 @@ def conv_in_affine_supported(kind: int, h: int, w: int, cin: int, cout: int) -> 
 
 
 @on_tensor_device
-def groupnorm_affine(partial: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float = 1e-5):
-    """Per-tile conv statistics [B, slots, pieces, 4] -> (scale, shift) [B, C] of GroupNorm(groups) in affine form."""
+def groupnorm_affine(partial: torch.Tensor, batch: int, slots: int, gamma: torch.Tensor, beta: torch.Tensor, groups: int,
+                     eps: float = 1e-5):
+    """Per-tile conv statistics (the flat "gn_partial" buffer of conv_igemm(..., return_partial=True)) -> (scale, shift)
+    [B, C] of GroupNorm(groups) in affine form."""
     require_cuda(partial, gamma, beta)
-    b, slots, pieces, _ = partial.shape
     c = gamma.numel()
-    scale = torch.empty((b, c), dtype=torch.float32, device=partial.device)
+    pieces = (partial.numel() - slots) // (2 * batch * slots)
+    scale = torch.empty((batch, c), dtype=torch.float32, device=partial.device)
     shift = torch.empty_like(scale)
-    check(_lib.load().clpk_groupnorm_affine(ptr(partial), ptr(_f32c(gamma)), ptr(_f32c(beta)), ptr(scale), ptr(shift), b, slots,
-                                            pieces, groups, c, eps, stream_ptr()), "clpk_groupnorm_affine")
+    check(_lib.load().clpk_groupnorm_affine(ptr(partial), ptr(_f32c(gamma)), ptr(_f32c(beta)), ptr(scale), ptr(shift), batch,
+                                            slots, pieces, groups, c, eps, stream_ptr()), "clpk_groupnorm_affine")
     return scale, shift
 
 

@@ -94,9 +94,9 @@ int clpk_groupnorm_silu(const float* x_nhwc_dev, const float* gamma_dev, const f
                         void* stream);
 
 /* The two halves of clpk_groupnorm_silu for producers that already emitted per-tile statistics (conv epilogue):
- * finalize: partial[b][slots][groups] float4 (tile mean, tile M2 = sum (x - mean)^2, tile element count n, unused) ->
- * stats[b][groups] float2 (mean, rstd), biased variance, combined in fp64 with the parallel-variance formula (robust for
- * |mean| >> std like torch's Welford pass; n_per_group is informational, the counts come from the triples);
+ * finalize: the gn_partial buffer of clpk_conv_epilogue (layout there) -> stats[b][groups] float2 (mean, rstd), biased
+ * variance, tiles combined with the parallel-variance formula (robust for |mean| >> std like torch's Welford pass;
+ * n_per_group is informational, the counts come from the buffer);
  * apply: y = (x - mean) * rstd * gamma + beta [SiLU] in the 16-bit operand format. */
 int clpk_groupnorm_finalize(const void* partial_dev, void* stats_dev, int batch, int slots, int groups,
                             double n_per_group, float eps, void* stream);
@@ -131,10 +131,11 @@ typedef struct clpk_conv_epilogue {
   void* out_op;               /* dev NHWC 16-bit (op_dtype) or NULL */
   float* out_nchw;            /* dev NCHW fp32 or NULL            */
   int cout_valid;             /* channels really present (<= cout_pad) */
-  /* Fused GroupNorm statistics of the FINAL output values (after bias / FiLM / residual): per-tile triples
-   * gn_partial[b][slot][g] = float4 (mean, M2, n, -) accumulated as shifted sums in the epilogue, slots =
-   * clpk_conv_gn_slots(...), g < cout / gn_cpg.  Fold them with clpk_groupnorm_finalize.  NULL = off.
-   * Needs an NHWC output and gn_cpg in {4, 8, 16} or a multiple of 32. */
+  /* Fused GroupNorm statistics of the FINAL output values (after bias / FiLM / residual), accumulated in the epilogue as
+   * shifted sums.  gn_partial = float buffer of 2 * batch * slots * groups + slots elements, slots =
+   * clpk_conv_gn_slots(...), groups = cout / gn_cpg:  [b][slot][g] float2 (tile mean, tile M2 = sum (x - mean)^2) followed
+   * by [slot] float element counts (geometry only, identical for every image).  Fold with clpk_groupnorm_finalize or
+   * clpk_groupnorm_affine.  NULL = off.  Needs an NHWC output and gn_cpg in {4, 8, 16} or a multiple of 32. */
   void* gn_partial;
   int gn_cpg;
   /* Input transform fused into the A-operand path — the consumer-side half of GroupNorm [+ SiLU] (blocks.py:41,43;

@@ -335,7 +335,7 @@ def test_groupnorm_affine_from_conv_statistics(ops):
     b1, b2 = (torch.randn(c, generator=g) + 3.0).cuda(), torch.randn(c, generator=g).cuda()
     gamma, beta = (1 + 0.1 * torch.randn(c, generator=g)).cuda(), (0.1 * torch.randn(c, generator=g)).cuda()
     o1 = ops.conv_igemm(x16, ops.pack_conv_weight(w1, 0), 0, c, b1, want_f32=True, want_op=True, gn_groups=8, return_partial=True)
-    sc, sh = ops.groupnorm_affine(o1["gn_partial"], gamma, beta, 8)
+    sc, sh = ops.groupnorm_affine(o1["gn_partial"], b, o1["gn_slots"], gamma, beta, 8)
     mean, rstd = o1["gn_stats"][..., 0], o1["gn_stats"][..., 1]
     np.testing.assert_allclose(sc.cpu().numpy(), (rstd.repeat_interleave(c // 8, dim=1) * gamma).cpu().numpy(), rtol=1e-6)
     np.testing.assert_allclose(sh.cpu().numpy(), (beta - mean.repeat_interleave(c // 8, dim=1) * rstd.repeat_interleave(c // 8, dim=1) * gamma).cpu().numpy(),

@@ -254,20 +254,25 @@ def test_ddim_250_steps_stochastic_graph_loop(oracle, golden):
 
 
 def test_fused_groupnorm_paths_match_unfused(oracle, monkeypatch):
-    """CLPK_FUSE_GN (default 3): norm2 + SiLU inside conv2 and out_norm inside the `out` conv (row-slab levels, W >= 128)
-    against the same plan with the stand-alone GroupNorm passes (CLPK_FUSE_GN=0), and both against the fp32 oracle."""
+    """CLPK_FUSE_GN=3 (opt-in, see plan.cu): norm2 + SiLU inside conv2 and out_norm inside the `out` conv (row-slab levels,
+    W >= 128) against the default plan with the stand-alone GroupNorm passes, and both against the fp32 oracle."""
     cfg = dict(z_dim=512, base=64, ch_mult=(1, 2))
     g = torch.Generator().manual_seed(4)
     x = torch.randn(2, 3, 128, 128, generator=g)
     z = torch.nn.functional.normalize(torch.randn(2, 512, generator=g), dim=-1)
     t = torch.tensor([999, 250])
     net, sd = make_net(oracle, cfg, seed=5)
+    monkeypatch.setenv("CLPK_FUSE_GN", "3")
     fused = net(x.cuda(), z.cuda(), t.cuda()).cpu()
     monkeypatch.setenv("CLPK_FUSE_GN", "0")
+    monkeypatch.setenv("CLPK_HEAD16", "0")
     net.release_plans()
     plain = net(x.cuda(), z.cuda(), t.cuda()).cpu()
     monkeypatch.delenv("CLPK_FUSE_GN")
+    monkeypatch.delenv("CLPK_HEAD16")
     net.release_plans()
+    head16 = net(x.cuda(), z.cuda(), t.cuda()).cpu()              # the default plan: 16-bit-only transposed-conv output
+    assert oracle.rel_l2(head16, plain) < 2e-3 and not torch.equal(head16, plain)
     assert not torch.equal(fused, plain)                         # the switch really changes the executed path
     with torch.no_grad():
         ref = oracle.unet_forward(sd, cfg["ch_mult"], x, z, t)
