@@ -54,18 +54,23 @@ struct TileCoord {
 
 // Work item -> tile.  Order (fastest first): channel tile, transposed-conv phase, spatial tile (pair).  Keeping the 4
 // phases of one spatial tile adjacent in time lets their interleaved output rows meet in L2 before they reach HBM.
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) {
+  return (uint32_t)(((unsigned long long)n * f.mul) >> f.shift);
+}
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int item, int rank) {
   TileCoord c;
   if (p.reverse) item = p.num_tiles - 1 - item;  // walk the tensor back to front (see IgemmParams::reverse)
-  const int nt = item % p.n_tiles_n;
-  int r = item / p.n_tiles_n;
-  c.phase = r % p.phases;
-  const int msp = (r / p.phases) * p.ncta + rank;
-  c.ok = msp < p.spatial_tiles;
-  const int tw = msp % p.tiles_w;
-  r = msp / p.tiles_w;
-  const int th = r % p.tiles_h;
-  c.b = r / p.tiles_h;
+  uint32_t r = fd_div((uint32_t)item, p.fd_tiles_n);
+  const int nt = item - (int)r * p.n_tiles_n;
+  const uint32_t q = fd_div(r, p.fd_phases);
+  c.phase = (int)(r - q * (uint32_t)p.phases);
+  const uint32_t msp = q * (uint32_t)p.ncta + (uint32_t)rank;
+  c.ok = (int)msp < p.spatial_tiles;
+  r = fd_div(msp, p.fd_tiles_w);
+  const int tw = (int)(msp - r * (uint32_t)p.tiles_w);
+  const uint32_t b = fd_div(r, p.fd_tiles_h);
+  const int th = (int)(r - b * (uint32_t)p.tiles_h);
+  c.b = (int)b;
   c.th = th;
   c.tw = tw;
   c.h0 = th * p.hbox;
@@ -568,6 +573,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int cstep = 32 * kEpiGroups;
     const int cpg = ep.gn_cpg;
     const int npairs = cpg >= 32 ? 1 : (cpg > 0 ? 32 / cpg : 0);
+    const int npairs_shift = npairs >= 8 ? 3 : npairs >= 4 ? 2 : npairs >= 2 ? 1 : 0;
     int ld_tile = cluster_id, ld_c = 32 * eg;
     uint32_t ld_slot = 0;
     int lc_tile = -1;
@@ -755,7 +761,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           // The fold duty ROTATES over the group's 4 warps (tile it -> warp it % 4): its ~200 clk of dependent latency would
           // otherwise always delay the same warp, and the accumulator is only released when the slowest warp is done.
           if (quarter == (it & 3) && lane < nch * npairs && tc.ok) {
-            const int fci = lane / npairs, pr = lane - fci * npairs;
+            const int fci = lane >> npairs_shift, pr = lane & (npairs - 1);   // npairs is 1, 2, 4 or 8
             const float4* rr = vec->red + vec->idx(red_par, eg, fci, 0) + pr;
             const float cnt = (float)(cpg >= 32 ? 32 : cpg);  // channels behind one partial of this chunk
             // re-base the 4 warps' shifted sums on the first valid warp's K (exact algebra, fixed order).  A warp without
@@ -1121,6 +1127,10 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   const long long nt = (long long)((p.spatial_tiles + p.ncta - 1) / p.ncta) * p.phases * p.n_tiles_n;
   CLPK_REQUIRE(nt < (1ll << 30), "too many tiles");
   p.num_tiles = (int)nt;
+  p.fd_tiles_n = make_fastdiv(p.n_tiles_n);
+  p.fd_phases = make_fastdiv(p.phases);
+  p.fd_tiles_w = make_fastdiv(p.tiles_w);
+  p.fd_tiles_h = make_fastdiv(p.tiles_h);
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
   const int stage_bytes = p.slab ? kSlabABytes + 3 * (p.block_n / p.ncta) * 128

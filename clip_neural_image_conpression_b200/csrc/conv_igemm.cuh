@@ -6,6 +6,23 @@ namespace clpk {
 
 constexpr int kMaxTapEntries = 16;  // 9 taps (3x3) or 4 phases x 4 taps (ConvTranspose 4x4 s2)
 
+// Division by a launch-time constant as multiply + shift (exact for 0 <= n < 2^31): q = (n * mul) >> shift with
+// mul = ceil(2^(31 + s) / d), s = ceil(log2 d), shift = 31 + s.  The tile decoder runs in every warp for every tile; four
+// hardware-less integer divisions there were ~150 of the ~240 instructions a warp spends per tile outside its chunks.
+struct FastDiv {
+  uint32_t mul, shift, d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  uint32_t s = 0;
+  while ((1u << s) < (uint32_t)d) ++s;
+  const unsigned long long num = 1ull << (31 + s);
+  f.mul = (uint32_t)((num + (unsigned long long)d - 1) / (unsigned long long)d);
+  f.shift = 31 + s;
+  f.d = (uint32_t)d;
+  return f;
+}
+
 // Everything the kernels need, passed by value.
 struct IgemmParams {
   // tile grid: output pixels for the 3x3 convs, INPUT pixels for the transposed conv (each phase maps them 1:1)
@@ -31,6 +48,7 @@ struct IgemmParams {
   int gn_cpg_shift;         // log2(channels per partial) when that is a power of two, else -1
   int reverse;              // 1 (default; env CLPK_IGEMM_REVERSE=0 turns it off): tiles are walked from the END of the tensor —
                             // the tail of the operand is what the preceding kernel wrote last and is the likeliest L2 resident
+  FastDiv fd_tiles_n, fd_phases, fd_tiles_w, fd_tiles_h;  // decode_tile divisors
   int xform;                // 1: input transform fused into the A path (ep.in_scale / in_shift; slab mainloop only): 4 extra
                             // warps normalise every landed slab in place before the tensor cores read it
   int xform_h2;             // 1 (default; env CLPK_XF_H2=0 turns it off): the transform's SiLU runs on packed halves (fp16 operands)

@@ -129,6 +129,10 @@ struct clpk_plan {
   bool any_sigma = false;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
+  // The per-step conditioning (cond_combine + the FiLM GEMV of all ResBlocks, ~22 us) does not depend on the stem, so the
+  // DDIM step forks it onto a side stream and joins before the first ResBlock (a parallel branch of the captured graph).
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t cap_stream = nullptr;  // private stream used only to capture the step graph (the caller's stream may be
                                       // the legacy default stream, which cannot be captured)
   // optional per-launch timing (clpk_plan_profile_forward): event pairs around every launch, tagged by class
@@ -325,13 +329,14 @@ int run_resblock(clpk_plan* P, ResBlockPlan& rb, cudaStream_t s) {
 }
 
 // everything after the conditioning vector: in_conv ... out   (unet.py:88-105).  film = [B, film_n].
-int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s) {
+int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s, cudaEvent_t cond_ready = nullptr) {
   const clpk_unet_config& c = P->cfg;
   P->prof_mark(kProfConvIn, s);  // stem (unet.py:88): im2col columns + pointwise GEMM on the tensor cores
   int src = launch_stem_im2col(x_nchw, P->stem_cols, P->B, c.img_ch, P->H, P->W, c.op_dtype, s);
   if (src == CLPK_OK) src = igemm_launch(P->stem.L, s);
   P->prof_mark(-1, s);
   if (src != CLPK_OK) return src;
+  if (cond_ready) CLPK_CHECK_CUDA(cudaStreamWaitEvent(s, cond_ready, 0));  // FiLM table (side stream) before the first conv1
   size_t r = 0;
   for (int l = 0; l < P->n_levels; ++l) {
     CLPK_TRY(run_resblock(P, P->rbs[r++], s));
@@ -366,6 +371,9 @@ extern "C" void clpk_plan_destroy(clpk_plan* P) {
   if (P->graph_exec) cudaGraphExecDestroy(P->graph_exec);
   if (P->graph) cudaGraphDestroy(P->graph);
   if (P->cap_stream) cudaStreamDestroy(P->cap_stream);
+  if (P->side_stream) cudaStreamDestroy(P->side_stream);
+  if (P->ev_fork) cudaEventDestroy(P->ev_fork);
+  if (P->ev_join) cudaEventDestroy(P->ev_join);
   for (cudaEvent_t e : P->prof_ev) cudaEventDestroy(e);
   for (void* q : P->allocs) cudaFree(q);
   if (P->ht_tab) cudaFree(P->ht_tab);
@@ -641,6 +649,9 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   P->launches_fwd = 5 + 2 + (int)P->rbs.size() * 2 + 2 * L + 1;  // + one or two launches per GroupNorm:
   for (const ResBlockPlan& rb : P->rbs) P->launches_fwd += (rb.gn1.fused ? 1 : 2) + (rb.gn2.fused ? 1 : 2);
   P->launches_fwd += P->out_gn.fused ? 1 : 2;
+  CLPK_CHECK_CUDA(cudaStreamCreateWithFlags(&P->side_stream, cudaStreamNonBlocking));
+  CLPK_CHECK_CUDA(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
+  CLPK_CHECK_CUDA(cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
   CLPK_CHECK_CUDA(cudaDeviceSynchronize());
   guard.p = nullptr;
   *out_plan = P;
@@ -672,9 +683,18 @@ extern "C" int clpk_unet_forward(clpk_plan* P, const float* x, const float* z, c
 // one DDIM step on plan-owned buffers: conditioning for run->step, eps = UNet(x_buf), x_buf <- update, step += 1
 static int ddim_step_body(clpk_plan* P, cudaStream_t s) {
   const int td = P->cfg.time_dim;
-  CLPK_TIMED(P, kProfCond, s, launch_cond_combine(P->zemb, P->ht_tab, P->run_dev, P->hcond, P->B, td, s));
-  CLPK_TRY(film_from_h(P, s));
-  CLPK_TRY(forward_body(P, P->x_buf, s));
+  // conditioning on the side stream (env CLPK_SIDE_STREAM=0: in line); per-launch profiling keeps everything in line
+  static const bool side_ok = [] { const char* e = getenv("CLPK_SIDE_STREAM"); return !(e && atoi(e) == 0); }();
+  const bool fork = side_ok && !P->prof_on && P->side_stream != nullptr;
+  cudaStream_t sc = fork ? P->side_stream : s;
+  if (fork) {
+    CLPK_CHECK_CUDA(cudaEventRecord(P->ev_fork, s));
+    CLPK_CHECK_CUDA(cudaStreamWaitEvent(sc, P->ev_fork, 0));
+  }
+  CLPK_TIMED(P, kProfCond, sc, launch_cond_combine(P->zemb, P->ht_tab, P->run_dev, P->hcond, P->B, td, sc));
+  CLPK_TRY(film_from_h(P, sc));
+  if (fork) CLPK_CHECK_CUDA(cudaEventRecord(P->ev_join, sc));
+  CLPK_TRY(forward_body(P, P->x_buf, s, fork ? P->ev_join : nullptr));
   const long long n = (long long)P->B * P->cfg.img_ch * P->H * P->W;
   CLPK_TIMED(P, kProfDdim, s, launch_ddim_step(P->x_buf, P->eps_buf, P->coef_tab, P->run_dev, P->x_buf, n, s));
   return CLPK_OK;
