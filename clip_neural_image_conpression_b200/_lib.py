@@ -80,6 +80,9 @@ SIGNATURES = {
     "clpk_conv_in_affine_supported": (_i, [_i, _i, _i, _i, _i]),
     "clpk_groupnorm_affine": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "clpk_pack_conv_weight": (_i64, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "clpk_head_conv_supported": (_i, [_i, _i, _i, _i]),
+    "clpk_pack_head_weight": (_i, [_vp, _vp, _i, _i, _vp]),
+    "clpk_head_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "clpk_conv_igemm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
     "clpk_conv_direct": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(ConvEpilogue), _vp]),
     "clpk_stem_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

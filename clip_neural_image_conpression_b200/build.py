@@ -13,7 +13,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libclpk.so"
-SOURCES = ["elementwise.cu", "groupnorm.cu", "conv_in.cu", "conv_igemm.cu", "plan.cu"]
+SOURCES = ["elementwise.cu", "groupnorm.cu", "conv_in.cu", "conv_igemm.cu", "head_conv.cu", "plan.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

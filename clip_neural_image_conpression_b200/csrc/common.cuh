@@ -44,6 +44,12 @@ void count_launch(int n = 1);
     }                                                                                           \
   } while (0)
 
+#define CLPK_TRY_RC(expr)           \
+  do {                              \
+    int _rc = (expr);               \
+    if (_rc != CLPK_OK) return _rc; \
+  } while (0)
+
 int num_sms();
 
 // Programmatic dependent launch (PDL), OFF by default (env CLPK_PDL=1 turns it on): every kernel of the DDIM step graph

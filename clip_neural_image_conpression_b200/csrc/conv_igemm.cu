@@ -992,7 +992,7 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+int encode_tensor_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
                       const cuuint32_t* box, int swizzle_bytes, CUtensorMapDataType dtype) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
@@ -1188,12 +1188,12 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   const int swz = atom_k * 2;
   cuuint32_t box_a[5] = {(cuuint32_t)atom_k, (cuuint32_t)(p.slab ? p.wbox + 2 : p.wbox), 1, (cuuint32_t)p.hbox, 1};
   const CUtensorMapDataType op_dt = p.op_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  int rc = encode_map(&out->map_a, x_bf16, 5, dims, strides, box_a, swz, op_dt);
+  int rc = encode_tensor_map(&out->map_a, x_bf16, 5, dims, strides, box_a, swz, op_dt);
   if (rc) return rc;
   cuuint64_t wdims[2] = {(cuuint64_t)p.taps * cin, (cuuint64_t)p.phases * p.cout_pad};
   cuuint64_t wstr[1] = {(cuuint64_t)p.taps * cin * 2};
   cuuint32_t box_w[2] = {(cuuint32_t)atom_k, (cuuint32_t)(p.block_n / p.ncta)};
-  rc = encode_map(&out->map_w, w_packed, 2, wdims, wstr, box_w, swz, op_dt);
+  rc = encode_tensor_map(&out->map_w, w_packed, 2, wdims, wstr, box_w, swz, op_dt);
   if (rc) return rc;
   // fp32 NHWC output maps for the TMA-store epilogue: [C, Wgrid, 1, Hgrid, B] per phase (transposed conv: the phase
   // (ph,pw) owns output pixels (2h+ph, 2w+pw) -> base offset + doubled w/h strides)
@@ -1208,7 +1208,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     cuuint32_t obox[5] = {32, (cuuint32_t)wsub, 1, (cuuint32_t)(32 / wsub), 1};  // one epilogue warp's 32 tile rows
     for (int phase = 0; phase < p.phases; ++phase) {
       const long long off = ((long long)(phase >> 1) * OW + (phase & 1)) * CO;
-      rc = encode_map(&out->maps_out.m[phase], reinterpret_cast<uint16_t*>(p.ep.out_op) + off, 5, odims, ostr, obox, 64, op_dt);
+      rc = encode_tensor_map(&out->maps_out.m[phase], reinterpret_cast<uint16_t*>(p.ep.out_op) + off, 5, odims, ostr, obox, 64, op_dt);
       if (rc) return rc;
     }
   }
@@ -1222,13 +1222,13 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     for (int phase = 0; phase < p.phases; ++phase) {
       const long long off = ((long long)(phase >> 1) * OW + (phase & 1)) * CO;
       if (p.ep.out_f32) {
-        rc = encode_map(&out->maps_out.m[phase], p.ep.out_f32 + off, 5, odims, ostr, obox, 128,
+        rc = encode_tensor_map(&out->maps_out.m[phase], p.ep.out_f32 + off, 5, odims, ostr, obox, 128,
                         CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
         if (rc) return rc;
       }
       if (p.ep.resid) {
         CLPK_REQUIRE((reinterpret_cast<uintptr_t>(p.ep.resid) & 15) == 0, "residual tensor must be 16-byte aligned");
-        rc = encode_map(&out->maps_res.m[phase], const_cast<float*>(p.ep.resid) + off, 5, odims, ostr, obox, 128,
+        rc = encode_tensor_map(&out->maps_res.m[phase], const_cast<float*>(p.ep.resid) + off, 5, odims, ostr, obox, 128,
                         CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
         if (rc) return rc;
       }

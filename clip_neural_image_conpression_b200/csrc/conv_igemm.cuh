@@ -85,6 +85,10 @@ int igemm_init();  // one-time function attributes; call outside stream capture
 int igemm_launch(const IgemmLaunch& L, cudaStream_t stream);
 int direct_launch(const IgemmLaunch& L, const void* x_bf16, const void* w_packed, cudaStream_t stream);
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+int encode_tensor_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                      const cuuint32_t* box, int swizzle_bytes, CUtensorMapDataType dtype);
+
 // padded GEMM-N of a conv with `cout` output channels, and the UMMA N tile chosen for it
 int igemm_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg);  // <= 0: unsupported
 // floats of a gn_partial buffer: batch * slots * pieces (mean, M2) pairs followed by `slots` element counts

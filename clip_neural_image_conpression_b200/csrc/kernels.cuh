@@ -47,6 +47,12 @@ int launch_gn_apply_ex(const void* x, int x_is_16, const float* gamma, const flo
 int launch_gn_apply(const float* x, const float* gamma, const float* beta, const float2* stats, void* y_op,
                     const GnShape& s, int silu, int op_dtype, cudaStream_t stream);
 
+// head_conv.cu
+bool head_conv_supported(int h, int w, int c, int cout);
+int launch_head_conv(const void* x_op, const float* scale, const float* shift, const void* w_packed, const float* bias,
+                     float* out_nchw, int batch, int h, int w, int c, int op_dtype, cudaStream_t stream);
+int launch_pack_head_weight(const float* w, void* out_op, int c, int op_dtype, cudaStream_t stream);
+
 // conv_in.cu
 int launch_conv_in(const float* x_nchw, const float* w, const float* b, float* y_nhwc, int batch, int cin, int h, int w_,
                    int cout, cudaStream_t stream);

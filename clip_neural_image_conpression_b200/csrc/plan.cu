@@ -112,6 +112,8 @@ struct clpk_plan {
   std::vector<uint16_t*> X16;  // per level: 16-bit copy of X[l]
   bool fuse_head = false;    // out_norm applied inside the `out` conv (see fuse_gn_mask)
   bool head16 = false;       // the last transposed conv writes only the 16-bit copy X16[0] (see head16_on)
+  bool head_fused = false;   // out_norm + out conv as the single head_conv kernel (env CLPK_HEAD_FUSED, default 1)
+  uint16_t* head_w = nullptr;  // [32][base] packed head weight (head_conv.cu)
   bool x16_gn = false;       // env CLPK_X16=1: GroupNorms on the residual stream read X16 instead of fp32 X
   float* Yf = nullptr;       // fp32 conv1 output, only for ResBlocks whose GroupNorm statistics cannot be fused
   void* gn_ws = nullptr;
@@ -352,7 +354,13 @@ int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s, cudaEvent_t 
   }
   if (P->head16) CLPK_TRY(run_groupnorm(P, P->X16[0], 1, P->out_gn, s));  // out_norm on the 16-bit transposed-conv output
   else CLPK_TRY(run_groupnorm_x(P, 0, P->out_gn, s));              // out_norm, no activation (unet.py:105)
-  CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->out_conv.L, s));  // -> eps_buf (NCHW)
+  if (P->head_fused) {
+    CLPK_TIMED(P, kProfConvOther, s,
+               launch_head_conv(P->X16[0], P->out_gn.scale, P->out_gn.shift, P->head_w, P->out_conv.bias, P->eps_buf, P->B,
+                                P->H, P->W, c.base, c.op_dtype, s));  // out(out_norm(x)) -> eps_buf (NCHW)
+  } else {
+    CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->out_conv.L, s));  // -> eps_buf (NCHW)
+  }
   return CLPK_OK;
 }
 
@@ -522,6 +530,16 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   P->fuse_head = (fuse_gn_mask() & 2) && P->out_gn.fused && !P->x16_gn &&
                  igemm_xform_ok(CLPK_CONV_3X3_S1, height, width, cfg->base, cfg->img_ch);
   P->head16 = P->fuse_head || (head16_on() && P->out_gn.fused && !P->x16_gn && cfg->base % 32 == 0);
+  {
+    const char* e = getenv("CLPK_HEAD_FUSED");
+    P->head_fused = !(e && atoi(e) == 0) && !P->fuse_head && P->head16 &&
+                    head_conv_supported(height, width, cfg->base, cfg->img_ch);
+  }
+  if (P->head_fused) {  // out_norm is applied inside head_conv: only the (scale, shift) table is computed
+    P->out_gn.in_consumer = true;
+    CLPK_TRY(P->alloc(&P->out_gn.scale, (long long)batch * cfg->base));
+    CLPK_TRY(P->alloc(&P->out_gn.shift, (long long)batch * cfg->base));
+  }
   if (P->fuse_head) {
     P->out_gn.in_consumer = true;
     CLPK_TRY(P->alloc(&P->out_gn.scale, (long long)batch * cfg->base));
@@ -642,6 +660,12 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     }
     CLPK_TRY(bind_conv(P, &P->out_conv, P->fuse_head ? (const void*)P->X16[0] : (const void*)P->T, eo));
     P->flops_fwd += P->out_conv.flops;
+    if (P->head_fused) {
+      const float* w = nullptr;
+      CLPK_TRY(tab.get("out.weight", (int64_t)cfg->img_ch * cfg->base * 9, &w));
+      CLPK_TRY(P->alloc(&P->head_w, 32ll * cfg->base));
+      CLPK_TRY(launch_pack_head_weight(w, P->head_w, cfg->base, cfg->op_dtype, nullptr));
+    }
   }
   P->flops_fwd += 2.0 * batch * (double)height * width * cfg->base * cfg->img_ch * 9;  // in_conv
   P->flops_fwd += 2.0 * batch * ((double)td * 4 * td * 2 + (double)cfg->z_dim * td + (double)film_n * td);

@@ -16,7 +16,7 @@ from ._lib import (CONV_3X3_S1, CONV_3X3_S2, CONVT_4X4_S2, ConvEpilogue, check, 
 
 __all__ = [
     "dequant_l2norm", "quant_encode", "quant_fit", "ddim_step", "timestep_embedding", "linear", "film_apply",
-    "groupnorm_silu", "groupnorm_affine", "conv_in_affine_supported", "pack_conv_weight", "conv_igemm", "conv_direct", "conv_in", "to_uint8_hwc", "psnr_sqerr_u8", "ssim_u8", "ddpm_combine",
+    "groupnorm_silu", "groupnorm_affine", "conv_in_affine_supported", "pack_conv_weight", "conv_igemm", "conv_direct", "head_conv", "conv_in", "to_uint8_hwc", "psnr_sqerr_u8", "ssim_u8", "ddpm_combine",
     "CONV_3X3_S1", "CONV_3X3_S2", "CONVT_4X4_S2",
 ]
 
@@ -258,6 +258,24 @@ def groupnorm_apply(x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tenso
     check(_lib.load().clpk_groupnorm_apply(ptr(x), ptr(_f32c(gamma)), ptr(_f32c(beta)), ptr(_f32c(stats)), ptr(y), b, hw, c,
                                            groups, int(silu), op_code(dtype), stream_ptr()), "clpk_groupnorm_apply")
     return y
+
+
+@on_tensor_device
+def head_conv(x_nhwc_op: torch.Tensor, in_scale: torch.Tensor, in_shift: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """out(out_norm(x)) of the UNet head as one kernel (see clpk_head_conv): x 16-bit NHWC, (in_scale, in_shift) [B, C] the
+    GroupNorm in affine form, w [3, C, 3, 3] / b [3] the reference-layout fp32 conv parameters.  Returns fp32 NCHW."""
+    require_cuda(x_nhwc_op, in_scale, in_shift, w, b)
+    bsz, h, wd, c = x_nhwc_op.shape
+    lib = _lib.load()
+    if not lib.clpk_head_conv_supported(h, wd, c, w.shape[0]):
+        raise ValueError(f"fused head kernel unsupported for W={wd}, C={c}, Cout={w.shape[0]}")
+    wp = torch.empty((32, c), dtype=x_nhwc_op.dtype, device=x_nhwc_op.device)
+    check(lib.clpk_pack_head_weight(ptr(_f32c(w)), ptr(wp), c, op_code(x_nhwc_op.dtype), stream_ptr()), "clpk_pack_head_weight")
+    out = torch.empty((bsz, 3, h, wd), dtype=torch.float32, device=x_nhwc_op.device)
+    keep = [_f32c(in_scale), _f32c(in_shift), _f32c(b), x_nhwc_op.contiguous()]
+    check(lib.clpk_head_conv(ptr(keep[3]), ptr(keep[0]), ptr(keep[1]), ptr(wp), ptr(keep[2]), ptr(out), bsz, h, wd, c,
+                             op_code(x_nhwc_op.dtype), stream_ptr()), "clpk_head_conv")
+    return out
 
 
 def conv_direct(*args, **kwargs):

@@ -162,6 +162,15 @@ int clpk_groupnorm_affine(const void* partial_dev, const float* gamma_dev, const
  * per group (<= 0: the fused statistics are not available for this shape). */
 int clpk_conv_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg);
 
+/* The UNet head out(out_norm(x)) (unet.py:78-79,105) as ONE kernel: GroupNorm (no activation) applied to the 16-bit NHWC
+ * activation in shared memory (in_scale / in_shift [batch][c] from clpk_groupnorm_affine), then the 3x3 conv to 3
+ * channels evaluated as a pointwise tcgen05 GEMM (N = 27 (tap, channel) columns) + a 9-point shift-add, fp32 NCHW output.
+ * w_packed: clpk_pack_head_weight of the reference-layout weight [3][c][3][3] -> 16-bit [32][c]. */
+int clpk_head_conv_supported(int h, int w, int c, int cout);
+int clpk_pack_head_weight(const float* w_dev, void* out_op_dev, int c, int op_dtype, void* stream);
+int clpk_head_conv(const void* x_op_nhwc_dev, const float* in_scale_dev, const float* in_shift_dev, const void* w_packed_dev,
+                   const float* bias_dev, float* out_nchw_dev, int batch, int h, int w, int c, int op_dtype, void* stream);
+
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed).
  * x: 16-bit (op_dtype) NHWC [batch, h_in, w_in, cin]; w_packed from clpk_pack_conv_weight with the same op_dtype.
  * Output spatial size: S1: (h_in, w_in); S2: (h_in/2, w_in/2); ConvT: (2*h_in, 2*w_in). */

@@ -346,6 +346,39 @@ def test_groupnorm_affine_from_conv_statistics(ops):
     assert float(torch.linalg.norm(fused - plain) / torch.linalg.norm(plain)) < 1e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("b,h,w,c", [
+    (2, 6, 256, 128),      # two 128-pixel tiles per row, one row per CTA band (halo rows recomputed by the neighbours)
+    (1, 5, 320, 64),       # ragged W: third tile half filled, one channel block
+    (3, 9, 40, 128),       # W < 128: a single partial tile per row
+    (2, 40, 128, 192),     # three channel blocks
+    (8, 200, 256, 128),    # bands of several rows that cross image boundaries (ring slots of two images)
+    (1, 1, 256, 128),      # single-row image: both vertical neighbours are padding
+])
+def test_head_conv_fused(ops, b, h, w, c, dtype):
+    """clpk_head_conv (out_norm + 3x3 conv to 3 channels as pointwise tcgen05 GEMM + 9-point shift-add) against the fp64
+    convolution of the normalised tensor rounded to the operand format, and against the implicit-GEMM kernel it replaces."""
+    g = torch.Generator().manual_seed(5 + w + c + h)
+    x16 = (torch.randn(b, h, w, c, generator=g) * 1.5 + 0.3).to(dtype).cuda()
+    sc = (1 + 0.3 * torch.randn(b, c, generator=g)).cuda()
+    sh = (0.5 * torch.randn(b, c, generator=g) + 0.4).cuda()
+    wt = (torch.randn(3, c, 3, 3, generator=g) / (c * 9) ** 0.5).cuda()
+    bias = torch.randn(3, generator=g).cuda()
+    y = ops.head_conv(x16, sc, sh, wt, bias)
+    assert y.shape == (b, 3, h, w) and torch.isfinite(y).all()
+    t16 = (x16.float() * sc[:, None, None, :] + sh[:, None, None, :]).to(dtype)
+    ref = F.conv2d(t16.float().permute(0, 3, 1, 2).double(), wt.to(dtype).double(), bias.double(), padding=1)
+    scale = max(1.0, float(ref.abs().max()))
+    ulp = 2.0 ** -11 if dtype == torch.float16 else 2.0 ** -8
+    # the in-kernel FMA and torch's mul+add may round a normalised value to neighbouring 16-bit numbers
+    assert float((y.double() - ref).abs().max()) < 8 * ulp * scale
+    assert float(torch.linalg.norm(y.double() - ref) / torch.linalg.norm(ref)) < (1e-3 if dtype == torch.float16 else 6e-3)
+    if w >= 128 and c % 64 == 0:
+        old = ops.conv_igemm(t16, ops.pack_conv_weight(wt, 0, dtype), 0, 3, bias, want_f32=False, want_nchw=True)["nchw"]
+        assert float((y - old).abs().max()) < 8 * ulp * scale
+    assert torch.equal(y, ops.head_conv(x16, sc, sh, wt, bias))          # deterministic
+
+
 # ------------------------------------------------------------------------------------------------ blocks, post-process
 def test_film_and_resblock_match_reference(ops, golden):
     from clip_neural_image_conpression_b200.models import FiLM, ResBlock

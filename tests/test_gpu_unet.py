@@ -271,10 +271,17 @@ def test_fused_groupnorm_paths_match_unfused(oracle, monkeypatch):
     monkeypatch.delenv("CLPK_FUSE_GN")
     monkeypatch.delenv("CLPK_HEAD16")
     net.release_plans()
-    head16 = net(x.cuda(), z.cuda(), t.cuda()).cpu()              # the default plan: 16-bit-only transposed-conv output
-    assert oracle.rel_l2(head16, plain) < 2e-3 and not torch.equal(head16, plain)
+    head = net(x.cuda(), z.cuda(), t.cuda()).cpu()                # the default plan: fused head kernel (head_conv.cu)
+    assert oracle.rel_l2(head, plain) < 2e-3 and not torch.equal(head, plain)
+    monkeypatch.setenv("CLPK_HEAD_FUSED", "0")
+    net.release_plans()
+    head16 = net(x.cuda(), z.cuda(), t.cuda()).cpu()              # 16-bit-only transposed-conv output, stand-alone out_norm
+    monkeypatch.delenv("CLPK_HEAD_FUSED")
+    net.release_plans()
+    assert oracle.rel_l2(head16, plain) < 2e-3 and oracle.rel_l2(head16, head) < 2e-3 and not torch.equal(head16, head)
     assert not torch.equal(fused, plain)                         # the switch really changes the executed path
     with torch.no_grad():
         ref = oracle.unet_forward(sd, cfg["ch_mult"], x, z, t)
     assert oracle.rel_l2(fused, plain) < 2e-3
     assert oracle.rel_l2(fused, ref) < EPS_TOL and oracle.rel_l2(plain, ref) < EPS_TOL
+    assert oracle.rel_l2(head, ref) < EPS_TOL and oracle.rel_l2(head16, ref) < EPS_TOL
