@@ -57,7 +57,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra_configs measurements (configs 3/4/5, bf16)")
     ap.add_argument("--images", type=int, default=1024, help="store size of the config-3 strong-scaling measurement")
-    ap.add_argument("--micro-batch", type=int, default=16, help="micro-batch of the config-3 store decode")
+    ap.add_argument("--micro-batch", type=int, default=32,
+                    help="micro-batch of the config-3 store decode (batch sweep on the final kernels, profiles/batch_sweep_r2.txt: 8 -> 61.4, 16 -> 64.0, 32 -> 66.5, 64 -> 67.0 images/s)")
     ap.add_argument("--only-store", action="store_true", help="run ONLY the config-3 store decode (value = its images/s, scaling strong)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--operand", choices=["f16", "bf16"], default="f16", help="tensor-core operand format")

@@ -302,19 +302,51 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ partial, float2* _
   if (lane == 0) stats[(long long)b * groups + g] = st;
 }
 
-// partial -> per-(image, channel) affine form of GroupNorm for convs that normalise their own A operand
-// (clpk_conv_epilogue.in_scale / in_shift): one block per image, one warp per group.
-__global__ void gn_affine_kernel(const float2* __restrict__ partial, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
-                                 int slots, int pieces, int groups, int c, float eps) {
+// partial -> per-(image, channel) affine form of GroupNorm for kernels that normalise their own A operand
+// (clpk_conv_epilogue.in_scale / in_shift, clpk_head_conv): one block per (group, image); its 4 warps fold a quarter of
+// the slots each (all relative to the first pair's mean, so the quarter sums simply add), warp 0 combines in fixed order.
+__global__ void __launch_bounds__(128)
+gn_affine_kernel(const float2* __restrict__ partial, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 float* __restrict__ scale, float* __restrict__ shift, int slots, int pieces, int groups, int c, float eps) {
+  __shared__ float4 part_s[4];
+  __shared__ float2 st_s;
   pdl_prologue_done();
-  const int b = blockIdx.x;
-  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (g >= groups) return;
-  const float* counts = reinterpret_cast<const float*>(partial + (long long)gridDim.x * slots * pieces);
-  const float2 st = gn_fold_partials(partial, counts, b, g, slots, pieces, groups, eps, lane);
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* counts = reinterpret_cast<const float*>(partial + (long long)gridDim.y * slots * pieces);
+  const int m = pieces / groups;
+  const float2* pp = partial + (long long)b * slots * pieces + g * m;
+  const float m0 = __ldg(pp).x;
+  float A = 0.f, Q = 0.f, M = 0.f, N = 0.f;
+#pragma unroll 4
+  for (int k = warp * 32 + lane; k < slots * m; k += 128) {
+    const int slot = k / m, j = k - slot * m;
+    const float2 v = __ldg(pp + (long long)slot * pieces + j);
+    const float n = __ldg(counts + slot);
+    const float d = v.x - m0, nd = n * d;
+    A += nd; Q = fmaf(nd, d, Q); M += v.y; N += n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    A += __shfl_xor_sync(0xffffffffu, A, o);
+    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+    M += __shfl_xor_sync(0xffffffffu, M, o);
+    N += __shfl_xor_sync(0xffffffffu, N, o);
+  }
+  if (lane == 0) part_s[warp] = make_float4(A, Q, M, N);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float4 t = part_s[0];
+#pragma unroll
+    for (int w = 1; w < 4; ++w) { t.x += part_s[w].x; t.y += part_s[w].y; t.z += part_s[w].z; t.w += part_s[w].w; }
+    const float inv_n = 1.0f / t.w, dm = t.x * inv_n;
+    const float var = fmaxf((t.z + fmaf(-t.x, dm, t.y)) * inv_n, 0.f);
+    st_s = make_float2(m0 + dm, 1.0f / sqrtf(var + eps));
+  }
+  __syncthreads();
+  const float2 st = st_s;
   const int cpg = c / groups;
-  for (int k = lane; k < cpg; k += 32) {
+  for (int k = threadIdx.x; k < cpg; k += 128) {
     const int ch = g * cpg + k;
     const float sc = st.y * __ldg(gamma + ch);
     scale[(long long)b * c + ch] = sc;
@@ -324,8 +356,8 @@ __global__ void gn_affine_kernel(const float2* __restrict__ partial, const float
 
 int launch_gn_affine(const float2* partial, const float* gamma, const float* beta, float* scale, float* shift, int batch,
                      int slots, int pieces, int groups, int c, float eps, cudaStream_t stream) {
-  CLPK_REQUIRE(groups > 0 && groups <= 32 && c % groups == 0 && pieces % groups == 0, "GroupNorm affine: bad group layout");
-  CLPK_CHECK_CUDA(launch_kernel_pdl(gn_affine_kernel, dim3(batch), dim3(32 * groups), 0, stream, partial, gamma, beta, scale,
+  CLPK_REQUIRE(groups > 0 && c % groups == 0 && pieces % groups == 0, "GroupNorm affine: bad group layout");
+  CLPK_CHECK_CUDA(launch_kernel_pdl(gn_affine_kernel, dim3(groups, batch), dim3(128), 0, stream, partial, gamma, beta, scale,
                                     shift, slots, pieces, groups, c, eps));
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;

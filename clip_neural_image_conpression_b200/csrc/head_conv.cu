@@ -15,23 +15,27 @@
 // issues ~8 MMAs per 32 KB tile, so — unlike in the 3x3 slab mainloop — shared-memory bandwidth is plentiful).
 //
 // One CTA owns a band of consecutive image rows; the D rows live in a 4-deep shared-memory ring (tap-major, one halo
-// column left and right kept at zero), and output row g is emitted as soon as D rows g-1, g, g+1 are there.
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..5 normalise the landed tile,
-// warps 6..9 move accumulators TMEM -> D ring and do the shift-add + NCHW fp32 store.
+// column left and right kept at zero; tap rows stored shifted so that the shift-add reads aligned float4), and output
+// row g is emitted as soon as D rows g-1, g, g+1 are there.
+// Warp roles (448 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..9 normalise the landed tile,
+// warps 10..13 move accumulators TMEM -> D ring and do the shift-add + NCHW fp32 store.
 #include "conv_igemm.cuh"
 #include "kernels.cuh"
 
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
 
 namespace clpk {
 
-constexpr int kHeadThreads = 320;
+constexpr int kHeadXfWarps = 8;                       // warps normalising the landed tile (the kernel's critical resource)
+constexpr int kHeadThreads = 64 + 32 * kHeadXfWarps + 128;
 constexpr int kHeadTileM = 128;
 constexpr int kHeadN = 32;          // 27 used: n = (r*3 + s)*3 + co
 constexpr int kHeadTaps = 27;
 constexpr int kHeadRing = 4;
 constexpr int kHeadMaxStages = 6;
+constexpr int kHeadMaxKpt = 4;      // C <= 256: the per-thread (scale, shift) of all channel blocks stay in registers
 constexpr int kHeadSmemBudget = 232448;
 
 struct HeadParams {
@@ -39,7 +43,7 @@ struct HeadParams {
   int tiles_w, kpt, stages;
   int rows_total, band;
   int op_f16;
-  int dpitch;                 // floats per tap row of the D ring: w + 2 rounded up to a multiple of 4
+  int dpitch;                 // floats per tap row of the D ring: w + 8 (shifted storage, see emit_row)
   const float* scale;         // [batch][c]
   const float* shift;
   const float* bias;          // [3]
@@ -64,8 +68,7 @@ head_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* smem_a = smem;
   uint8_t* smem_w = smem_a + (size_t)p.stages * stage_bytes;  // kpt atoms of 32 rows x 128 B
   float* dring = reinterpret_cast<float*>(smem_w + (size_t)p.kpt * kHeadN * 128);
-  float* tab = dring + (size_t)kHeadRing * kHeadTaps * p.dpitch;   // scale[c] | shift[c] of the current image
-  HeadBarriers* bars = reinterpret_cast<HeadBarriers*>(tab + 2 * p.c);
+  HeadBarriers* bars = reinterpret_cast<HeadBarriers*>(dring + (size_t)kHeadRing * kHeadTaps * p.dpitch);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("clpk: head kernel shared memory is not 1024-byte aligned\n");
@@ -76,7 +79,7 @@ head_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->ready[s], 4);
+      mbar_init(&bars->ready[s], kHeadXfWarps);
       mbar_init(&bars->empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -153,46 +156,64 @@ head_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + kHeadXfWarps) {
     // ===================================================== transform warps: out_norm in place on the landed tile
+    constexpr int kXfThreads = 32 * kHeadXfWarps, kRowStep = kXfThreads / 8, kRows = kHeadTileM / kRowStep;
     const int xt = threadIdx.x - 64;
-    const int jp = xt & 7, i0 = xt >> 3;     // 16-byte piece (8 channels) and first row; rows i0 + 16 k
+    const int jp = xt & 7, i0 = xt >> 3;     // 16-byte piece (8 channels) and first row; rows i0 + kRowStep * k
     const bool f16 = p.op_f16 != 0;
     int cur_b = -1, stage = 0;
     uint32_t phase = 0;
+    // (scale, shift) of this thread's 8 channels of every channel block live in REGISTERS and are reloaded only when the
+    // band crosses into the next image: reading them from a shared table per tile cost as many smem wavefronts as the
+    // tile itself (profiles/ncu_full_r2.txt)
+    float sc[kHeadMaxKpt][8], sh[kHeadMaxKpt][8];
     for (int it = 0; it < n_items; ++it) {
       const int j = j0 + it / p.tiles_w, tw = it - (it / p.tiles_w) * p.tiles_w;
       const int b = j / p.h;
       if (b != cur_b) {
-        named_bar_sync(1, 128);
-        for (int ch = xt; ch < p.c; ch += 128) {
-          tab[ch] = __ldg(p.scale + (long long)b * p.c + ch);
-          tab[p.c + ch] = __ldg(p.shift + (long long)b * p.c + ch);
+#pragma unroll
+        for (int kc = 0; kc < kHeadMaxKpt; ++kc) {
+          if (kc < p.kpt) {
+            const float4* ps = reinterpret_cast<const float4*>(p.scale + (long long)b * p.c + kc * 64 + 8 * jp);
+            const float4* ph = reinterpret_cast<const float4*>(p.shift + (long long)b * p.c + kc * 64 + 8 * jp);
+            const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), h0 = __ldg(ph), h1 = __ldg(ph + 1);
+            sc[kc][0] = s0.x; sc[kc][1] = s0.y; sc[kc][2] = s0.z; sc[kc][3] = s0.w;
+            sc[kc][4] = s1.x; sc[kc][5] = s1.y; sc[kc][6] = s1.z; sc[kc][7] = s1.w;
+            sh[kc][0] = h0.x; sh[kc][1] = h0.y; sh[kc][2] = h0.z; sh[kc][3] = h0.w;
+            sh[kc][4] = h1.x; sh[kc][5] = h1.y; sh[kc][6] = h1.z; sh[kc][7] = h1.w;
+          }
         }
-        named_bar_sync(1, 128);
         cur_b = b;
       }
       mbar_wait(&bars->full[stage], phase);
       const int px_valid = min(kHeadTileM, p.w - tw * kHeadTileM);   // pixels beyond the row are TMA zero fill: keep 0
-      for (int kc = 0; kc < p.kpt; ++kc) {
-        float sc[8], sh[8];
-        const float4 s0 = *reinterpret_cast<const float4*>(tab + kc * 64 + 8 * jp);
-        const float4 s1 = *reinterpret_cast<const float4*>(tab + kc * 64 + 8 * jp + 4);
-        const float4 h0 = *reinterpret_cast<const float4*>(tab + p.c + kc * 64 + 8 * jp);
-        const float4 h1 = *reinterpret_cast<const float4*>(tab + p.c + kc * 64 + 8 * jp + 4);
-        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-        sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+#pragma unroll
+      for (int kc = 0; kc < kHeadMaxKpt; ++kc) {
+        if (kc >= p.kpt) break;
         uint8_t* a = smem_a + (size_t)stage * stage_bytes + (size_t)kc * kHeadTileM * 128;
-        uint4 q[8];
+        // (rows beyond px_valid hold TMA zero fill; transforming them too would turn the padding into `shift`, so the
+        //  whole tile takes the unpredicated fast path only when it is full)
+        uint4 q[kRows];
+        if (px_valid == kHeadTileM) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int i = i0 + 16 * r;
-          if (i < px_valid) q[r] = *reinterpret_cast<const uint4*>(a + i * 128 + ((jp ^ (i & 7)) << 4));
-        }
+          for (int r = 0; r < kRows; ++r) {
+            const int i = i0 + kRowStep * r;
+            q[r] = *reinterpret_cast<const uint4*>(a + i * 128 + ((jp ^ (i & 7)) << 4));
+          }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int i = i0 + 16 * r;
-          if (i < px_valid) *reinterpret_cast<uint4*>(a + i * 128 + ((jp ^ (i & 7)) << 4)) = affine_act8(q[r], sc, sh, false, f16);
+          for (int r = 0; r < kRows; ++r) {
+            const int i = i0 + kRowStep * r;
+            *reinterpret_cast<uint4*>(a + i * 128 + ((jp ^ (i & 7)) << 4)) = affine_act8(q[r], sc[kc], sh[kc], false, f16);
+          }
+        } else {
+          for (int r = 0; r < kRows; ++r) {
+            const int i = i0 + kRowStep * r;
+            if (i < px_valid) {
+              uint4* ptr = reinterpret_cast<uint4*>(a + i * 128 + ((jp ^ (i & 7)) << 4));
+              *ptr = affine_act8(*ptr, sc[kc], sh[kc], false, f16);
+            }
+          }
         }
       }
       fence_proxy_async_smem();
@@ -203,31 +224,36 @@ head_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else {
     // ===================================================== epilogue warps: TMEM -> D ring, then shift-add of row j - 1
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-    const int et = threadIdx.x - 192;             // 0 .. 127
+    const int et = threadIdx.x - (64 + 32 * kHeadXfWarps);   // 0 .. 127
     const int row = quarter * 32 + lane;          // pixel of the tile
     const float b0 = __ldg(p.bias), b1 = __ldg(p.bias + 1), b2 = __ldg(p.bias + 2);
     const long long plane = (long long)p.h * p.w;
+    // Tap row (r, s) of a D row is stored SHIFTED by 5 - s columns (source pixel q at index q + 5 - s), so the values output
+    // pixel x needs from all 27 tap rows sit at the same 16-byte aligned index x + 4: four outputs per LDS.128.
     auto emit_row = [&](int g) {                  // output row g from D rows g-1, g, g+1 (all 128 epilogue threads)
       const int b = g / p.h, y = g - b * p.h;
       float* o = p.out + ((long long)b * 3) * plane + (long long)y * p.w;
-      for (int x = et; x < p.w; x += 128) {
-        float a0 = b0, a1 = b1, a2 = b2;
+      for (int x = 4 * et; x < p.w; x += 4 * 128) {
+        float4 a0 = make_float4(b0, b0, b0, b0), a1 = make_float4(b1, b1, b1, b1), a2 = make_float4(b2, b2, b2, b2);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const int yy = y + r - 1;
           if (yy < 0 || yy >= p.h) continue;      // zero padding of the normalised tensor
-          const float* d = dring + (size_t)((g + r - 1) & (kHeadRing - 1)) * kHeadTaps * p.dpitch + x;   // + s below
+          const float* d = dring + (size_t)((g + r - 1) & (kHeadRing - 1)) * kHeadTaps * p.dpitch + x + 4;
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
-            const float* t = d + (size_t)((r * 3 + s) * 3) * p.dpitch + s;   // ring column index = 1 + (x + s - 1)
-            a0 += t[0];
-            a1 += t[p.dpitch];
-            a2 += t[2 * p.dpitch];
+            const float* t = d + (size_t)((r * 3 + s) * 3) * p.dpitch;
+            const float4 v0 = *reinterpret_cast<const float4*>(t);
+            const float4 v1 = *reinterpret_cast<const float4*>(t + p.dpitch);
+            const float4 v2 = *reinterpret_cast<const float4*>(t + 2 * p.dpitch);
+            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+            a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+            a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
           }
         }
-        o[x] = a0;
-        o[plane + x] = a1;
-        o[2 * plane + x] = a2;
+        *reinterpret_cast<float4*>(o + x) = a0;
+        *reinterpret_cast<float4*>(o + plane + x) = a1;
+        *reinterpret_cast<float4*>(o + 2 * plane + x) = a2;
       }
     };
     int it = 0;
@@ -248,7 +274,7 @@ head_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int px = tw * kHeadTileM + row;
         if (px < p.w) {
 #pragma unroll
-          for (int n = 0; n < kHeadTaps; ++n) drow[(size_t)n * p.dpitch + 1 + px] = __uint_as_float(r[n]);
+          for (int n = 0; n < kHeadTaps; ++n) drow[(size_t)n * p.dpitch + px + 5 - ((n / 3) % 3)] = __uint_as_float(r[n]);
         }
       }
       named_bar_sync(2, 128);                      // D row j complete (every warp wrote its pixel quarter of every tile)
@@ -279,8 +305,8 @@ __global__ void pack_head_weight_kernel(const float* __restrict__ w, uint16_t* _
 static int head_stage_count(int w, int c, int* smem_bytes) {
   const int kpt = c / 64;
   const int stage_bytes = kpt * kHeadTileM * 128;
-  const int dpitch = (w + 2 + 3) / 4 * 4;
-  const int fixed = kpt * kHeadN * 128 + kHeadRing * kHeadTaps * dpitch * 4 + 2 * c * 4 + (int)sizeof(HeadBarriers) + 64;
+  const int dpitch = w + 8;
+  const int fixed = kpt * kHeadN * 128 + kHeadRing * kHeadTaps * dpitch * 4 + (int)sizeof(HeadBarriers) + 64;
   const int stages = std::min(kHeadMaxStages, (kHeadSmemBudget - fixed) / stage_bytes);
   if (smem_bytes) *smem_bytes = fixed + stages * stage_bytes;
   return stages;
@@ -288,12 +314,12 @@ static int head_stage_count(int w, int c, int* smem_bytes) {
 
 bool head_conv_supported(int h, int w, int c, int cout) {
   (void)h;
-  if (cout != 3 || c % 64 != 0 || c < 64 || c > 512 || w < 8) return false;
+  if (cout != 3 || c % 64 != 0 || c < 64 || c > 64 * kHeadMaxKpt || w < 8 || w % 4 != 0) return false;
   return head_stage_count(w, c, nullptr) >= 2;
 }
 
 int launch_head_conv(const void* x_op, const float* scale, const float* shift, const void* w_packed, const float* bias,
-                     float* out_nchw, int batch, int h, int w, int c, int op_dtype, cudaStream_t stream) {
+                     float* out_nchw, int batch, int h, int w, int c, int op_dtype, cudaStream_t stream, int max_stages) {
   CLPK_REQUIRE(head_conv_supported(h, w, c, 3), "fused head kernel unsupported for W=%d C=%d", w, c);
   static std::mutex mu;
   static bool attr_done[64] = {};
@@ -312,10 +338,11 @@ int launch_head_conv(const void* x_op, const float* scale, const float* shift, c
   p.kpt = c / 64;
   int smem_bytes = 0;
   p.stages = head_stage_count(w, c, &smem_bytes);
+  if (max_stages >= 2 && max_stages < p.stages) p.stages = max_stages;  // (experiments: CLPK_HEAD_STAGES at plan creation)
   p.rows_total = batch * h;
   p.band = (p.rows_total + num_sms() - 1) / num_sms();
   p.op_f16 = (op_dtype == CLPK_OP_F16) ? 1 : 0;
-  p.dpitch = (w + 2 + 3) / 4 * 4;
+  p.dpitch = w + 8;
   p.scale = scale; p.shift = shift; p.bias = bias; p.out = out_nchw;
   const CUtensorMapDataType dt = p.op_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap map_a, map_w;
@@ -369,5 +396,5 @@ extern "C" int clpk_head_conv(const void* x_op, const float* in_scale, const flo
                               const float* bias, float* out_nchw, int batch, int h, int w, int c, int op_dtype, void* stream) {
   CLPK_REQUIRE(x_op && in_scale && in_shift && w_packed && bias && out_nchw && batch > 0, "clpk_head_conv: bad arguments");
   CLPK_REQUIRE(op_dtype == CLPK_OP_BF16 || op_dtype == CLPK_OP_F16, "clpk_head_conv: operand dtype %d unknown", op_dtype);
-  return launch_head_conv(x_op, in_scale, in_shift, w_packed, bias, out_nchw, batch, h, w, c, op_dtype, (cudaStream_t)stream);
+  return launch_head_conv(x_op, in_scale, in_shift, w_packed, bias, out_nchw, batch, h, w, c, op_dtype, (cudaStream_t)stream, 0);
 }

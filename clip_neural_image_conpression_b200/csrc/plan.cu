@@ -114,6 +114,7 @@ struct clpk_plan {
   bool head16 = false;       // the last transposed conv writes only the 16-bit copy X16[0] (see head16_on)
   bool head_fused = false;   // out_norm + out conv as the single head_conv kernel (env CLPK_HEAD_FUSED, default 1)
   uint16_t* head_w = nullptr;  // [32][base] packed head weight (head_conv.cu)
+  int head_stages = 0;       // experiments: cap of the head kernel's A ring (env CLPK_HEAD_STAGES at plan creation)
   bool x16_gn = false;       // env CLPK_X16=1: GroupNorms on the residual stream read X16 instead of fp32 X
   float* Yf = nullptr;       // fp32 conv1 output, only for ResBlocks whose GroupNorm statistics cannot be fused
   void* gn_ws = nullptr;
@@ -357,7 +358,7 @@ int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s, cudaEvent_t 
   if (P->head_fused) {
     CLPK_TIMED(P, kProfConvOther, s,
                launch_head_conv(P->X16[0], P->out_gn.scale, P->out_gn.shift, P->head_w, P->out_conv.bias, P->eps_buf, P->B,
-                                P->H, P->W, c.base, c.op_dtype, s));  // out(out_norm(x)) -> eps_buf (NCHW)
+                                P->H, P->W, c.base, c.op_dtype, s, P->head_stages));  // out(out_norm(x)) -> eps_buf (NCHW)
   } else {
     CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->out_conv.L, s));  // -> eps_buf (NCHW)
   }
@@ -534,6 +535,8 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     const char* e = getenv("CLPK_HEAD_FUSED");
     P->head_fused = !(e && atoi(e) == 0) && !P->fuse_head && P->head16 &&
                     head_conv_supported(height, width, cfg->base, cfg->img_ch);
+    const char* hs = getenv("CLPK_HEAD_STAGES");
+    P->head_stages = hs ? atoi(hs) : 0;
   }
   if (P->head_fused) {  // out_norm is applied inside head_conv: only the (scale, shift) table is computed
     P->out_gn.in_consumer = true;
