@@ -42,7 +42,7 @@ struct __align__(8) PipeBarriers {
   uint64_t ready[kMaxStages];   // kXform: the stage's A slab has been normalised in place (leader CTA's copy is waited on)
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t res_full[4 * kEpiGroups][4];  // per epilogue warp: residual sub-box landed in the warp's staging slot s
+  uint64_t res_full[4 * kEpiGroups][6];  // per epilogue warp: residual sub-box landed in the warp's staging slot s
   uint32_t tmem_base;
 };
 
@@ -292,7 +292,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(&bars->tmem_empty[s], 4 * kEpiGroups * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int g = 0; g < 4 * kEpiGroups; ++g)
-      for (int s = 0; s < 4; ++s) mbar_init(&bars->res_full[g][s], 1);
+      for (int s = 0; s < 6; ++s) mbar_init(&bars->res_full[g][s], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -1157,6 +1157,11 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     int per_group = p.ep.resid ? 3 : 2;
     while (per_group > 1 && (kSmemBudget - fixed - kEpiGroups * per_group * kStagingBytes) / stage_bytes < want_stages) --per_group;
     { const char* e = getenv("CLPK_IGEMM_SLOTS"); if (e && atoi(e) >= 1 && atoi(e) <= 3) per_group = atoi(e); }
+    if (kind == CLPK_CONVT_4X4_S2) {  // (a transposed conv is bound by its residual look-ahead: slots beat ring depth)
+      const char* e = getenv("CLPK_CONVT_SLOTS");
+      const int want = e ? atoi(e) : per_group;
+      if (want >= 1 && want <= 6 && (kSmemBudget - fixed - kEpiGroups * want * kStagingBytes) / stage_bytes >= 3) per_group = want;
+    }
     p.n_staging = kEpiGroups * per_group;
     if ((kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes < 2) {
       p.n_staging = 0;
