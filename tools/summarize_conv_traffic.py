@@ -22,16 +22,18 @@ def main():
     rows = list(csv.DictReader([ln for ln in src.read_text().splitlines() if not ln.startswith("==")]))
     by = collections.OrderedDict()
     for r in rows:
-        d = by.setdefault(int(r["ID"]), {"name": r["Kernel Name"][6:34], "grid": r["Grid Size"]})
+        d = by.setdefault(int(r["ID"]), {"name": r["Kernel Name"].replace("void clpk::", "")[:28], "grid": r["Grid Size"]})
         v, u, m = float(r["Metric Value"].replace(",", "")), r["Metric Unit"], r["Metric Name"]
         if "bytes" in m:
             v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         if "time" in m:
             v *= {"ns": 1e-3, "us": 1, "ms": 1e3}.get(u, 1)
         d[m] = v
-    out = ["# ncu --metrics (time, DRAM bytes, L2 bytes, tensor-pipe activity) --clock-control none over the 36 conv_igemm launches of ONE DDIM step",
-           "# command: python bench.py --steps 1 --warmup 3 --ddim-steps 2 --no-cpu-baseline   (-k regex:conv_igemm -s 216 -c 36)",
-           "# launch order = stem, [ResBlock conv1, conv2] x2 + down per level, mid x2, [conv1, conv2] x2 + up per level, out",
+    import subprocess
+    head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    out = ["# ncu --metrics (time, DRAM bytes, L2 bytes, tensor-pipe activity) --clock-control none over the 36 conv launches of ONE DDIM step",
+           f"# command: python bench.py --steps 1 --warmup 3 --ddim-steps 2 --no-cpu-baseline --no-extras   (-k regex:conv_igemm|head_conv -s 216 -c 36); kernels of commit {head}",
+           "# launch order = stem, [ResBlock conv1, conv2] x2 + down per level, mid x2, [conv1, conv2] x2 + up per level, head (#35: head_conv_kernel = out_norm + out)",
            f"{'#':>2s} {'kernel':28s} {'grid':12s} {'us':>8s} {'dram_rd_MB':>10s} {'dram_wr_MB':>10s} {'l2_MB':>9s} {'tensor%':>8s}"]
     items = list(by.values())
     tt = 0.0

@@ -35,7 +35,7 @@ def main():
         a[1] += v
     tot = sum(a[1] for a in agg.values())
     out = [f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` over "
-           f"`python bench.py --steps 1 --warmup 3 --ddim-steps 2 --no-cpu-baseline` ({len(seq)} launches)",
+           f"`python bench.py --steps 1 --warmup 3 --ddim-steps 2 --no-cpu-baseline --no-extras` ({len(seq)} launches)",
            "# per-launch times are cold-cache and serialised: compare SHARES, not absolutes", "",
            f"{'kernel':58s} {'launches':>8s} {'total_us':>10s} {'share':>7s} {'avg_us':>9s}"]
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -49,6 +49,9 @@ def main():
         out.append(f"# forward total {sum(s[3] for s in seq[idx[0]:idx[1]]):.1f} us in {idx[1] - idx[0]} launches")
     (outdir / f"launches_{tag}.txt").write_text("\n".join(out) + "\n")
 
+    if str(rep) == "-":   # launch list only (the per-kernel table comes from tools/summarize_full.py)
+        print((outdir / f"launches_{tag}.txt").read_text()[:3000])
+        return
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
