@@ -119,3 +119,39 @@ def test_shard_bounds_partition():
     assert [parallel.shard_bounds(1024, r, 8) for r in (0, 7)] == [(0, 128), (896, 1024)]
     with pytest.raises(ValueError):
         parallel.shard_bounds(4, 4, 4)
+
+
+def test_reference_arm_runs_the_staged_reference(tmp_path):
+    """bench.py's CPU arm: with oracle/_ref present it times the UNMODIFIED reference (zipimport of the archive written by
+    oracle/stage_ref.py); the archive holds exactly the reference's .py files.  64 px keeps this at a few seconds."""
+    import importlib.util
+    import zipfile
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    archive = root / "oracle" / "_ref" / "clip_feature_codec.zip"
+    if not archive.exists():
+        if not Path("/root/reference/src/clip_feature_codec").exists():
+            pytest.skip("neither the staged archive nor the reference tree is present")
+        from oracle import stage_ref
+        assert stage_ref.stage()
+    names = zipfile.ZipFile(archive).namelist()
+    assert "clip_feature_codec/models/unet.py" in names and "clip_feature_codec/diffusion/ddim.py" in names
+    ref_tree = Path("/root/reference/src/clip_feature_codec")
+    if ref_tree.exists():      # byte-identical to the sources where they lie
+        z = zipfile.ZipFile(archive)
+        for n in names:
+            assert z.read(n) == (ref_tree / n.split("/", 1)[1]).read_bytes(), n
+    spec = importlib.util.spec_from_file_location("bench_mod", root / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ips, ms, cores, kind = bench.cpu_reference_sample(64, 1, 1, 0)
+    assert kind == "reference" and ips > 0 and ms > 0 and cores >= 1
+
+
+def test_bench_extras_are_declared():
+    """The bench line's contract keys for the extra configurations exist in the source (cheap guard against renames)."""
+    from pathlib import Path
+    src = (Path(__file__).resolve().parents[1] / "bench.py").read_text()
+    for key in ("bf16_operands", "config3_store1024", "config4_ddim250_b64", "config5_wide_512px", "cpu_baseline", "roofline",
+                "h2d_bytes_per_step", "gpu_launches"):
+        assert key in src
