@@ -40,8 +40,10 @@ struct __align__(8) PipeBarriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t ready[kMaxStages];   // kXform: the stage's A slab has been normalised in place (leader CTA's copy is waited on)
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[4];    // 2 accumulator buffers; 4 in the two-rows-per-item slab variant (2 rows x 2 buffers)
+  uint64_t tmem_empty[4];
+  uint64_t full_b[4];       // kRows2: weight-block ring (the A slabs use full / empty)
+  uint64_t empty_b[4];
   uint64_t res_full[4 * kEpiGroups][6];  // per epilogue warp: residual sub-box landed in the warp's staging slot s
   uint32_t tmem_base;
 };
@@ -57,7 +59,8 @@ struct TileCoord {
 __device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) {
   return (uint32_t)(((unsigned long long)n * f.mul) >> f.shift);
 }
-__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int item, int rank) {
+// rows2 (two-rows-per-item slab variant): work items are pairs of vertically adjacent row tiles; `sub` selects the row
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int item, int rank, int sub = 0) {
   TileCoord c;
   if (p.reverse) item = p.num_tiles - 1 - item;  // walk the tensor back to front (see IgemmParams::reverse)
   uint32_t r = fd_div((uint32_t)item, p.fd_tiles_n);
@@ -69,7 +72,11 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int item,
   r = fd_div(msp, p.fd_tiles_w);
   const int tw = (int)(msp - r * (uint32_t)p.tiles_w);
   const uint32_t b = fd_div(r, p.fd_tiles_h);
-  const int th = (int)(r - b * (uint32_t)p.tiles_h);
+  int th = (int)(r - b * p.fd_tiles_h.d);   // (divisor = row tiles, or row-tile PAIRS in rows2 mode)
+  if (p.rows2) {  // fd_tiles_h divides by the number of row PAIRS
+    th = 2 * th + sub;
+    c.ok = c.ok && th < p.tiles_h;
+  }
   c.b = (int)b;
   c.th = th;
   c.tw = tw;
@@ -233,7 +240,7 @@ __device__ __forceinline__ void gn_chunk_reduce(const float (&sums)[16], int lan
 
 constexpr int kSlabABytes = 17 * 1024;  // (128 + 2) slab rows x 128 B = 16640, padded to the 1024-byte swizzle-atom pitch
 
-template <int BLOCK_K, int NCTA, bool kSlab, bool kXform>
+template <int BLOCK_K, int NCTA, bool kSlab, bool kXform, bool kRows2 = false>
 __global__ void __launch_bounds__(kNumThreads + (kXform ? kXformThreads : 0), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ OutMaps maps_out, const __grid_constant__ OutMaps maps_res,
@@ -247,6 +254,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   constexpr int kABytes = kSlab ? kSlabABytes : kAAtomBytes * kAtoms;   // one A stage
   static_assert(!kSlab || BLOCK_K == 64, "slab mode stages 64-channel slabs");
   static_assert(!kXform || kSlab, "the input transform works on row slabs");
+  static_assert(!kRows2 || (kSlab && !kXform && NCTA == 2), "two rows per item: CTA-pair slab mainloop only");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   CLPK_GTRACE(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 300);  // kernel entry
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -260,7 +268,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int cluster_id = blockIdx.x / NCTA, num_clusters = gridDim.x / NCTA;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.stages * kABytes;
-  uint8_t* smem_s = smem_b + (size_t)p.stages * b_bytes;  // staging buffers (1024-aligned: all sizes are multiples)
+  uint8_t* smem_s = smem_b + (size_t)(kRows2 ? p.stages_b : p.stages) * b_bytes;  // staging buffers (1024-aligned sizes)
   EpiVectors vec_s;
   vec_s.mul = reinterpret_cast<float*>(smem_s + (size_t)p.n_staging * kStagingBytes);
   vec_s.add = vec_s.mul + p.block_n;
@@ -287,9 +295,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(&bars->empty[s], 1);
       mbar_init(&bars->ready[s], 4 * NCTA);  // one arrive per transform warp (of both CTAs of a pair)
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
       mbar_init(&bars->tmem_empty[s], 4 * kEpiGroups * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&bars->full_b[s], 1);
+      mbar_init(&bars->empty_b[s], 1);
     }
     for (int g = 0; g < 4 * kEpiGroups; ++g)
       for (int s = 0; s < 6; ++s) mbar_init(&bars->res_full[g][s], 1);
@@ -306,7 +316,113 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   pdl_prologue_done();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   CLPK_GTRACE(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 301);  // setup done
 
-  if (warp == 0) {
+  if (kRows2 && warp == 0) {
+    // ===================================================== TMA producer, two output rows per item (kRows2)
+    // Item = row tiles (h0, h0 + 1) of one 128-pixel column segment, two accumulators.  Per 64-channel block the four
+    // slabs of input rows h0-1 .. h0+2 go through the A ring (slab i feeds row h0 with kernel row i and row h0+1 with
+    // kernel row i-1) and the three weight blocks B_r (taps (r, 0..2)) through their own ring: every slab is staged once
+    // for two output rows (4 instead of 6 slab fills) and every weight block once for both rows (3 instead of 6) —
+    // 140 KB instead of 249 KB of operand fill per 128x128 output tile.  (Built to test whether the mainloop is bound by
+    // operand-fill bytes: it is not — see igemm_setup — so this variant is opt-in.)
+    // Issue order = consumption order: slab0 slab1 B0 slab2 B1 slab3 B2.
+    const uint32_t slab_tx = (uint32_t)(p.wbox + 2) * 128u, b_tx = (uint32_t)b_bytes;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int item = cluster_id; item < p.num_tiles; item += num_clusters) {
+      const TileCoord tc = decode_tile(p, item, (int)rank, 0);
+      const int w_row = tc.n0 + (int)rank * b_rows;
+      for (int kc = 0; kc < p.kpt; ++kc) {
+#pragma unroll
+        for (int step = 0; step < 7; ++step) {
+          const bool is_b = (step == 2 || step == 4 || step == 6);
+          const int idx = is_b ? (step - 2) / 2 : (step < 2 ? step : (step + 1) / 2);   // B_r index or slab index
+          if (!is_b) {
+            mbar_wait(&bars->empty[sa], pa ^ 1u);
+            if (elect_one()) {
+              const uint32_t lead_full = mapa_u32(smem_u32(&bars->full[sa]), 0u);
+              if (rank == 0) mbar_arrive_expect_tx(&bars->full[sa], 2u * slab_tx);
+              tma_load_5d_pair(smem_a + (size_t)sa * kABytes, &map_a, lead_full, kc * 64, tc.w0 - 1, 0, tc.h0 + idx - 1, tc.b);
+            }
+            __syncwarp();
+            if (++sa == p.stages) { sa = 0; pa ^= 1u; }
+          } else {
+            mbar_wait(&bars->empty_b[sb], pb ^ 1u);
+            if (elect_one()) {
+              const uint32_t lead_full = mapa_u32(smem_u32(&bars->full_b[sb]), 0u);
+              if (rank == 0) mbar_arrive_expect_tx(&bars->full_b[sb], 2u * b_tx);
+#pragma unroll
+              for (int s3 = 0; s3 < 3; ++s3)
+                tma_load_2d_pair(smem_b + (size_t)sb * b_bytes + s3 * b_atom_bytes, &map_w, lead_full,
+                                 (idx * 3 + s3) * p.cin + kc * 64, w_row);
+            }
+            __syncwarp();
+            if (++sb == p.stages_b) { sb = 0; pb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (kRows2 && warp == 1) {
+    // ===================================================== MMA issuer, two output rows per item (leader CTA issues)
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_16bit(kTileM * NCTA, p.block_n, p.op_f16 != 0);
+      const uint64_t adesc0 = make_kmajor_desc<kSwizzle>(smem_u32(smem_a));
+      const uint64_t bdesc0 = make_kmajor_desc<kSwizzle>(smem_u32(smem_b));
+      const uint64_t a_step = (uint64_t)(kABytes >> 4), b_step = (uint64_t)(b_bytes >> 4);
+      int sa = 0, sb = 0;      // ring slots of the NEXT slab / weight block to be waited for
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int item = cluster_id; item < p.num_tiles; item += num_clusters, ++it) {
+        const int as0 = (2 * it) & 3;                       // accumulators of rows h0 and h0 + 1
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;   // buffer index (2 it + sub) & 3 is reused every 2 items
+        mbar_wait(&bars->tmem_empty[as0], aphase ^ 1u);
+        mbar_wait(&bars->tmem_empty[as0 + 1], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d0 = tmem_base + (uint32_t)(as0 * p.block_n), tmem_d1 = tmem_d0 + (uint32_t)p.block_n;
+        for (int kc = 0; kc < p.kpt; ++kc) {
+          int slot[4];         // ring slots of this channel block's four slabs
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            // slabs first needed at this step: 0 and 1 at r = 0, then r + 1
+#pragma unroll
+            for (int i = (r == 0 ? 0 : r + 1); i <= r + 1; ++i) {
+              mbar_wait(&bars->full[sa], pa);
+              slot[i] = sa;
+              if (++sa == p.stages) { sa = 0; pa ^= 1u; }
+            }
+            mbar_wait(&bars->full_b[sb], pb);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t bdesc = bdesc0 + b_step * (uint64_t)sb;
+              const uint64_t ad0 = adesc0 + a_step * (uint64_t)slot[r], ad1 = adesc0 + a_step * (uint64_t)slot[r + 1];
+#pragma unroll
+              for (int s3 = 0; s3 < 3; ++s3) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t ao = (uint64_t)(s3 * 8 + 2 * kk);
+                  const uint64_t bo = (uint64_t)(s3 * (b_atom_bytes >> 4) + 2 * kk);
+                  const uint32_t acc = (s3 == 0 && kk == 0 && r == 0) ? (uint32_t)(kc != 0) : 1u;
+                  umma_f16kind_pair(tmem_d0, ad0 + ao, bdesc + bo, idesc, acc);
+                  umma_f16kind_pair(tmem_d1, ad1 + ao, bdesc + bo, idesc, acc);
+                }
+              }
+              // the weight block and slab r are done (slab r + 1 is used once more, by row h0 at the next step)
+              umma_commit_pair(&bars->empty_b[sb]);
+              umma_commit_pair(&bars->empty[slot[r]]);
+              if (r == 2) {
+                umma_commit_pair(&bars->empty[slot[3]]);
+                if (kc == p.kpt - 1) {
+                  umma_commit_pair(&bars->tmem_full[as0]);
+                  umma_commit_pair(&bars->tmem_full[as0 + 1]);
+                }
+              }
+            }
+            __syncwarp();
+            if (++sb == p.stages_b) { sb = 0; pb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ===================================================== TMA producer
     // The whole warp walks the loop converged (every lane waits on the barrier); only the issue of the uniform-datapath
     // TMA instructions sits under elect.sync.  Issuing them from a divergent `if (lane == 0)` region makes the compiler
@@ -574,14 +690,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int cpg = ep.gn_cpg;
     const int npairs = cpg >= 32 ? 1 : (cpg > 0 ? 32 / cpg : 0);
     const int npairs_shift = npairs >= 8 ? 3 : npairs >= 4 ? 2 : npairs >= 2 ? 1 : 0;
-    int ld_tile = cluster_id, ld_c = 32 * eg;
+    int ld_tile = cluster_id, ld_c = 32 * eg, ld_sub = 0;
     uint32_t ld_slot = 0;
-    int lc_tile = -1;
+    int lc_tile = -1, lc_sub = -1;
     TileCoord lc{};
     auto issue_res_load = [&]() {  // lane 0 only
-      while (ld_tile < p.num_tiles && ld_c >= p.block_n) { ld_c = 32 * eg; ld_tile += num_clusters; }
+      while (ld_tile < p.num_tiles && ld_c >= p.block_n) {
+        ld_c = 32 * eg;
+        if (kRows2 && ld_sub == 0) ld_sub = 1; else { ld_sub = 0; ld_tile += num_clusters; }
+      }
       if (ld_tile >= p.num_tiles) return;
-      if (ld_tile != lc_tile) { lc = decode_tile(p, ld_tile, (int)rank); lc_tile = ld_tile; }  // (integer divisions)
+      if (ld_tile != lc_tile || ld_sub != lc_sub) { lc = decode_tile(p, ld_tile, (int)rank, ld_sub); lc_tile = ld_tile; lc_sub = ld_sub; }
       mbar_arrive_expect_tx(&res_full[ld_slot], (uint32_t)kWarpSlotBytes);
       tma_load_5d(wslots + (size_t)ld_slot * kWarpSlotBytes, &maps_res.m[lc.phase], &res_full[ld_slot], lc.n0 + ld_c,
                   lc.w0 + sub_w, 0, lc.h0 + sub_h, lc.b);
@@ -591,10 +710,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (res_tma && lane == 0 && !(CLPK_DBG(1)))
       for (int i = 0; i < A; ++i) issue_res_load();
     const uint32_t lead_tmem_empty0 = (NCTA == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[0]), 0u) : 0u;
-    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      const TileCoord tc = decode_tile(p, tile, (int)rank);
+    constexpr int kSub = kRows2 ? 2 : 1;     // row tiles per work item; TMEM holds 2 * kSub accumulators
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters)
+    for (int sub = 0; sub < kSub; ++sub, ++it) {
+      const int as = it & (2 * kSub - 1);
+      const uint32_t aphase = (uint32_t)(it >> (kRows2 ? 2 : 1)) & 1u;
+      const TileCoord tc = decode_tile(p, tile, (int)rank, sub);
       const int h = tc.h0 + hl, w = tc.w0 + wl;
       const bool valid = tc.ok && (hl < p.hbox) && (h < p.grid_h) && (w < p.grid_w);
       const int oh = h * p.out_scale + (tc.phase >> 1), ow = w * p.out_scale + (tc.phase & 1);
@@ -1123,16 +1244,37 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   { int gh, gw, ph; tile_geometry(kind, h_in, w_in, &gh, &gw, &p.wbox, &p.hbox, &ph); }
   p.tiles_w = (p.grid_w + p.wbox - 1) / p.wbox;
   p.tiles_h = (p.grid_h + p.hbox - 1) / p.hbox;
-  p.spatial_tiles = batch * p.tiles_h * p.tiles_w;
-  const long long nt = (long long)((p.spatial_tiles + p.ncta - 1) / p.ncta) * p.phases * p.n_tiles_n;
-  CLPK_REQUIRE(nt < (1ll << 30), "too many tiles");
-  p.num_tiles = (int)nt;
-  p.fd_tiles_n = make_fastdiv(p.n_tiles_n);
-  p.fd_phases = make_fastdiv(p.phases);
-  p.fd_tiles_w = make_fastdiv(p.tiles_w);
-  p.fd_tiles_h = make_fastdiv(p.tiles_h);
-  p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
+  // two rows per item (see the kRows2 producer): CTA-pair slab convs without the in-smem input transform; whether the two
+  // operand rings fit shared memory is decided below, together with the staging slots
+  p.rows2 = 0;
+  if (p.slab && p.ncta == 2 && !p.xform && p.tiles_h >= 2 && 4 * p.block_n <= 512) {
+    // only where pairing rows does not cost a wave: an item is twice as long, so ceil(items / pairs) must halve
+    // (256 px at batch 8: 28 -> 14 items per CTA pair; 128 px: 7 -> 4 would be 14 % more work on the critical CTA)
+    const int pairs = std::max(1, num_sms() / 2);
+    const long long n1 = ((long long)batch * p.tiles_h * p.tiles_w + 1) / 2 * p.n_tiles_n;
+    const long long n2 = ((long long)batch * ((p.tiles_h + 1) / 2) * p.tiles_w + 1) / 2 * p.n_tiles_n;
+    const bool no_extra_wave = 2 * ((n2 + pairs - 1) / pairs) <= (n1 + pairs - 1) / pairs;
+    // OFF by default (env CLPK_IGEMM_ROWS2=1: where wave-neutral, =2: always): measured on B200 it is neutral at best
+    // (256 px conv1 123.9 -> 126.0 us with 44 % less operand fill; conv2 loses a residual staging slot to the second ring
+    // unless the weight ring is cut to 2) — the slab mainloop is NOT bound by operand-fill bytes.
+    const char* e = getenv("CLPK_IGEMM_ROWS2");
+    p.rows2 = e ? (atoi(e) == 1 ? (no_extra_wave ? 1 : 0) : atoi(e) == 2 ? 1 : 0) : 0;
+  }
+  auto compute_tiles = [&]() -> int {
+    const int item_rows = p.rows2 ? (p.tiles_h + 1) / 2 : p.tiles_h;   // row tiles (or row-tile pairs) per image column
+    p.spatial_tiles = batch * item_rows * p.tiles_w;
+    const long long nt = (long long)((p.spatial_tiles + p.ncta - 1) / p.ncta) * p.phases * p.n_tiles_n;
+    CLPK_REQUIRE(nt < (1ll << 30), "too many tiles");
+    p.num_tiles = (int)nt;
+    p.fd_tiles_n = make_fastdiv(p.n_tiles_n);
+    p.fd_phases = make_fastdiv(p.phases);
+    p.fd_tiles_w = make_fastdiv(p.tiles_w);
+    p.fd_tiles_h = make_fastdiv(item_rows);
+    p.tmem_cols = 32;
+    while (p.tmem_cols < (p.rows2 ? 4 : 2) * p.block_n) p.tmem_cols *= 2;
+    return CLPK_OK;
+  };
+  CLPK_TRY_RC(compute_tiles());
   const int stage_bytes = p.slab ? kSlabABytes + 3 * (p.block_n / p.ncta) * 128
                                  : kTileM * p.block_k * 2 + (p.block_n / p.ncta) * p.block_k * 2;
   // chunked epilogue whenever the tile has >= 32 channels and an NHWC output; its fp32 output (if any) is staged
@@ -1156,7 +1298,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     if (p.xform) { const char* e = getenv("CLPK_XF_STAGES"); want_stages = e ? atoi(e) : 3; }
     int per_group = p.ep.resid ? 3 : 2;
     while (per_group > 1 && (kSmemBudget - fixed - kEpiGroups * per_group * kStagingBytes) / stage_bytes < want_stages) --per_group;
-    { const char* e = getenv("CLPK_IGEMM_SLOTS"); if (e && atoi(e) >= 1 && atoi(e) <= 3) per_group = atoi(e); }
+    { const char* e = getenv("CLPK_IGEMM_SLOTS"); if (e && atoi(e) >= 1 && atoi(e) <= 4) per_group = atoi(e); }
     if (kind == CLPK_CONVT_4X4_S2) {  // (a transposed conv is bound by its residual look-ahead: slots beat ring depth)
       const char* e = getenv("CLPK_CONVT_SLOTS");
       const int want = e ? atoi(e) : per_group;
@@ -1187,6 +1329,27 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   p.stages = std::min(kMaxStages, (kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes);
   CLPK_REQUIRE(p.stages >= 2, "tile does not fit shared memory");
   out->smem_bytes = p.stages * stage_bytes + p.n_staging * kStagingBytes + fixed;
+  p.stages_b = 0;
+  if (p.rows2) {
+    // two rings: slabs (17 KB each; 2 in use + prefetch) and weight blocks (3 taps of a kernel row; 1 in use + prefetch).
+    // Wanted: >= 4 slabs + 3 weight blocks; staging slots are given up (down to 1 per group) before ring depth.
+    const int bb = 3 * (p.block_n / p.ncta) * 128;
+    int nb = 2;
+    { const char* e = getenv("CLPK_ROWS2_NB"); if (e && atoi(e) >= 2 && atoi(e) <= 4) nb = atoi(e); }
+    int per_group = p.n_staging / kEpiGroups;
+    auto na_for = [&](int pg) { return (kSmemBudget - fixed - kEpiGroups * pg * kStagingBytes - nb * bb) / kSlabABytes; };
+    while (per_group > 1 && na_for(per_group) < 4) --per_group;
+    const int na = std::min(kMaxStages, na_for(per_group));
+    if (p.n_staging > 0 && na >= 3) {
+      p.n_staging = kEpiGroups * per_group;
+      p.stages = na;
+      p.stages_b = nb;
+      out->smem_bytes = na * kSlabABytes + nb * bb + p.n_staging * kStagingBytes + fixed;
+    } else {
+      p.rows2 = 0;   // does not fit: back to one row per item
+      CLPK_TRY_RC(compute_tiles());
+    }
+  }
   out->grid = p.ncta * std::min(p.num_tiles, num_sms() / p.ncta);
 
   const int atom_k = std::min(p.block_k, 64);  // one TMA box = one swizzle atom (<= 128 bytes of K per row)
@@ -1242,9 +1405,9 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   return rc;
 }
 
-template <int BK, int NC, bool SLAB = false, bool XF = false>
+template <int BK, int NC, bool SLAB = false, bool XF = false, bool R2 = false>
 static cudaError_t set_smem_attr() {
-  return cudaFuncSetAttribute(conv_igemm_kernel<BK, NC, SLAB, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  return cudaFuncSetAttribute(conv_igemm_kernel<BK, NC, SLAB, XF, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
 }
 
 // function attributes are per device (context): set them once for every device this process launches on
@@ -1266,12 +1429,13 @@ int igemm_init() {
   if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 1, true>();
   if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2, true, true>();
   if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 1, true, true>();
+  if (attr_err == cudaSuccess) attr_err = set_smem_attr<64, 2, true, false, true>();
   CLPK_CHECK_CUDA(attr_err);
   done[dev] = true;
   return CLPK_OK;
 }
 
-template <int BK, int NC, bool SLAB = false, bool XF = false>
+template <int BK, int NC, bool SLAB = false, bool XF = false, bool R2 = false>
 static cudaError_t launch_variant(const IgemmLaunch& L, cudaStream_t stream) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)L.grid);
@@ -1294,14 +1458,15 @@ static cudaError_t launch_variant(const IgemmLaunch& L, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BK, NC, SLAB, XF>, L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
+  return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BK, NC, SLAB, XF, R2>, L.map_a, L.map_w, L.maps_out, L.maps_res, L.p);
 }
 
 int igemm_launch(const IgemmLaunch& L, cudaStream_t stream) {
   int irc = igemm_init();
   if (irc) return irc;
   cudaError_t e;
-  if (L.p.slab && L.p.xform) e = (L.p.ncta == 2) ? launch_variant<64, 2, true, true>(L, stream) : launch_variant<64, 1, true, true>(L, stream);
+  if (L.p.slab && L.p.rows2) e = launch_variant<64, 2, true, false, true>(L, stream);
+  else if (L.p.slab && L.p.xform) e = (L.p.ncta == 2) ? launch_variant<64, 2, true, true>(L, stream) : launch_variant<64, 1, true, true>(L, stream);
   else if (L.p.slab) e = (L.p.ncta == 2) ? launch_variant<64, 2, true>(L, stream) : launch_variant<64, 1, true>(L, stream);
   else if (L.p.block_k == 128) e = (L.p.ncta == 2) ? launch_variant<128, 2>(L, stream) : launch_variant<128, 1>(L, stream);
   else if (L.p.block_k == 64) e = (L.p.ncta == 2) ? launch_variant<64, 2>(L, stream) : launch_variant<64, 1>(L, stream);

@@ -34,6 +34,9 @@ struct IgemmParams {
   int tiles_w, tiles_h;
   int phases, taps, kpt;    // kpt = k-blocks per tap = cin / block_k
   int num_tiles, stages, tmem_cols;   // num_tiles = work items: ceil(spatial tiles / ncta) * phases * n_tiles_n
+  int rows2;                // 1: two-rows-per-item slab variant (CTA pairs): a work item = row tiles (h0, h0+1) of one column
+                            // segment with two accumulators; slabs and weight blocks are staged once for both rows
+  int stages_b;             // rows2: depth of the weight-block ring (`stages` = depth of the slab ring)
   int ncta;                 // 1, or 2 = CTA pairs (tcgen05 cta_group::2): two M tiles share one B tile split over the pair
   int spatial_tiles;        // batch * tiles_h * tiles_w
   int op_f16;               // operand format: 1 = fp16, 0 = bf16

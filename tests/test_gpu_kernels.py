@@ -346,6 +346,36 @@ def test_groupnorm_affine_from_conv_statistics(ops):
     assert float(torch.linalg.norm(fused - plain) / torch.linalg.norm(plain)) < 1e-3
 
 
+@pytest.mark.parametrize("b,h,w,cin,cout,film,resid", [
+    (2, 6, 256, 128, 128, True, False),     # conv1-like: FiLM, 16-bit output, statistics
+    (3, 5, 192, 64, 64, False, True),       # odd H (masked second row of the last pair), ragged W, residual
+    (1, 2, 128, 192, 128, False, True),     # three channel blocks, a single row pair
+])
+def test_conv_two_rows_per_item_variant(ops, monkeypatch, b, h, w, cin, cout, film, resid):
+    """CLPK_IGEMM_ROWS2=2 (opt-in mainloop: two output rows per work item, separate slab / weight rings, four TMEM
+    accumulators) against the default one-row slab mainloop: same products, only the fp32 accumulation order differs
+    (channel block outer / kernel row inner instead of the reverse)."""
+    g = torch.Generator().manual_seed(31 + h + cin)
+    xb = torch.randn(b, h, w, cin, generator=g).to(torch.float16).cuda()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    kw = {}
+    if film:
+        kw.update(film_scale1p=(1 + 0.3 * torch.randn(b, cout, generator=g)).cuda(), film_shift=torch.randn(b, cout, generator=g).cuda())
+    if resid:
+        kw["resid"] = torch.randn(b, h, w, cout, generator=g).cuda()
+    wp = ops.pack_conv_weight(wt, 0)
+    ref = ops.conv_igemm(xb, wp, 0, cout, bias, want_f32=True, want_op=True, gn_groups=8, **kw)
+    monkeypatch.setenv("CLPK_IGEMM_ROWS2", "2")
+    two = ops.conv_igemm(xb, wp, 0, cout, bias, want_f32=True, want_op=True, gn_groups=8, **kw)
+    monkeypatch.delenv("CLPK_IGEMM_ROWS2")
+    scale = max(1.0, float(ref["f32"].abs().max()))
+    assert float((two["f32"] - ref["f32"]).abs().max()) < 2e-5 * scale
+    assert float((two["op"].float() - ref["op"].float()).abs().max()) <= 2.0 ** -10 * scale      # at most one fp16 ulp apart
+    assert torch.allclose(two["gn_stats"], ref["gn_stats"], rtol=1e-5, atol=1e-6)
+    assert not torch.equal(two["f32"], ref["f32"]) or cin == 64                                   # the switch changed the path
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("b,h,w,c", [
     (2, 6, 256, 128),      # two 128-pixel tiles per row, one row per CTA band (halo rows recomputed by the neighbours)
