@@ -13,6 +13,7 @@ $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_a_$TAG.log 2>&1
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum \
     --clock-control none -k regex:"conv_igemm|head_conv" -s 216 -c 36 --csv --log-file $OUT/convs_$TAG.csv $CMD > $OUT/ncu_b_$TAG.log 2>&1
+[ "${FULL:-1}" = "0" ] && { ls -la $OUT/*_$TAG* | tail -6; exit 0; }   # FULL=0: launch list + conv table only (2 min instead of 13)
 # one whole forward + DDIM update: 6 warm-up forwards x 74 kernels of the filter are skipped
 ncu --set full --clock-control none -k regex:"$K" -s 444 -c 74 -f -o /tmp/full_$TAG $CMD > $OUT/ncu_c_$TAG.log 2>&1
 ncu -i /tmp/full_$TAG.ncu-rep --page raw --csv > $OUT/full_$TAG.csv 2>/dev/null
