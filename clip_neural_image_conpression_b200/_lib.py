@@ -100,6 +100,8 @@ SIGNATURES = {
     "clpk_plan_work_breakdown": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "clpk_plan_groupnorm_bytes": (_i, [_vp, C.POINTER(C.c_double)]),
     "clpk_to_uint8_hwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "clpk_resample_u8": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
+    "clpk_u8_hwc_to_float_chw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "clpk_psnr_sqerr_u8": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
     "clpk_ddpm_combine": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp]),
     "clpk_ssim_ws_bytes": (_i64, [_i, _i, _i, _i]),

@@ -5,6 +5,8 @@ Drop-in for the reference CLI (PKG/cli/eval.py:33-86): same flags, same printed 
   * images are decoded in micro-batches (`--batch`, default 8) instead of one at a time;
   * under torchrun the manifest is partitioned contiguously over the ranks (one GPU each); PSNR sums are all-reduced
     and rank 0 prints — nothing is exchanged inside the DDIM loop;
+  * the originals are decoded on the host (PIL) but BICUBIC-resized and converted on the device, bit-identically to
+    Pillow (eval/resample.py);
   * PSNR and SSIM are computed on the device in the uint8 domain (SSIM = scikit-image's structural_similarity defaults,
     see eval/metrics.py); LPIPS / CLIP-similarity are NaN (lpips and open_clip need pretrained networks that are not
     part of this stack — the reference also reports NaN for LPIPS when the package is missing).
@@ -21,6 +23,7 @@ import torch
 from .. import parallel
 from ..diffusion import DDIMSampler, NoiseScheduler
 from ..eval.metrics import psnr_batch, ssim_batch
+from ..eval.resample import load_original_device
 from ..io.bitstream import read_bitstreams
 from ..pipeline import decode_codes
 from .reconstruct_diffusion import load_net, load_store_meta
@@ -43,7 +46,8 @@ def build_parser() -> argparse.ArgumentParser:
 
 
 def load_original(path: str, size: int) -> np.ndarray:
-    """eval.py:66-67 — RGB, BICUBIC resize, [-1,1], CHW."""
+    """eval.py:66-67 on the host — RGB, BICUBIC resize, [-1,1], CHW (kept as the reference-shaped helper; the CLI itself
+    uses eval.resample.load_original_device)."""
     from PIL import Image
 
     img = Image.open(path).convert("RGB").resize((size, size), Image.BICUBIC)
@@ -76,7 +80,8 @@ def main(argv=None) -> None:
     metrics = []
     for i in range(0, len(mine), 64):
         chunk = mine[i:i + 64]
-        orig = torch.from_numpy(np.stack([load_original(r["image"], args.size) for r in chunk])).to(device)
+        # eval.py:66-67 with the BICUBIC resize + float conversion on the device (bit-identical to Pillow / numpy)
+        orig = torch.stack([load_original_device(r["image"], args.size, device) for r in chunk])
         rec = recon[i:i + len(chunk)]
         for r, p, ss in zip(chunk, psnr_batch(orig, rec), ssim_batch(orig, rec)):   # eval.py:69-70, on the device
             metrics.append({"image": r["image"], "psnr": p, "ssim": ss, "lpips": float("nan"), "clip_sim": float("nan")})

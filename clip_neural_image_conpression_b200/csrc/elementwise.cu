@@ -592,6 +592,62 @@ extern "C" int clpk_film_apply(const float* x, const float* scale1p, const float
   return CLPK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ BICUBIC originals
+// PIL's 8-bit resampling (Pillow src/libImaging/Resample.c, what `Image.resize(size, Image.BICUBIC)` of
+// PKG/cli/eval.py:66 runs): one separable pass = out[o] = clip8((2^21 + sum_k kk[o][k] * in[xmin[o] + k]) >> 22) with
+// int32 fixed-point coefficients (22 fractional bits) precomputed per (input size, output size) on the host
+// (eval/resample.py, bit-identical to PIL's doubles).  The tensor is viewed as [outer][in_size][inner] uint8:
+// horizontal pass of an HWC image = (H, W, C), vertical pass = (1, H, W*C).  Integer arithmetic -> bit exact.
+__global__ void resample_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int* __restrict__ bounds,
+                                   const int* __restrict__ kk, int ksize, long long outer, int in_size, int out_size, int inner) {
+  const long long total = outer * out_size * inner;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % inner);
+    const long long r = idx / inner;
+    const int o = (int)(r % out_size);
+    const long long u = r / out_size;
+    const int xmin = __ldg(bounds + 2 * o), n = __ldg(bounds + 2 * o + 1);
+    const uint8_t* sp = src + (u * in_size + xmin) * inner + i;
+    const int* kp = kk + (long long)o * ksize;
+    int acc = 1 << 21;
+    for (int k = 0; k < n; ++k) acc += __ldg(kp + k) * (int)sp[(long long)k * inner];
+    acc >>= 22;   // arithmetic shift: floor, like PIL's clip8 lookup index
+    dst[idx] = (uint8_t)min(max(acc, 0), 255);
+  }
+}
+
+// float CHW in [-1, 1] from uint8 HWC: (float32(u8) / 127.5f) - 1.0f, two separately rounded ops (eval.py:67 numpy)
+__global__ void u8_hwc_to_float_chw_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int h, int w, int c) {
+  const long long total = (long long)h * w * c;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % w);
+    const long long r = idx / w;
+    const int y = (int)(r % h);
+    const int ch = (int)(r / h);
+    dst[idx] = __fsub_rn(__fdiv_rn((float)src[((long long)y * w + x) * c + ch], 127.5f), 1.0f);
+  }
+}
+
+extern "C" int clpk_resample_u8(const uint8_t* src, uint8_t* dst, const int32_t* bounds, const int32_t* kk, int ksize,
+                                int64_t outer, int in_size, int out_size, int inner, void* stream) {
+  CLPK_REQUIRE(src && dst && bounds && kk && ksize > 0 && outer > 0 && in_size > 0 && out_size > 0 && inner > 0,
+               "clpk_resample_u8: bad arguments");
+  const long long total = outer * out_size * inner;
+  resample_u8_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16), 256, 0, (cudaStream_t)stream>>>(
+      src, dst, bounds, kk, ksize, outer, in_size, out_size, inner);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
+extern "C" int clpk_u8_hwc_to_float_chw(const uint8_t* src, float* dst, int h, int w, int c, void* stream) {
+  CLPK_REQUIRE(src && dst && h > 0 && w > 0 && c > 0, "clpk_u8_hwc_to_float_chw: bad arguments");
+  const long long total = (long long)h * w * c;
+  u8_hwc_to_float_chw_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16), 256, 0,
+                               (cudaStream_t)stream>>>(src, dst, h, w, c);
+  CLPK_CHECK_LAUNCH();
+  return CLPK_OK;
+}
+
 extern "C" int clpk_to_uint8_hwc(const float* x, uint8_t* out, int batch, int ch, int h, int w, void* stream) {
   CLPK_REQUIRE(x && out && batch > 0 && ch > 0 && h > 0 && w > 0, "clpk_to_uint8_hwc: bad arguments");
   const long long total = (long long)batch * ch * h * w;

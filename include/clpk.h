@@ -256,6 +256,17 @@ int clpk_plan_groupnorm_bytes(const clpk_plan* plan, double* bytes);
 /* u8[b,h,w,c] = uint8((clamp(x[b,c,h,w],-1,1) + 1) * 127.5)  (truncation) — reconstruct_diffusion.py:55-56 */
 int clpk_to_uint8_hwc(const float* x_nchw_dev, uint8_t* out_hwc_dev, int batch, int ch, int h, int w, void* stream);
 
+/* The BICUBIC-resized original of the eval loop (PKG/cli/eval.py:66-67: `Image.open(p).convert("RGB").resize((S,S),
+ * Image.BICUBIC)`, then `float32(u8) / 127.5 - 1` as CHW) on the device, bit-identical to Pillow's 8-bit resampler.
+ * clpk_resample_u8 is ONE separable pass over a uint8 tensor viewed as [outer][in_size][inner] -> [outer][out_size][inner]
+ * (horizontal pass of an HWC image: outer = H, in = W, inner = C; vertical: outer = 1, in = H, inner = W*C; Pillow runs the
+ * horizontal pass first and skips a pass whose size does not change).  bounds [out_size][2] = (first input index, count),
+ * kk [out_size][ksize] = int32 coefficients with 22 fractional bits, exactly Pillow's precompute_coeffs +
+ * normalize_coeffs_8bpc (host: eval/resample.py::bicubic_coeffs).  out = clip8((2^21 + sum kk*in) >> 22). */
+int clpk_resample_u8(const uint8_t* src_dev, uint8_t* dst_dev, const int32_t* bounds_dev, const int32_t* kk_dev, int ksize,
+                     int64_t outer, int in_size, int out_size, int inner, void* stream);
+int clpk_u8_hwc_to_float_chw(const uint8_t* src_hwc_dev, float* dst_chw_dev, int h, int w, int c, void* stream);
+
 /* per-image PSNR in the uint8 domain (metrics.py:16-29): sq_err_sum[b] = sum((u8(a)-u8(b))^2) as exact int64;
  * the host finishes 20*log10(255/sqrt(mse)).  Inputs fp32 in [-1,1], any layout as long as both agree. */
 int clpk_psnr_sqerr_u8(const float* a_dev, const float* b_dev, int64_t* sq_err_sum_dev, int batch, int64_t per_image,

@@ -377,6 +377,71 @@ def ssim(img1: np.ndarray, img2: np.ndarray) -> float:
     return plane(x1, x2)
 
 
+# ------------------------------------------------------------------------------------------------ BICUBIC originals
+def _pil_bicubic_coeffs(in_size: int, out_size: int):
+    """Pillow src/libImaging/Resample.c: precompute_coeffs (bicubic, a = -0.5, full-image box) + normalize_coeffs_8bpc,
+    written as the plain loops of the C source.  Third-party arithmetic on the path (PKG/cli/eval.py:66 calls
+    `Image.resize((S, S), Image.BICUBIC)`); pinned against Pillow itself, which IS installed here and on the GPU box
+    (tests/test_oracle_golden.py::test_bicubic_restatement_matches_pillow)."""
+    prec = 32 - 8 - 2
+
+    def filt(x: float) -> float:
+        a = -0.5
+        x = -x if x < 0.0 else x
+        if x < 1.0:
+            return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+        if x < 2.0:
+            return (((x - 5) * x + 8) * x - 4) * a
+        return 0.0
+
+    scale = filterscale = in_size / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    ss = 1.0 / filterscale
+    bounds, kk = [], []
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        xmin = 0 if xmin < 0 else xmin
+        xmax = int(center + support + 0.5)
+        xmax = in_size if xmax > in_size else xmax
+        xmax -= xmin
+        k = [filt((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for w in k:
+            ww += w
+        if ww != 0.0:
+            k = [w / ww for w in k]
+        ki = [int(-0.5 + w * (1 << prec)) if w < 0 else int(0.5 + w * (1 << prec)) for w in k]
+        bounds.append((xmin, xmax))
+        kk.append(ki + [0] * (ksize - xmax))
+    return bounds, kk
+
+
+def bicubic_resize_u8(img_hwc: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """`Image.fromarray(img).resize((out_w, out_h), Image.BICUBIC)` for uint8 HWC images (eval.py:66): horizontal pass, then
+    vertical pass (a pass is skipped when its size does not change), out = clip8((2^21 + sum k*in) >> 22)."""
+    def one_pass(a: np.ndarray, out_size: int, axis: int) -> np.ndarray:
+        if a.shape[axis] == out_size:
+            return a
+        bounds, kk = _pil_bicubic_coeffs(a.shape[axis], out_size)
+        src = np.moveaxis(a, axis, 0).astype(np.int64)
+        out = np.empty((out_size,) + src.shape[1:], np.uint8)
+        for o, ((xmin, n), k) in enumerate(zip(bounds, kk)):
+            acc = (1 << 21) + np.tensordot(np.asarray(k[:n], np.int64), src[xmin:xmin + n], axes=(0, 0))
+            out[o] = np.clip(acc >> 22, 0, 255).astype(np.uint8)
+        return np.moveaxis(out, 0, axis)
+
+    return one_pass(one_pass(np.asarray(img_hwc, np.uint8), out_w, 1), out_h, 0)
+
+
+def original_to_float_chw(img_hwc_u8: np.ndarray) -> np.ndarray:
+    """PKG/cli/eval.py:67 — (np.array(img).astype(np.float32) / 127.5 - 1.0).transpose(2, 0, 1)."""
+    return (np.asarray(img_hwc_u8).astype(np.float32) / 127.5 - 1.0).transpose(2, 0, 1)
+
+
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     """||a-b||_2 / ||b||_2 in fp64 (the north-star's per-step epsilon metric)."""
     a, b = a.double().flatten(), b.double().flatten()

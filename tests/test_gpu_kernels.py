@@ -409,6 +409,23 @@ def test_head_conv_fused(ops, b, h, w, c, dtype):
     assert torch.equal(y, ops.head_conv(x16, sc, sh, wt, bias))          # deterministic
 
 
+@pytest.mark.parametrize("h,w,oh,ow", [(37, 53, 32, 32), (300, 200, 256, 256), (64, 64, 256, 256), (512, 768, 256, 256),
+                                        (256, 256, 256, 256), (17, 9, 64, 48), (1000, 30, 31, 300), (256, 300, 256, 128)])
+def test_bicubic_resize_bit_exact_vs_pillow(oracle, h, w, oh, ow):
+    """The eval originals' BICUBIC resize on the device == Pillow's Image.resize byte for byte (down- and up-scaling, one
+    pass skipped, extreme aspect ratios), and the float CHW conversion == numpy's of eval.py:67 bit for bit."""
+    from PIL import Image
+    from clip_neural_image_conpression_b200.eval.resample import resize_bicubic_u8, u8_hwc_to_float_chw
+    rng = np.random.default_rng(h * 1000 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = np.array(Image.fromarray(img).resize((ow, oh), Image.BICUBIC))
+    got = resize_bicubic_u8(cu(img), oh, ow)
+    assert got.shape == (oh, ow, 3) and np.array_equal(got.cpu().numpy(), ref)
+    assert np.array_equal(ref, oracle.bicubic_resize_u8(img, oh, ow))
+    f = u8_hwc_to_float_chw(got).cpu().numpy()
+    assert np.array_equal(f, oracle.original_to_float_chw(ref))
+
+
 # ------------------------------------------------------------------------------------------------ blocks, post-process
 def test_film_and_resblock_match_reference(ops, golden):
     from clip_neural_image_conpression_b200.models import FiLM, ResBlock

@@ -9,7 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def make_store(tmp_path, oracle, n=5, size=32, base=32, ch_mult=(1, 2)):
+def make_store(tmp_path, oracle, n=5, size=32, base=32, ch_mult=(1, 2), orig_hw=None):
     from clip_neural_image_conpression_b200.codecs import PerChannelAffineQuantizer
     from clip_neural_image_conpression_b200.io.bitstream import write_bitstream
     from PIL import Image
@@ -20,7 +20,8 @@ def make_store(tmp_path, oracle, n=5, size=32, base=32, ch_mult=(1, 2)):
     manifest = []
     rng = np.random.default_rng(0)
     for i in range(n):
-        img = rng.integers(0, 256, (size, size, 3), dtype=np.uint8)
+        hw = orig_hw[i % len(orig_hw)] if orig_hw else (size, size)   # originals of other sizes exercise the BICUBIC resize
+        img = rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
         Image.fromarray(img).save(tmp_path / f"{i}.png")
         write_bitstream(qz.encode(Z[i]).tobytes(), 512, tmp_path / f"{i}.clp")
         manifest.append({"image": str(tmp_path / f"{i}.png"), "bitstream": str(tmp_path / f"{i}.clp")})
@@ -92,6 +93,20 @@ def oracle_eval_rows(oracle, Z, qz, sd, manifest, seed, batch, size, steps, rank
         img0 = load_original(manifest[i]["image"], size)
         rows.append((oracle.psnr(img0, rec), oracle.ssim(img0, rec)))
     return rows
+
+
+def test_cli_eval_resizes_originals_like_pillow(tmp_path, oracle, capsys):
+    """Originals larger / smaller / non-square than --size: the CLI's device-side BICUBIC resize gives the metric values of
+    the reference loop body, whose originals go through Pillow's resize on the host (eval.py:66-67)."""
+    from clip_neural_image_conpression_b200.cli import eval as cli_eval
+    Z, qz, sd, manifest = make_store(tmp_path, oracle, n=4, orig_hw=[(48, 40), (20, 33), (32, 32), (100, 64)])
+    cli_eval.main(["--store_dir", str(tmp_path), "--weights", str(tmp_path / "w.pt"), "--size", "32", "--steps", "5", "--base", "32",
+                   "--ch_mult", "1", "2", "--seed", "0", "--batch", "4", "--out_json", str(tmp_path / "m.json")])
+    capsys.readouterr()
+    rows = json.loads((tmp_path / "m.json").read_text())
+    ref_rows = oracle_eval_rows(oracle, Z, qz, sd, manifest, seed=0, batch=4, size=32, steps=5)
+    for r, (pr, sr) in zip(rows, ref_rows):
+        assert abs(r["psnr"] - pr) < 0.02 and abs(r["ssim"] - sr) < 2e-3, (r, pr, sr)
 
 
 def test_cli_eval_two_ranks_nccl(tmp_path, oracle):

@@ -140,3 +140,22 @@ def test_ddpm_helpers_match_reference(oracle, golden):
         mean, var, x0c = oracle.p_mean_variance(tabs, eps, xt, t)
         assert np.array_equal(mean.numpy(), g[f"{sch}.mean"]) and np.array_equal(var.numpy(), g[f"{sch}.var"])
         assert np.array_equal(x0c.numpy(), g[f"{sch}.x0_clamped"])
+
+
+@pytest.mark.parametrize("h,w,oh,ow", [(37, 53, 32, 32), (300, 200, 256, 256), (64, 64, 256, 256), (256, 256, 256, 256),
+                                        (17, 9, 64, 48), (500, 30, 31, 300), (256, 300, 256, 128)])
+def test_bicubic_restatement_matches_pillow(oracle, h, w, oh, ow):
+    """The oracle's restatement of Pillow's 8-bit BICUBIC resampler (third-party arithmetic behind PKG/cli/eval.py:66) and
+    the product's host-side coefficient tables, against Pillow itself: every byte / every coefficient identical."""
+    from PIL import Image
+    from clip_neural_image_conpression_b200.eval.resample import bicubic_coeffs
+    rng = np.random.default_rng(h * 1000 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = np.array(Image.fromarray(img).resize((ow, oh), Image.BICUBIC))
+    assert np.array_equal(oracle.bicubic_resize_u8(img, oh, ow), ref)
+    for in_size, out_size in ((w, ow), (h, oh)):
+        b, k = bicubic_coeffs(in_size, out_size)
+        ob, ok = oracle._pil_bicubic_coeffs(in_size, out_size)
+        assert np.array_equal(b, np.asarray(ob, np.int32)) and np.array_equal(k, np.asarray(ok, np.int32))
+    f = oracle.original_to_float_chw(ref)
+    assert f.dtype == np.float32 and f.shape == (3, oh, ow) and np.array_equal(f, (ref.astype(np.float32) / 127.5 - 1.0).transpose(2, 0, 1))
