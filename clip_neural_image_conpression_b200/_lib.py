@@ -42,6 +42,7 @@ class ConvEpilogue(C.Structure):
         ("in_scale", C.c_void_p),
         ("in_shift", C.c_void_p),
         ("in_silu", C.c_int),
+        ("resid_op", C.c_void_p),
     ]
 
 

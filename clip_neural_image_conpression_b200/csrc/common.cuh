@@ -387,6 +387,12 @@ __device__ __forceinline__ float from_op(uint16_t raw, bool f16) {
   return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&raw));
 }
 
+// two packed 16-bit operand values -> fp32 (low half first)
+__device__ __forceinline__ float2 unpack_op2(uint32_t u, bool f16) {
+  if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
 // GroupNorm apply [+ SiLU] of 8 packed 16-bit values: r = v * sc + sh (one FMA, (scale, shift) = (rstd*gamma,
 // beta - mean*rstd*gamma)), SiLU as ONE MUFU op per element: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32).
 __device__ __forceinline__ float tanh_approx(float x) {

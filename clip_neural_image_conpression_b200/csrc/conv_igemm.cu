@@ -144,7 +144,6 @@ static inline int epi_vector_bytes(int block_n, int xf_cin) {
   return 2 * 4 * block_n + (red_bytes(block_n) + 63) / 64 * 64 + (2 * 4 * xf_cin + 63) / 64 * 64;
 }
 
-constexpr int kStagingBytes = kTileM * 128;
 
 // Fused GroupNorm statistics helpers.  A thread holds 32 consecutive output channels of one pixel; P = number of
 // consumer-GroupNorm groups those 32 channels span (1, 2, 4 or 8).  row_sums: per-thread (sum, sumsq) per group —
@@ -270,7 +269,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint8_t* smem_b = smem + (size_t)p.stages * kABytes;
   uint8_t* smem_s = smem_b + (size_t)(kRows2 ? p.stages_b : p.stages) * b_bytes;  // staging buffers (1024-aligned sizes)
   EpiVectors vec_s;
-  vec_s.mul = reinterpret_cast<float*>(smem_s + (size_t)p.n_staging * kStagingBytes);
+  vec_s.mul = reinterpret_cast<float*>(smem_s + (size_t)p.n_staging * 4 * p.slot_bytes);
   vec_s.add = vec_s.mul + p.block_n;
   vec_s.nchg = red_chunks_per_group(p.block_n) > 0 ? red_chunks_per_group(p.block_n) : 1;
   vec_s.red = reinterpret_cast<float4*>(vec_s.add + p.block_n);
@@ -435,7 +434,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
         const TileCoord tc = decode_tile(p, tile, (int)rank);
         const int w_row = tc.phase * p.cout_pad + tc.n0 + (int)rank * b_rows;
-        if (p.ep.resid && p.chunked && tc.ok && elect_one()) {
+        if ((p.ep.resid || p.ep.resid_op) && p.chunked && tc.ok && elect_one()) {
           // the epilogue will add this residual tile: pull it into L2 while the MMAs run (the residual map's box is one
           // epilogue warp's 32-row sub-box)
           for (int q = 0; q < p.res_ahead; ++q) {
@@ -670,7 +669,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int gtid = etid & 127;             // within the group
     const bool f16 = p.op_f16 != 0;
     const int S = p.n_staging / kEpiGroups;  // staging slots of this warp (a 16 KB staging buffer = 4 warp slots)
-    uint8_t* wslots = smem_s + (size_t)ew * S * kWarpSlotBytes;
+    const int slot_bytes = p.slot_bytes;     // per-warp slot: 32 rows x 128 B (fp32 sub-box) or x 64 B (all-16-bit epilogue)
+    uint8_t* wslots = smem_s + (size_t)ew * S * slot_bytes;
     uint64_t* res_full = bars->res_full[ew];
     const int bar_id = 1 + eg;
     int it = 0;
@@ -679,7 +679,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     int cached_key = -1;
     // Residual sub-boxes are TMA-loaded straight into the staging slot that is later stored from (read-modify-write in
     // place).  Lane 0 keeps `A` of them in flight; (ld_tile, ld_c, ld_slot) is its load cursor.
-    const bool res_tma = p.chunked && (ep.resid != nullptr);
+    const bool res16 = p.chunked && (ep.resid_op != nullptr);  // 16-bit residual (operand format): 64-byte rows, 64B swizzle
+    const bool res_tma = p.chunked && (ep.resid != nullptr || res16);
     const bool st_f32 = p.chunked && (ep.out_f32 != nullptr);  // fp32 output goes through the staging slots + TMA store
     // a 16-bit-only output (ResBlock conv1) is staged too (64-byte rows, 64B swizzle): 4x fewer L1/smem wavefronts than
     // 32 lanes x 16 B scattered over 32 lines per store instruction
@@ -701,8 +702,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       if (ld_tile >= p.num_tiles) return;
       if (ld_tile != lc_tile || ld_sub != lc_sub) { lc = decode_tile(p, ld_tile, (int)rank, ld_sub); lc_tile = ld_tile; lc_sub = ld_sub; }
-      mbar_arrive_expect_tx(&res_full[ld_slot], (uint32_t)kWarpSlotBytes);
-      tma_load_5d(wslots + (size_t)ld_slot * kWarpSlotBytes, &maps_res.m[lc.phase], &res_full[ld_slot], lc.n0 + ld_c,
+      mbar_arrive_expect_tx(&res_full[ld_slot], (uint32_t)(res16 ? 32 * 64 : kWarpSlotBytes));
+      tma_load_5d(wslots + (size_t)ld_slot * slot_bytes, &maps_res.m[lc.phase], &res_full[ld_slot], lc.n0 + ld_c,
                   lc.w0 + sub_w, 0, lc.h0 + sub_h, lc.b);
       if (++ld_slot == (uint32_t)S) ld_slot = 0;
       ld_c += cstep;
@@ -749,7 +750,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         CLPK_TRACE(tr, 101);
         int ci = 0;
         for (int c = 32 * eg; c < p.block_n; c += cstep, ++ci) {
-          uint8_t* sbuf = wslots + (size_t)slot * kWarpSlotBytes;
+          uint8_t* sbuf = wslots + (size_t)slot * slot_bytes;
           uint32_t r[32];
           float gsums[16];
           float4* redw = vec->red + vec->idx(red_par, eg, ci, quarter);
@@ -793,6 +794,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               CLPK_TRACE(tr, 103);
               mbar_wait(&res_full[slot], sphase);  // residual sub-box has landed (implies the slot was free)
               CLPK_TRACE(tr, 104);
+              if (res16) {
+                // 16-bit residual: row `lane` is 64 B, piece j8 (channels 8 j8 .. 8 j8 + 7) at (j8 ^ ((lane >> 1) & 3)) —
+                // the layout the 16-bit result is stored back in, so every lane only ever touches its own row
+                const uint8_t* rrow = sbuf + lane * 64;
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                  const uint4 q = *reinterpret_cast<const uint4*>(rrow + ((j8 ^ ((lane >> 1) & 3)) << 4));
+                  const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 f = unpack_op2(qq[k], f16);
+                    unpack2(add2(pack2(v[8 * j8 + 2 * k], v[8 * j8 + 2 * k + 1]), pack2(f.x, f.y)), v[8 * j8 + 2 * k],
+                            v[8 * j8 + 2 * k + 1]);
+                  }
+                }
+              } else
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 q = *reinterpret_cast<const float4*>(srow + ((j4 ^ (lane & 7)) << 4));
@@ -830,7 +847,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               if (st_16) {
                 // 16-byte piece j (channels 8j .. 8j+7) of row `lane` lives at piece (j ^ ((lane >> 1) & 3)): 64B swizzle
                 // (with a residual the slot still holds the fp32 sub-box other lanes may be reading: reconverge first)
-                if (res_tma) __syncwarp();
+                if (res_tma && !res16) __syncwarp();
                 uint8_t* srow16 = sbuf + lane * 64;
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) *reinterpret_cast<uint4*>(srow16 + ((j8 ^ ((lane >> 1) & 3)) << 4)) = pk[j8];
@@ -945,6 +962,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     y = fmaf(y, __ldg(ep.film_scale1p + (long long)tc.b * ep.film_stride + n + j),
                              __ldg(ep.film_shift + (long long)tc.b * ep.film_stride + n + j));
                   if (ep.resid) y += ep.resid[opix * ldc + n + j];
+                  if (ep.resid_op) y += from_op(reinterpret_cast<const uint16_t*>(ep.resid_op)[opix * ldc + n + j], f16);
                   if (ep.out_f32) ep.out_f32[opix * ldc + n + j] = y;
                   if (ep.out_op) reinterpret_cast<uint16_t*>(ep.out_op)[opix * ldc + n + j] = to_op(y, f16);
                   if (ep.out_nchw) ep.out_nchw[(((long long)tc.b * ldc + n + j) * p.out_h + oh) * p.out_w + ow] = y;
@@ -1010,6 +1028,7 @@ __global__ void conv_direct_kernel(const uint16_t* __restrict__ x, const uint16_
     const int oh = h * p.out_scale + (phase >> 1), ow = w * p.out_scale + (phase & 1);
     const long long opix = ((long long)b * p.out_h + oh) * p.out_w + ow;
     if (ep.resid) y += ep.resid[opix * ldc + n];
+    if (ep.resid_op) y += from_op(reinterpret_cast<const uint16_t*>(ep.resid_op)[opix * ldc + n], f16);
     if (ep.out_f32) ep.out_f32[opix * ldc + n] = y;
     if (ep.out_op) reinterpret_cast<uint16_t*>(ep.out_op)[opix * ldc + n] = to_op(y, f16);
     if (ep.out_nchw) ep.out_nchw[(((long long)b * ldc + n) * p.out_h + oh) * p.out_w + ow] = y;
@@ -1162,7 +1181,7 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   p.block_k = (cin % 128 == 0 && p.ncta == 1) ? 128 : (cin % 64 == 0) ? 64 : 32;
   // a short K loop with a residual epilogue (the transposed conv: 4 taps) is epilogue-bound: spend the shared memory on
   // residual look-ahead slots rather than on 128-wide k-blocks
-  if (p.block_k == 128 && ep->resid) p.block_k = 64;
+  if (p.block_k == 128 && (ep->resid || ep->resid_op)) p.block_k = 64;
   { const char* e = getenv("CLPK_IGEMM_BK");
     if (e && atoi(e) == 64 && p.block_k == 128) p.block_k = 64;
     if (e && atoi(e) == 128 && cin % 128 == 0) p.block_k = 128; }
@@ -1191,7 +1210,12 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   if (p.ep.cout_valid <= 0) p.ep.cout_valid = cout;
   CLPK_REQUIRE(p.ep.cout_valid == cout, "cout_valid must equal cout");
   if (cout % 16 != 0)
-    CLPK_REQUIRE(!p.ep.out_f32 && !p.ep.out_op && !p.ep.resid, "Cout %% 16 != 0 supports the NCHW output only");
+    CLPK_REQUIRE(!p.ep.out_f32 && !p.ep.out_op && !p.ep.resid && !p.ep.resid_op, "Cout %% 16 != 0 supports the NCHW output only");
+  if (p.ep.resid_op) {
+    CLPK_REQUIRE(!p.ep.resid, "resid and resid_op are exclusive");
+    CLPK_REQUIRE(p.ep.out_op && !p.ep.out_f32 && !p.ep.out_nchw, "a 16-bit residual needs a 16-bit-only NHWC output");
+    CLPK_REQUIRE((reinterpret_cast<uintptr_t>(p.ep.resid_op) & 15) == 0, "residual tensor must be 16-byte aligned");
+  }
 
   cuuint64_t dims[5], strides[4];
   const long long C = cin, W = w_in, H = h_in;
@@ -1288,26 +1312,33 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   const int fixed = p.smem_slack + epi_vector_bytes(p.block_n, p.xform ? cin : 0) + (int)sizeof(PipeBarriers) + 16;
   p.n_staging = 0;
   const bool op16_ok = p.ep.out_op != nullptr && (reinterpret_cast<uintptr_t>(p.ep.out_op) & 15) == 0;
-  if (p.chunked && (p.ep.out_f32 || p.ep.resid || op16_ok)) {
-    CLPK_REQUIRE(p.ep.out_f32 != nullptr || !p.ep.resid || op16_ok, "a residual input needs an NHWC output");
+  const bool any_resid = p.ep.resid || p.ep.resid_op;
+  // an epilogue that moves only 16-bit tensors through the slots (16-bit-only output, no residual or a 16-bit one) gets
+  // half-size slots: twice the residual look-ahead, or more pipeline stages, out of the same shared memory
+  p.slot_bytes = (!p.ep.out_f32 && !p.ep.resid && op16_ok) ? kWarpSlotBytes / 2 : kWarpSlotBytes;
+  { const char* e = getenv("CLPK_IGEMM_SLOT4K"); if (e && atoi(e) != 0) p.slot_bytes = kWarpSlotBytes; }
+  const int staging_bytes = 4 * p.slot_bytes;   // one staging buffer = the 4 warp slots of an epilogue group
+  if (p.chunked && (p.ep.out_f32 || any_resid || op16_ok)) {
+    CLPK_REQUIRE(p.ep.out_f32 != nullptr || !any_resid || op16_ok, "a residual input needs an NHWC output");
     // as many staging slots per epilogue group (<= 3) as the smem ring can spare without losing depth; a residual
     // epilogue keeps (slots - 1) chunk loads in flight per group, so its throughput hangs on this
     // (measured: the 256-wide CTA-pair tiles of the 64x64 / 32x32 layers prefer a 5-deep ring over a second staging slot)
     int want_stages = (p.block_k == 128 || p.slab) ? 3 : (p.ncta == 2 && p.block_n >= 256) ? 5 : 4;
     // the in-smem transform adds a third phase (fill -> normalise -> MMA) to every stage's life: one more stage in flight
     if (p.xform) { const char* e = getenv("CLPK_XF_STAGES"); want_stages = e ? atoi(e) : 3; }
-    int per_group = p.ep.resid ? 3 : 2;
-    while (per_group > 1 && (kSmemBudget - fixed - kEpiGroups * per_group * kStagingBytes) / stage_bytes < want_stages) --per_group;
+    int per_group = p.ep.resid ? 3 : p.ep.resid_op ? 4 : 2;
+    { const char* e = getenv("CLPK_IGEMM_SLOTS16"); if (e && p.ep.resid_op && atoi(e) >= 1 && atoi(e) <= 6) per_group = atoi(e); }
+    while (per_group > 1 && (kSmemBudget - fixed - kEpiGroups * per_group * staging_bytes) / stage_bytes < want_stages) --per_group;
     { const char* e = getenv("CLPK_IGEMM_SLOTS"); if (e && atoi(e) >= 1 && atoi(e) <= 4) per_group = atoi(e); }
     if (kind == CLPK_CONVT_4X4_S2) {  // (a transposed conv is bound by its residual look-ahead: slots beat ring depth)
       const char* e = getenv("CLPK_CONVT_SLOTS");
       const int want = e ? atoi(e) : per_group;
-      if (want >= 1 && want <= 6 && (kSmemBudget - fixed - kEpiGroups * want * kStagingBytes) / stage_bytes >= 3) per_group = want;
+      if (want >= 1 && want <= 6 && (kSmemBudget - fixed - kEpiGroups * want * staging_bytes) / stage_bytes >= 3) per_group = want;
     }
     p.n_staging = kEpiGroups * per_group;
-    if ((kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes < 2) {
+    if ((kSmemBudget - fixed - p.n_staging * staging_bytes) / stage_bytes < 2) {
       p.n_staging = 0;
-      if (p.ep.out_f32 || p.ep.resid) p.chunked = 0;  // (a 16-bit-only output falls back to direct stores from registers)
+      if (p.ep.out_f32 || any_resid) p.chunked = 0;  // (a 16-bit-only output falls back to direct stores from registers)
     }
   }
   p.gn_groups = p.gn_slots = 0;
@@ -1326,9 +1357,9 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
   // 3x3 convs (their per-warp look-ahead loads cover the latency), a small win for the short-K transposed conv
   p.res_ahead = (kind == CLPK_CONVT_4X4_S2) ? 2 : 0;
   { const char* e = getenv("CLPK_IGEMM_PREFETCH"); if (e) p.res_ahead = std::max(0, std::min(4, atoi(e))); }
-  p.stages = std::min(kMaxStages, (kSmemBudget - fixed - p.n_staging * kStagingBytes) / stage_bytes);
+  p.stages = std::min(kMaxStages, (kSmemBudget - fixed - p.n_staging * staging_bytes) / stage_bytes);
   CLPK_REQUIRE(p.stages >= 2, "tile does not fit shared memory");
-  out->smem_bytes = p.stages * stage_bytes + p.n_staging * kStagingBytes + fixed;
+  out->smem_bytes = p.stages * stage_bytes + p.n_staging * staging_bytes + fixed;
   p.stages_b = 0;
   if (p.rows2) {
     // two rings: slabs (17 KB each; 2 in use + prefetch) and weight blocks (3 taps of a kernel row; 1 in use + prefetch).
@@ -1337,14 +1368,14 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     int nb = 2;
     { const char* e = getenv("CLPK_ROWS2_NB"); if (e && atoi(e) >= 2 && atoi(e) <= 4) nb = atoi(e); }
     int per_group = p.n_staging / kEpiGroups;
-    auto na_for = [&](int pg) { return (kSmemBudget - fixed - kEpiGroups * pg * kStagingBytes - nb * bb) / kSlabABytes; };
+    auto na_for = [&](int pg) { return (kSmemBudget - fixed - kEpiGroups * pg * staging_bytes - nb * bb) / kSlabABytes; };
     while (per_group > 1 && na_for(per_group) < 4) --per_group;
     const int na = std::min(kMaxStages, na_for(per_group));
     if (p.n_staging > 0 && na >= 3) {
       p.n_staging = kEpiGroups * per_group;
       p.stages = na;
       p.stages_b = nb;
-      out->smem_bytes = na * kSlabABytes + nb * bb + p.n_staging * kStagingBytes + fixed;
+      out->smem_bytes = na * kSlabABytes + nb * bb + p.n_staging * staging_bytes + fixed;
     } else {
       p.rows2 = 0;   // does not fit: back to one row per item
       CLPK_TRY_RC(compute_tiles());
@@ -1381,6 +1412,19 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     }
   }
   memset(&out->maps_res, 0, sizeof(out->maps_res));
+  if (p.chunked && p.ep.resid_op) {  // 16-bit residual: same geometry as the 16-bit output map
+    const long long CO = cout, OW = p.out_w, OH = p.out_h, sc = p.out_scale;
+    cuuint64_t odims[5] = {(cuuint64_t)CO, (cuuint64_t)p.grid_w, 1, (cuuint64_t)p.grid_h, (cuuint64_t)batch};
+    cuuint64_t ostr[4] = {(cuuint64_t)(sc * CO * 2), (cuuint64_t)(sc * OW * CO * 2), (cuuint64_t)(sc * OW * CO * 2),
+                          (cuuint64_t)(OH * OW * CO * 2)};
+    cuuint32_t obox[5] = {32, (cuuint32_t)wsub, 1, (cuuint32_t)(32 / wsub), 1};
+    for (int phase = 0; phase < p.phases; ++phase) {
+      const long long off = ((long long)(phase >> 1) * OW + (phase & 1)) * CO;
+      rc = encode_tensor_map(&out->maps_res.m[phase], const_cast<uint16_t*>(reinterpret_cast<const uint16_t*>(p.ep.resid_op)) + off, 5,
+                             odims, ostr, obox, 64, op_dt);
+      if (rc) return rc;
+    }
+  }
   if (p.chunked && (p.ep.out_f32 || p.ep.resid)) {
     const long long CO = cout, OW = p.out_w, OH = p.out_h, sc = p.out_scale;
     cuuint64_t odims[5] = {(cuuint64_t)CO, (cuuint64_t)p.grid_w, 1, (cuuint64_t)p.grid_h, (cuuint64_t)batch};

@@ -66,6 +66,13 @@ static int fuse_gn_mask() {
   const char* e = getenv("CLPK_FUSE_GN");
   return e ? atoi(e) : 0;
 }
+// env CLPK_RES16 (default 1): with fp16 operands the residual stream x <- x + conv2(...) (blocks.py:44, unet.py:104) is kept
+// in fp16 ONLY — conv2 / the transposed convs read the residual as a 16-bit tile and write the 16-bit sum (rounded once per
+// block from the fp32 accumulator + residual), GroupNorm reads 2 B per element, and no fp32 copy of the stream exists.
+static bool res16_wanted() {
+  const char* e = getenv("CLPK_RES16");
+  return !(e && atoi(e) == 0);
+}
 // env CLPK_HEAD16 (default 1): the last transposed conv, whose result only out_norm reads, stores just the 16-bit copy
 // (statistics still come from its fp32 accumulators) and out_norm reads 2 B instead of 4 B per element.
 static bool head16_on() {
@@ -116,6 +123,7 @@ struct clpk_plan {
   uint16_t* head_w = nullptr;  // [32][base] packed head weight (head_conv.cu)
   int head_stages = 0;       // experiments: cap of the head kernel's A ring (env CLPK_HEAD_STAGES at plan creation)
   bool x16_gn = false;       // env CLPK_X16=1: GroupNorms on the residual stream read X16 instead of fp32 X
+  bool res16 = false;        // the residual stream lives in X16 ONLY (fp16): no fp32 X traffic at all (see res16_wanted)
   float* Yf = nullptr;       // fp32 conv1 output, only for ResBlocks whose GroupNorm statistics cannot be fused
   void* gn_ws = nullptr;
   float *temb = nullptr, *h1 = nullptr, *ht = nullptr, *hcond = nullptr, *film = nullptr, *zemb = nullptr;
@@ -464,9 +472,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   for (int l = 0; l <= L; ++l) {
     const long long n = (long long)batch * P->lv_h[l] * P->lv_w[l] * P->lv_c[l];
     max_act = std::max(max_act, n);
-    float* x = nullptr;
-    CLPK_TRY(P->alloc(&x, n));
-    P->X.push_back(x);
+    P->X.push_back(nullptr);  // fp32 stream: allocated below unless the plan keeps the stream in 16 bits only
     uint16_t* x16 = nullptr;
     CLPK_TRY(P->alloc(&x16, n));
     P->X16.push_back(x16);
@@ -528,9 +534,24 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   }
   CLPK_TRY(setup_gn(P, &P->out_gn, CLPK_CONVT_4X4_S2, P->lv_h[1], P->lv_w[1]));
   gn_after_up[0] = &P->out_gn;
-  P->fuse_head = (fuse_gn_mask() & 2) && P->out_gn.fused && !P->x16_gn &&
+  {
+    // 16-bit-only residual stream (res16_wanted): every GroupNorm on the stream must take its statistics from the producing
+    // conv's fp32 accumulators (a statistics pass over the rounded copy would be slower and less exact).  fp16 operands
+    // only: bf16's 8-bit mantissa is too coarse for a running sum.
+    bool all_fused = P->out_gn.fused;
+    for (const ResBlockPlan& rb : P->rbs) all_fused = all_fused && rb.gn1.fused;
+    P->res16 = res16_wanted() && cfg->op_dtype == CLPK_OP_F16 && all_fused && !P->x16_gn;
+    if (P->res16) {
+      P->x16_gn = true;   // every producer writes X16, every GroupNorm on the stream reads it
+      for (ResBlockPlan& rb : P->rbs) rb.emit16 = true;
+    } else {
+      for (int l = 0; l <= L; ++l)
+        CLPK_TRY(P->alloc(&P->X[l], (long long)batch * P->lv_h[l] * P->lv_w[l] * P->lv_c[l]));
+    }
+  }
+  P->fuse_head = (fuse_gn_mask() & 2) && P->out_gn.fused && (!P->x16_gn || P->res16) &&
                  igemm_xform_ok(CLPK_CONV_3X3_S1, height, width, cfg->base, cfg->img_ch);
-  P->head16 = P->fuse_head || (head16_on() && P->out_gn.fused && !P->x16_gn && cfg->base % 32 == 0);
+  P->head16 = P->fuse_head || P->res16 || (head16_on() && P->out_gn.fused && !P->x16_gn && cfg->base % 32 == 0);
   {
     const char* e = getenv("CLPK_HEAD_FUSED");
     P->head_fused = !(e && atoi(e) == 0) && !P->fuse_head && P->head16 &&
@@ -568,9 +589,14 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     CLPK_TRY(bind_conv(P, &rb.conv1, P->T, e1));
     clpk_conv_epilogue e2{};
     e2.bias = rb.conv2.bias;
-    e2.resid = P->X[rb.level];
-    e2.out_f32 = P->X[rb.level];
-    e2.out_op = rb.emit16 ? P->X16[rb.level] : nullptr;
+    if (P->res16) {   // blocks.py:44 on the 16-bit stream, in place
+      e2.resid_op = P->X16[rb.level];
+      e2.out_op = P->X16[rb.level];
+    } else {
+      e2.resid = P->X[rb.level];
+      e2.out_f32 = P->X[rb.level];
+      e2.out_op = rb.emit16 ? P->X16[rb.level] : nullptr;
+    }
     e2.cout_valid = rb.c;
     wire_gn(&e2, gn_after_conv2[i]);
     const void* a2 = P->T;
@@ -596,7 +622,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
                        P->lv_h[l], P->lv_w[l], &dn));
     clpk_conv_epilogue ed{};
     ed.bias = dn.bias;
-    ed.out_f32 = P->X[l + 1];
+    ed.out_f32 = P->res16 ? nullptr : P->X[l + 1];
     ed.out_op = P->x16_gn ? P->X16[l + 1] : nullptr;
     ed.cout_valid = P->lv_c[l + 1];
     wire_gn(&ed, gn_after_down[l]);
@@ -612,7 +638,11 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     eu.resid = P->X[l];  // skip connection, added in place
     eu.out_f32 = P->X[l];
     eu.out_op = P->x16_gn ? P->X16[l] : nullptr;
-    if (l == 0 && P->head16) {
+    if (P->res16) {
+      eu.resid = nullptr;
+      eu.resid_op = P->X16[l];
+      eu.out_f32 = nullptr;
+    } else if (l == 0 && P->head16) {
       // the last transposed conv's result is read by out_norm only: keep just the 16-bit copy (its GroupNorm statistics
       // still come from the fp32 accumulators), which the `out` conv normalises in shared memory
       eu.out_f32 = nullptr;
@@ -643,7 +673,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     CLPK_TRY(P->alloc(&P->stem_cols, (long long)batch * height * width * 32));
     clpk_conv_epilogue es{};
     es.bias = st.bias;
-    es.out_f32 = P->X[0];
+    es.out_f32 = P->res16 ? nullptr : P->X[0];
     es.out_op = P->x16_gn ? P->X16[0] : nullptr;
     es.cout_valid = cfg->base;
     wire_gn(&es, &P->rbs[0].gn1);

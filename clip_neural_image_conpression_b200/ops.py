@@ -159,7 +159,11 @@ def _conv(fn_name: str, x_nhwc_op, w_packed, kind, cout, bias, film_scale1p, fil
         fs, fb = _f32c(film_scale1p), _f32c(film_shift)
         keep += [fs, fb]
         ep.film_scale1p, ep.film_shift, ep.film_stride = ptr(fs), ptr(fb), fs.stride(0)
-    ep.resid = ptr(resid)
+    if resid is not None and resid.dtype in (torch.float16, torch.bfloat16):
+        assert resid.dtype == x_nhwc_op.dtype and resid.is_contiguous(), "a 16-bit residual must be in the operand dtype"
+        ep.resid_op = ptr(resid)      # residual stream kept in 16 bits (clpk_conv_epilogue.resid_op)
+    else:
+        ep.resid = ptr(resid)
     ep.out_f32 = ptr(out_f32)
     ep.out_op = ptr(out_op)
     ep.out_nchw = ptr(out_nchw)
@@ -188,14 +192,16 @@ def _conv_out_hw(kind: int, h: int, w: int):
 @on_tensor_device
 def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, bias: torch.Tensor, *,
                film_scale1p=None, film_shift=None, resid=None, want_f32=True, want_op=False, want_nchw=False,
-               gn_groups: int = 0, impl: str = "igemm", in_affine=None, return_partial: bool = False):
+               gn_groups: int = 0, impl: str = "igemm", in_affine=None, return_partial: bool = False,
+               inplace: bool = False):
     """Implicit-GEMM conv on the tensor cores (x and w_packed in the same 16-bit dtype).  Returns a dict of the
     requested outputs: "f32" NHWC fp32, "op" NHWC in the operand dtype, "nchw" fp32 NCHW.  gn_groups > 0 additionally
     returns "gn_stats" [B, gn_groups, 2] = (mean, rstd) of a GroupNorm(gn_groups) over the output, accumulated by the
     conv epilogue (no extra pass over the tensor).  in_affine = (scale [B, Cin], shift [B, Cin], silu) applies
     a <- act(x * scale + shift) to the A operand inside the kernel (clpk_conv_epilogue.in_scale; geometries with
     conv_in_affine_supported(...) only).  return_partial additionally returns the raw per-tile statistics ("gn_partial",
-    "gn_slots") for groupnorm_affine."""
+    "gn_slots") for groupnorm_affine.  A `resid` in the operand dtype is added as a 16-bit residual (resid_op: the
+    16-bit-only residual stream of the plan); with inplace=True the result overwrites it."""
     b, h, w, _ = x_nhwc_op.shape
     oh, ow = _conv_out_hw(kind, h, w)
     dev = x_nhwc_op.device
@@ -206,6 +212,13 @@ def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout:
         outs["op"] = torch.empty((b, oh, ow, cout), dtype=x_nhwc_op.dtype, device=dev)
     if want_nchw:
         outs["nchw"] = torch.empty((b, cout, oh, ow), dtype=torch.float32, device=dev)
+    resid16 = None
+    if resid is not None and resid.dtype in (torch.float16, torch.bfloat16):
+        # 16-bit residual: needs a 16-bit-only NHWC output; inplace=True updates the residual tensor itself
+        assert want_op and not want_f32 and not want_nchw, "a 16-bit residual needs want_op=True, want_f32=False"
+        resid16 = resid.contiguous()
+        if inplace:
+            outs["op"] = resid16
     partial, slots, cpg = None, 0, 0
     if gn_groups > 0:
         cpg = cout // gn_groups
@@ -215,7 +228,8 @@ def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout:
         # [b][slots][groups] (tile mean, tile M2) pairs followed by [slots] element counts (see include/clpk.h)
         partial = torch.zeros(2 * b * slots * gn_groups + slots, dtype=torch.float32, device=dev)
     _conv("clpk_conv_igemm" if impl == "igemm" else "clpk_conv_direct", x_nhwc_op, w_packed, kind, cout, bias,
-          film_scale1p, film_shift, _f32c(resid) if resid is not None else None, outs.get("f32"), outs.get("op"),
+          film_scale1p, film_shift, resid16 if resid16 is not None else (_f32c(resid) if resid is not None else None),
+          outs.get("f32"), outs.get("op"),
           outs.get("nchw"), partial, cpg, in_affine)
     if gn_groups > 0 and return_partial:
         outs["gn_partial"], outs["gn_slots"] = partial, slots

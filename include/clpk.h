@@ -147,6 +147,10 @@ typedef struct clpk_conv_epilogue {
   const float* in_scale;
   const float* in_shift;
   int in_silu;
+  /* Residual in the 16-bit operand format (NHWC, op_dtype) instead of fp32: y += resid_op, for a residual stream that is
+   * kept in 16 bits only (blocks.py:44, unet.py:104 with the running sum rounded to fp16 once per block).  Exclusive with
+   * `resid`; needs out_op and no out_f32 (may alias out_op: in-place update).  NULL = off. */
+  const void* resid_op;
 } clpk_conv_epilogue;
 
 /* 1 when clpk_conv_igemm accepts in_scale / in_shift for this geometry, else 0. */

@@ -29,8 +29,8 @@ def test_header_symbols_are_exported_and_typed(lib):
 
 def test_struct_layouts_match_header(lib):
     from clip_neural_image_conpression_b200._lib import ConvEpilogue, UnetConfig
-    assert C.sizeof(ConvEpilogue) == 112 and ConvEpilogue.cout_valid.offset == 64 and ConvEpilogue.gn_cpg.offset == 80
-    assert ConvEpilogue.in_scale.offset == 88 and ConvEpilogue.in_silu.offset == 104
+    assert C.sizeof(ConvEpilogue) == 120 and ConvEpilogue.cout_valid.offset == 64 and ConvEpilogue.gn_cpg.offset == 80
+    assert ConvEpilogue.in_scale.offset == 88 and ConvEpilogue.in_silu.offset == 104 and ConvEpilogue.resid_op.offset == 112
     assert C.sizeof(UnetConfig) == (3 + 8 + 4) * 4
 
 

@@ -248,6 +248,61 @@ def test_conv_igemm(ops, kind, b, h, w, cin, cout, film, resid, dtype):
         assert float((o["op"].double().permute(0, 3, 1, 2) - ref).abs().max()) < 1.2 * half_ulp * max(scale, 1.0)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("kind,b,h,w,cin,cout,film", [
+    (0, 2, 32, 32, 128, 128, False),     # conv2 on the 16-bit residual stream, generic tiles
+    (0, 3, 5, 256, 128, 128, True),      # row-slab CTA pairs, odd tile count, several residual sub-boxes in flight
+    (0, 1, 8, 8, 512, 512, False),       # two N tiles, half-filled M tile
+    (0, 4, 64, 64, 256, 256, False),     # several tiles per CTA pair: slot ring wraps many times
+    (0, 1, 9, 40, 64, 64, False),        # 32-pixel tiles, masked columns
+    (2, 2, 16, 16, 256, 128, False),     # transposed conv + 16-bit skip add, 4 phases
+    (2, 1, 8, 8, 128, 64, False),
+    (0, 1, 16, 16, 64, 48, False),       # cout % 32 != 0: direct (un-chunked) epilogue
+])
+def test_conv_16bit_residual_stream(ops, kind, b, h, w, cin, cout, film, dtype):
+    """clpk_conv_epilogue.resid_op: the residual arrives as a 16-bit NHWC tile and the 16-bit sum is stored, in place
+    (blocks.py:44 / unet.py:104 on a residual stream kept in 16 bits).  Result == round(fp32 conv + bias + residual) to
+    half an ulp of the 16-bit format, fused GroupNorm statistics == those of the UN-rounded sums, and the cross-check
+    kernel agrees."""
+    g = torch.Generator().manual_seed(kind * 77 + cin + h)
+    xb = torch.randn(b, h, w, cin, generator=g).to(dtype).cuda()
+    if kind == 2:
+        wt = (torch.randn(cin, cout, 4, 4, generator=g) / (cin * 4) ** 0.5).cuda()
+        ref = F.conv_transpose2d(xb.float().permute(0, 3, 1, 2).double(), wt.to(dtype).double(), stride=2, padding=1)
+    else:
+        wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).cuda()
+        ref = F.conv2d(xb.float().permute(0, 3, 1, 2).double(), wt.to(dtype).double(), padding=1)
+    bias = torch.randn(cout, generator=g).cuda()
+    ref = ref + bias.double()[None, :, None, None]
+    kw = {}
+    if film:
+        sc, sh = (1 + 0.3 * torch.randn(b, cout, generator=g)).cuda(), torch.randn(b, cout, generator=g).cuda()
+        kw.update(film_scale1p=sc, film_shift=sh)
+        ref = ref * sc.double()[:, :, None, None] + sh.double()[:, :, None, None]
+    r16 = (3.0 * torch.randn(b, ref.shape[2], ref.shape[3], cout, generator=g)).to(dtype).cuda()
+    ref = ref + r16.double().permute(0, 3, 1, 2)
+    wp = ops.pack_conv_weight(wt, kind, dtype)
+    gn = 8 if cout % 32 == 0 else 0
+    o = ops.conv_igemm(xb, wp, kind, cout, bias, resid=r16.clone(), want_f32=False, want_op=True, gn_groups=gn, **kw)
+    d = ops.conv_direct(xb, wp, kind, cout, bias, resid=r16.clone(), want_f32=False, want_op=True, **kw)
+    scale = max(float(ref.abs().max()), 1.0)
+    half_ulp = 2.0 ** -11 if dtype == torch.float16 else 2.0 ** -8
+    y = o["op"].double().permute(0, 3, 1, 2)
+    assert o["op"].dtype == dtype and float((y - ref).abs().max()) < 1.2 * half_ulp * scale
+    # the cross-check kernel rounds the same fp32 value (summation order aside: allow one 16-bit ulp on rare ties)
+    assert float((o["op"].double() - d["op"].double()).abs().max()) <= 2.4 * half_ulp * scale
+    assert float((o["op"] != d["op"]).double().mean()) < 1e-2
+    if gn:
+        rg = ref.reshape(b, gn, -1)
+        mean, var = rg.mean(-1), rg.var(-1, unbiased=False)
+        assert float((o["gn_stats"][..., 0].double() - mean).abs().max()) < 1e-4 * scale
+        assert float((o["gn_stats"][..., 1].double() * (var + 1e-5).sqrt() - 1).abs().max()) < 1e-4
+    # in place: the residual tensor itself receives the sum
+    acc = r16.clone()
+    o2 = ops.conv_igemm(xb, wp, kind, cout, bias, resid=acc, want_f32=False, want_op=True, inplace=True, **kw)
+    assert o2["op"].data_ptr() == acc.data_ptr() and torch.equal(acc, o["op"])
+
+
 @pytest.mark.parametrize("kind,b,h,w,cin,cout,resid", [
     (0, 2, 32, 32, 128, 128, True),      # cpg 16: two groups per 32-column chunk
     (0, 3, 16, 16, 32, 32, False),       # cpg 4

@@ -262,6 +262,7 @@ def test_fused_groupnorm_paths_match_unfused(oracle, monkeypatch):
     z = torch.nn.functional.normalize(torch.randn(2, 512, generator=g), dim=-1)
     t = torch.tensor([999, 250])
     net, sd = make_net(oracle, cfg, seed=5)
+    monkeypatch.setenv("CLPK_RES16", "0")                         # these switches act on the plan with the fp32 residual stream
     monkeypatch.setenv("CLPK_FUSE_GN", "3")
     fused = net(x.cuda(), z.cuda(), t.cuda()).cpu()
     monkeypatch.setenv("CLPK_FUSE_GN", "0")
@@ -285,3 +286,33 @@ def test_fused_groupnorm_paths_match_unfused(oracle, monkeypatch):
     assert oracle.rel_l2(fused, plain) < 2e-3
     assert oracle.rel_l2(fused, ref) < EPS_TOL and oracle.rel_l2(plain, ref) < EPS_TOL
     assert oracle.rel_l2(head, ref) < EPS_TOL and oracle.rel_l2(head16, ref) < EPS_TOL
+
+
+def test_16bit_residual_stream_matches_fp32_stream(oracle, monkeypatch):
+    """Default plan (fp16 operands): the residual stream lives in fp16 only (CLPK_RES16, plan.cu).  Against the plan with
+    the fp32 stream (CLPK_RES16=0) and against the fp32 oracle, at a size with row-slab and generic-tile levels; bf16
+    operands keep the fp32 stream (the switch must not change their result)."""
+    cfg = dict(z_dim=512, base=64, ch_mult=(1, 2, 2))
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(2, 3, 128, 128, generator=g)
+    z = torch.nn.functional.normalize(torch.randn(2, 512, generator=g), dim=-1)
+    t = torch.tensor([999, 3])
+    net, sd = make_net(oracle, cfg, seed=15)
+    r16 = net(x.cuda(), z.cuda(), t.cuda()).cpu()
+    monkeypatch.setenv("CLPK_RES16", "0")
+    net.release_plans()
+    r32 = net(x.cuda(), z.cuda(), t.cuda()).cpu()
+    monkeypatch.delenv("CLPK_RES16")
+    net.release_plans()
+    with torch.no_grad():
+        ref = oracle.unet_forward(sd, cfg["ch_mult"], x, z, t)
+    assert not torch.equal(r16, r32)                                # the switch really changes the executed path
+    e16, e32 = oracle.rel_l2(r16, ref), oracle.rel_l2(r32, ref)
+    assert e32 < EPS_TOL and e16 < EPS_TOL and e16 < 2.0 * e32 + 1e-3, (e16, e32)
+    assert oracle.rel_l2(r16, r32) < 3e-3
+    net.operand_dtype = torch.bfloat16
+    b_on = net(x.cuda(), z.cuda(), t.cuda()).cpu()
+    monkeypatch.setenv("CLPK_RES16", "0")
+    net.release_plans()
+    b_off = net(x.cuda(), z.cuda(), t.cuda()).cpu()
+    assert torch.equal(b_on, b_off)
