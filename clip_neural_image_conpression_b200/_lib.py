@@ -71,6 +71,8 @@ SIGNATURES = {
     "clpk_quant_fit": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "clpk_ddim_step": (_i, [_vp, _vp, _vp, C.POINTER(_f), _vp, _i64, _vp]),
     "clpk_timestep_embedding": (_i, [_vp, _vp, _i, _i, _f, _vp]),
+    "clpk_timestep_embedding_table": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "clpk_plan_set_time_freqs": (_i, [_vp, _vp]),
     "clpk_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "clpk_film_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "clpk_groupnorm_ws_bytes": (_i64, [_i, _i, _i, _i]),

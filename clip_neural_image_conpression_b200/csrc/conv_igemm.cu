@@ -29,7 +29,10 @@
 
 namespace clpk {
 
-constexpr int kEpiGroups = 2;                       // epilogue warp groups (4 warps each) alternating 32-column chunks
+#ifndef CLPK_EPI_GROUPS
+#define CLPK_EPI_GROUPS 2
+#endif
+constexpr int kEpiGroups = CLPK_EPI_GROUPS;         // epilogue warp groups (4 warps each) alternating 32-column chunks
 constexpr int kNumThreads = 64 + 128 * kEpiGroups;   // warp 0 TMA, warp 1 MMA, then the epilogue groups
 constexpr int kXformThreads = 128;                    // + 4 transform warps in the kXform variants (input GroupNorm fused)
 constexpr int kTileM = 128;
@@ -523,8 +526,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t phase = 0;
       int it = 0;
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        const int as = it & (p.nacc - 1);                   // accumulator ring of p.nacc (2 or 4) TMEM buffers
+        const uint32_t aphase = (uint32_t)(it >> p.nacc_shift) & 1u;
         CLPK_TRACE(blockIdx.x == 0 && lane == 0, 200);
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);  // epilogue(s) have drained this accumulator
         tc_fence_after();
@@ -714,8 +717,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     constexpr int kSub = kRows2 ? 2 : 1;     // row tiles per work item; TMEM holds 2 * kSub accumulators
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters)
     for (int sub = 0; sub < kSub; ++sub, ++it) {
-      const int as = it & (2 * kSub - 1);
-      const uint32_t aphase = (uint32_t)(it >> (kRows2 ? 2 : 1)) & 1u;
+      const int as = kRows2 ? (it & 3) : (it & (p.nacc - 1));
+      const uint32_t aphase = (uint32_t)(it >> (kRows2 ? 2 : p.nacc_shift)) & 1u;
       const TileCoord tc = decode_tile(p, tile, (int)rank, sub);
       const int h = tc.h0 + hl, w = tc.w0 + wl;
       const bool valid = tc.ok && (hl < p.hbox) && (h < p.grid_h) && (w < p.grid_w);
@@ -871,7 +874,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (++slot == (uint32_t)S) { slot = 0; sphase ^= 1u; }
           }
           CLPK_TRACE(tr, 107);
-          if (ep.gn_partial && !(CLPK_DBG(33))) {
+          if (ep.gn_partial && !(CLPK_DBG(33 | 512))) {
             // fold the row sums over the warp's 32 rows; the owning lanes park the warp's partials for the fixed-order
             // 4-warp fold at the end of the tile
             __syncwarp();
@@ -889,7 +892,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (NCTA == 2) mbar_arrive_cluster(lead_tmem_empty0 + (uint32_t)as * 8u);  // the issuer waits in the leader CTA
           else mbar_arrive(&bars->tmem_empty[as]);
         }
-        if (ep.gn_partial && !(CLPK_DBG(33))) {
+        if (ep.gn_partial && !(CLPK_DBG(33 | 512 | 256))) {
           // one barrier per tile: the 4 warps' partials of every chunk of this group are parked in red_t; thread
           // (chunk ci, pair pr) folds them in fixed order.  red is double-buffered by tile parity: a thread can only write
           // red[it & 1] again (tile it + 2) after passing the barrier of tile it + 1, which the folding threads of tile it
@@ -1294,8 +1297,14 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
     p.fd_phases = make_fastdiv(p.phases);
     p.fd_tiles_w = make_fastdiv(p.tiles_w);
     p.fd_tiles_h = make_fastdiv(item_rows);
+    // accumulator ring: 2 TMEM buffers; env CLPK_IGEMM_NACC=4 makes it 4 when the tile is narrow enough (block_n <= 128 ->
+    // 512 columns).  Measured neutral (stem 103 -> 105 us, transposed conv 138 -> 138 us, whole step +0.8 %): the short-K
+    // kernels are not bound by the MMA -> epilogue -> MMA hand-over.  The two-rows variant always uses 4 (2 rows x 2).
+    p.nacc = 2;
+    { const char* e = getenv("CLPK_IGEMM_NACC"); if (e && atoi(e) == 4 && !p.rows2 && 4 * p.block_n <= 512) p.nacc = 4; }
+    p.nacc_shift = p.nacc == 4 ? 2 : 1;
     p.tmem_cols = 32;
-    while (p.tmem_cols < (p.rows2 ? 4 : 2) * p.block_n) p.tmem_cols *= 2;
+    while (p.tmem_cols < (p.rows2 ? 4 : p.nacc) * p.block_n) p.tmem_cols *= 2;
     return CLPK_OK;
   };
   CLPK_TRY_RC(compute_tiles());

@@ -46,6 +46,7 @@ struct IgemmParams {
   int chunked;              // 1: chunked epilogue (32 columns at a time: folded vectors, fused GN stats, staged TMA store of
                             // the fp32 output if there is one); 0: narrow direct path (the 3-channel `out` conv)
   int n_staging;            // epilogue staging buffers (4 warp slots each) for the TMA-store path, 0 = direct stores
+  int nacc, nacc_shift;     // TMEM accumulator ring depth (2 or 4) and its log2
   int slot_bytes;           // one warp slot: 32 rows x 128 B (4096: fp32 output / residual) or x 64 B (2048: all-16-bit epilogue)
   int res_ahead;            // residual chunks the epilogue leader keeps in flight ahead of the one being processed
   int gn_groups, gn_slots, gn_sub;  // fused GroupNorm statistics: groups, partial slots per image, chunks per group slot

@@ -281,24 +281,27 @@ int launch_add_const(float* p, float v, int n, cudaStream_t stream) {
 
 // ------------------------------------------------------------------------------------------------ timestep embedding
 // unet.py:33-36: freqs = exp(float32(-ln(max_period)) * k / half) evaluated in fp32; args = float(t) * freqs.
+// freqs != NULL: the caller's frequency table [half] (the host evaluates the expression above with its own expf, e.g. the
+// reference's torch-CPU exp: a 1-ulp difference in a frequency is amplified by t <= 999 to ~1e-4 in the angle).
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int batch, int dim,
-                                          float neg_log_period) {
+                                          float neg_log_period, const float* __restrict__ freqs) {
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * half) return;
   const int b = i / half, k = i - b * half;
-  const float f = expf(__fdiv_rn(__fmul_rn(neg_log_period, (float)k), (float)half));
+  const float f = freqs ? __ldg(freqs + k) : expf(__fdiv_rn(__fmul_rn(neg_log_period, (float)k), (float)half));
   const float a = __fmul_rn((float)t[b], f);
   out[(long long)b * dim + k] = cosf(a);
   out[(long long)b * dim + half + k] = sinf(a);
   if ((dim & 1) && k == 0) out[(long long)b * dim + dim - 1] = 0.f;
 }
 
-int launch_timestep_embedding(const int64_t* t, float* out, int batch, int dim, float max_period, cudaStream_t stream) {
+int launch_timestep_embedding(const int64_t* t, float* out, int batch, int dim, float max_period, cudaStream_t stream,
+                              const float* freqs) {
   const int total = batch * (dim / 2);
   // float32(-math.log(max_period)): the reference evaluates the log in double and rounds once (unet.py:33)
   const float neg_log_period = (float)(-log((double)max_period));
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, stream>>>(t, out, batch, dim, neg_log_period);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, stream>>>(t, out, batch, dim, neg_log_period, freqs);
   CLPK_CHECK_LAUNCH();
   return CLPK_OK;
 }
@@ -574,6 +577,12 @@ extern "C" int clpk_timestep_embedding(const int64_t* t, float* out, int batch, 
                                        void* stream) {
   CLPK_REQUIRE(t && out && batch > 0 && dim >= 2, "clpk_timestep_embedding: bad arguments");
   return launch_timestep_embedding(t, out, batch, dim, max_period, (cudaStream_t)stream);
+}
+
+extern "C" int clpk_timestep_embedding_table(const int64_t* t, const float* freqs, float* out, int batch, int dim,
+                                             void* stream) {
+  CLPK_REQUIRE(t && freqs && out && batch > 0 && dim >= 2, "clpk_timestep_embedding_table: bad arguments");
+  return launch_timestep_embedding(t, out, batch, dim, 10000.f, (cudaStream_t)stream, freqs);
 }
 
 extern "C" int clpk_linear(const float* x, const float* w, const float* b, const float* add, float* y, int m, int n,

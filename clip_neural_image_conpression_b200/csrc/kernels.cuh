@@ -23,7 +23,8 @@ int launch_cond_combine(const float* zemb, const float* ht_tab, const DdimRun* r
                         cudaStream_t stream);
 int launch_add_const(float* p, float v, int n, cudaStream_t stream);
 int launch_delay(long long ns, cudaStream_t stream);
-int launch_timestep_embedding(const int64_t* t, float* out, int batch, int dim, float max_period, cudaStream_t stream);
+int launch_timestep_embedding(const int64_t* t, float* out, int batch, int dim, float max_period, cudaStream_t stream,
+                              const float* freqs = nullptr);
 int launch_linear(const float* x, const float* w, const float* b, const float* add, int add_rows, float* y, int m, int n,
                   int k, int act, cudaStream_t stream);
 

@@ -66,12 +66,20 @@ static int fuse_gn_mask() {
   const char* e = getenv("CLPK_FUSE_GN");
   return e ? atoi(e) : 0;
 }
-// env CLPK_RES16 (default 1): with fp16 operands the residual stream x <- x + conv2(...) (blocks.py:44, unet.py:104) is kept
-// in fp16 ONLY — conv2 / the transposed convs read the residual as a 16-bit tile and write the 16-bit sum (rounded once per
-// block from the fp32 accumulator + residual), GroupNorm reads 2 B per element, and no fp32 copy of the stream exists.
+// env CLPK_RES16 (default 1): with fp16 operands the residual stream x <- x + conv2(...) (blocks.py:44, unet.py:104) of the
+// WIDE resolution levels (rows of >= CLPK_RES16_MIN_W pixels, default 128: the row-slab levels, whose tensors are the
+// HBM-bound ones) is kept in fp16 ONLY — conv2 / the transposed conv read the residual as a 16-bit tile and write the
+// 16-bit sum (rounded once per block from the fp32 accumulator + residual), GroupNorm reads 2 B per element, and no fp32
+// copy of that level's stream exists.  Narrower levels keep the fp32 stream: their tensors live in L2, the 16-bit form buys
+// little there, and every rounding of the stream costs accuracy (on the 64 px config-1 net a 16-bit stream at every level
+// costs 2 dB of final PSNR after 50 closed-loop steps).
 static bool res16_wanted() {
   const char* e = getenv("CLPK_RES16");
   return !(e && atoi(e) == 0);
+}
+static int res16_min_width() {
+  const char* e = getenv("CLPK_RES16_MIN_W");
+  return e ? atoi(e) : 128;
 }
 // env CLPK_HEAD16 (default 1): the last transposed conv, whose result only out_norm reads, stores just the 16-bit copy
 // (statistics still come from its fp32 accumulators) and out_norm reads 2 B instead of 4 B per element.
@@ -123,10 +131,13 @@ struct clpk_plan {
   uint16_t* head_w = nullptr;  // [32][base] packed head weight (head_conv.cu)
   int head_stages = 0;       // experiments: cap of the head kernel's A ring (env CLPK_HEAD_STAGES at plan creation)
   bool x16_gn = false;       // env CLPK_X16=1: GroupNorms on the residual stream read X16 instead of fp32 X
-  bool res16 = false;        // the residual stream lives in X16 ONLY (fp16): no fp32 X traffic at all (see res16_wanted)
+  std::vector<char> lv16;    // per level: the residual stream lives in X16[l] ONLY (fp16), no fp32 X[l] (see res16_wanted)
+  bool s16(int level) const { return lv16[level] != 0; }
+  bool x16(int level) const { return x16_gn || lv16[level] != 0; }  // GroupNorms on the stream of this level read X16
   float* Yf = nullptr;       // fp32 conv1 output, only for ResBlocks whose GroupNorm statistics cannot be fused
   void* gn_ws = nullptr;
   float *temb = nullptr, *h1 = nullptr, *ht = nullptr, *hcond = nullptr, *film = nullptr, *zemb = nullptr;
+  float* time_freqs = nullptr;  // optional host-evaluated timestep-embedding frequencies [time_dim / 2] (clpk_plan_set_time_freqs)
   int64_t* t_buf = nullptr;
   float* eps_buf = nullptr;  // NCHW eps of the current step
   float* x_buf = nullptr;    // NCHW DDIM state
@@ -327,7 +338,7 @@ int run_groupnorm(clpk_plan* P, const void* x, int x_is_16, const GnPlan& gn, cu
 
 // GroupNorm over the residual stream of `level`: the 16-bit copy when its statistics are fused, else fp32 X
 int run_groupnorm_x(clpk_plan* P, int level, const GnPlan& gn, cudaStream_t s) {
-  if (gn.fused && P->x16_gn) return run_groupnorm(P, P->X16[level], 1, gn, s);
+  if (gn.fused && P->x16(level)) return run_groupnorm(P, P->X16[level], 1, gn, s);
   return run_groupnorm(P, P->X[level], 0, gn, s);
 }
 
@@ -478,6 +489,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     P->X16.push_back(x16);
   }
   { const char* e = getenv("CLPK_X16"); P->x16_gn = e && atoi(e) != 0; }
+  P->lv16.assign(L + 1, 0);
   CLPK_TRY(P->alloc(&P->Y, max_act));
   CLPK_TRY(P->alloc(&P->Yf, max_act));
   CLPK_TRY(P->alloc(&P->T, max_act));
@@ -535,23 +547,23 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   CLPK_TRY(setup_gn(P, &P->out_gn, CLPK_CONVT_4X4_S2, P->lv_h[1], P->lv_w[1]));
   gn_after_up[0] = &P->out_gn;
   {
-    // 16-bit-only residual stream (res16_wanted): every GroupNorm on the stream must take its statistics from the producing
-    // conv's fp32 accumulators (a statistics pass over the rounded copy would be slower and less exact).  fp16 operands
-    // only: bf16's 8-bit mantissa is too coarse for a running sum.
-    bool all_fused = P->out_gn.fused;
-    for (const ResBlockPlan& rb : P->rbs) all_fused = all_fused && rb.gn1.fused;
-    P->res16 = res16_wanted() && cfg->op_dtype == CLPK_OP_F16 && all_fused && !P->x16_gn;
-    if (P->res16) {
-      P->x16_gn = true;   // every producer writes X16, every GroupNorm on the stream reads it
-      for (ResBlockPlan& rb : P->rbs) rb.emit16 = true;
-    } else {
-      for (int l = 0; l <= L; ++l)
-        CLPK_TRY(P->alloc(&P->X[l], (long long)batch * P->lv_h[l] * P->lv_w[l] * P->lv_c[l]));
+    // 16-bit-only residual stream per level (res16_wanted): every GroupNorm on that level's stream must take its statistics
+    // from the producing conv's fp32 accumulators (a statistics pass over the rounded copy would be slower and less exact).
+    // fp16 operands only: bf16's 8-bit mantissa is too coarse for a running sum.
+    std::vector<char> fused(L + 1, 1);
+    fused[0] = P->out_gn.fused ? 1 : 0;
+    for (const ResBlockPlan& rb : P->rbs)
+      if (!rb.gn1.fused) fused[rb.level] = 0;
+    for (int l = 0; l <= L; ++l) {
+      P->lv16[l] = res16_wanted() && cfg->op_dtype == CLPK_OP_F16 && fused[l] && !P->x16_gn && P->lv_w[l] >= res16_min_width();
+      if (!P->lv16[l]) CLPK_TRY(P->alloc(&P->X[l], (long long)batch * P->lv_h[l] * P->lv_w[l] * P->lv_c[l]));
     }
+    for (ResBlockPlan& rb : P->rbs)
+      if (P->s16(rb.level)) rb.emit16 = true;
   }
-  P->fuse_head = (fuse_gn_mask() & 2) && P->out_gn.fused && (!P->x16_gn || P->res16) &&
+  P->fuse_head = (fuse_gn_mask() & 2) && P->out_gn.fused && !P->x16_gn &&
                  igemm_xform_ok(CLPK_CONV_3X3_S1, height, width, cfg->base, cfg->img_ch);
-  P->head16 = P->fuse_head || P->res16 || (head16_on() && P->out_gn.fused && !P->x16_gn && cfg->base % 32 == 0);
+  P->head16 = P->fuse_head || P->s16(0) || (head16_on() && P->out_gn.fused && !P->x16_gn && cfg->base % 32 == 0);
   {
     const char* e = getenv("CLPK_HEAD_FUSED");
     P->head_fused = !(e && atoi(e) == 0) && !P->fuse_head && P->head16 &&
@@ -589,7 +601,7 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     CLPK_TRY(bind_conv(P, &rb.conv1, P->T, e1));
     clpk_conv_epilogue e2{};
     e2.bias = rb.conv2.bias;
-    if (P->res16) {   // blocks.py:44 on the 16-bit stream, in place
+    if (P->s16(rb.level)) {   // blocks.py:44 on the 16-bit stream, in place
       e2.resid_op = P->X16[rb.level];
       e2.out_op = P->X16[rb.level];
     } else {
@@ -622,8 +634,8 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
                        P->lv_h[l], P->lv_w[l], &dn));
     clpk_conv_epilogue ed{};
     ed.bias = dn.bias;
-    ed.out_f32 = P->res16 ? nullptr : P->X[l + 1];
-    ed.out_op = P->x16_gn ? P->X16[l + 1] : nullptr;
+    ed.out_f32 = P->s16(l + 1) ? nullptr : P->X[l + 1];
+    ed.out_op = P->x16(l + 1) ? P->X16[l + 1] : nullptr;
     ed.cout_valid = P->lv_c[l + 1];
     wire_gn(&ed, gn_after_down[l]);
     CLPK_TRY(bind_conv(P, &dn, P->X16[l], ed));
@@ -637,8 +649,8 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     eu.bias = up.bias;
     eu.resid = P->X[l];  // skip connection, added in place
     eu.out_f32 = P->X[l];
-    eu.out_op = P->x16_gn ? P->X16[l] : nullptr;
-    if (P->res16) {
+    eu.out_op = P->x16(l) ? P->X16[l] : nullptr;
+    if (P->s16(l)) {
       eu.resid = nullptr;
       eu.resid_op = P->X16[l];
       eu.out_f32 = nullptr;
@@ -673,8 +685,8 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
     CLPK_TRY(P->alloc(&P->stem_cols, (long long)batch * height * width * 32));
     clpk_conv_epilogue es{};
     es.bias = st.bias;
-    es.out_f32 = P->res16 ? nullptr : P->X[0];
-    es.out_op = P->x16_gn ? P->X16[0] : nullptr;
+    es.out_f32 = P->s16(0) ? nullptr : P->X[0];
+    es.out_op = P->x16(0) ? P->X16[0] : nullptr;
     es.cout_valid = cfg->base;
     wire_gn(&es, &P->rbs[0].gn1);
     CLPK_TRY(bind_conv(P, &st, P->stem_cols, es));
@@ -715,6 +727,16 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
   return CLPK_OK;
 }
 
+extern "C" int clpk_plan_set_time_freqs(clpk_plan* P, const float* freqs_dev) {
+  CLPK_REQUIRE(P && freqs_dev, "clpk_plan_set_time_freqs: null argument");
+  DevGuard dg(P->device);
+  const int half = P->cfg.time_dim / 2;
+  if (!P->time_freqs) CLPK_TRY(P->alloc(&P->time_freqs, half));
+  CLPK_CHECK_CUDA(cudaMemcpy(P->time_freqs, freqs_dev, (size_t)half * sizeof(float), cudaMemcpyDeviceToDevice));
+  P->steps = 0;   // a prepared DDIM loop holds time_proj(temb(t_i)) of the old table: prepare again
+  return CLPK_OK;
+}
+
 extern "C" int64_t clpk_plan_device_bytes(const clpk_plan* P) { return P ? P->bytes : 0; }
 extern "C" double clpk_plan_flops_per_forward(const clpk_plan* P) { return P ? P->flops_fwd : 0.0; }
 extern "C" int clpk_plan_launches_per_forward(const clpk_plan* P) { return P ? P->launches_fwd : 0; }
@@ -726,7 +748,7 @@ extern "C" int clpk_unet_forward(clpk_plan* P, const float* x, const float* z, c
   cudaStream_t s = (cudaStream_t)stream;
   const clpk_unet_config& c = P->cfg;
   const int td = c.time_dim;
-  CLPK_TRY(launch_timestep_embedding(t, P->temb, P->B, td, 10000.f, s));                             // unet.py:83
+  CLPK_TRY(launch_timestep_embedding(t, P->temb, P->B, td, 10000.f, s, P->time_freqs));              // unet.py:83
   CLPK_TRY(launch_linear(P->temb, P->tp0_w, P->tp0_b, nullptr, 0, P->h1, P->B, 4 * td, td, 1, s));   // :84 Linear+SiLU
   CLPK_TRY(launch_linear(P->h1, P->tp2_w, P->tp2_b, nullptr, 0, P->ht, P->B, td, 4 * td, 0, s));     // :84 Linear
   CLPK_TRY(launch_linear(z, P->zp_w, P->zp_b, P->ht, P->B, P->hcond, P->B, td, c.z_dim, 1, s));      // :85-86
@@ -790,7 +812,7 @@ extern "C" int clpk_plan_prepare_ddim(clpk_plan* P, int steps, const int64_t* ts
   }
   CLPK_CHECK_CUDA(cudaMemcpyAsync(ts_dev, ts_host, (size_t)steps * sizeof(int64_t), cudaMemcpyHostToDevice, s));
   CLPK_CHECK_CUDA(cudaMemcpyAsync(P->coef_tab, coef_host, (size_t)steps * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
-  CLPK_TRY(launch_timestep_embedding(ts_dev, temb, steps, td, 10000.f, s));
+  CLPK_TRY(launch_timestep_embedding(ts_dev, temb, steps, td, 10000.f, s, P->time_freqs));
   CLPK_TRY(launch_linear(temb, P->tp0_w, P->tp0_b, nullptr, 0, h1, steps, 4 * td, td, 1, s));
   CLPK_TRY(launch_linear(h1, P->tp2_w, P->tp2_b, nullptr, 0, P->ht_tab, steps, td, 4 * td, 0, s));
   CLPK_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -927,7 +949,7 @@ extern "C" int clpk_plan_work_breakdown(const clpk_plan* P, double* conv_res_flo
 extern "C" int clpk_plan_groupnorm_bytes(const clpk_plan* P, double* bytes) {
   CLPK_REQUIRE(P && bytes, "clpk_plan_groupnorm_bytes: null argument");
   double tot = 0;
-  auto in_bytes_x = [&](const GnPlan& gn) { return (gn.fused && P->x16_gn) ? 2.0 : 4.0; };
+  auto in_bytes_x = [&](const GnPlan& gn) { return (gn.fused && P->x16(gn.level)) ? 2.0 : 4.0; };
   for (const ResBlockPlan& rb : P->rbs) {  // (GroupNorms applied inside their consumer conv have no stand-alone pass)
     const double n = (double)P->B * rb.h * rb.w * rb.c;
     if (!rb.gn1.in_consumer) tot += n * (in_bytes_x(rb.gn1) + 2.0);

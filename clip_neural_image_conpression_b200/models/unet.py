@@ -50,6 +50,10 @@ class _Plan:
             check(lib.clpk_plan_create(C.byref(cfg), batch, height, width, len(sd), names, ptrs, numels, C.byref(handle)),
                   "clpk_plan_create")
         self.lib, self.handle = lib, handle
+        with torch.cuda.device(self.device):   # timestep-embedding frequencies as the reference's torch-CPU exp gives them
+            f = ops.timestep_frequencies(net.time_dim).to(self.device)
+            torch.cuda.current_stream().synchronize()
+            check(lib.clpk_plan_set_time_freqs(handle, f.data_ptr()), "clpk_plan_set_time_freqs")
         self.batch, self.height, self.width = batch, height, width
         self.ddim_key = None
 

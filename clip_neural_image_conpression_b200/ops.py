@@ -7,6 +7,8 @@ fp16 by default, bf16 selectable — and an fp32 residual stream).
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import math
 
 import torch
 
@@ -75,13 +77,28 @@ def ddim_step(x: torch.Tensor, eps: torch.Tensor, coef, noise: torch.Tensor | No
     return out
 
 
+@functools.lru_cache(maxsize=32)
+def timestep_frequencies(dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    """The reference's frequency table (unet.py:33-34), evaluated by torch on the CPU exactly as the reference writes it:
+    float32 scalar * arange / half, then torch.exp.  CPU tensor [dim // 2]."""
+    half = dim // 2
+    return torch.exp(-math.log(max_period) * torch.arange(0, half) / half)
+
+
 @on_tensor_device
-def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0, host_freqs: bool = True) -> torch.Tensor:
+    """unet.py:22-39.  host_freqs (default): the frequencies come from the torch-CPU table above, so the embedding equals
+    the reference's CPU result to ~1e-6; False: the device's own expf (what the reference computes when t is on CUDA)."""
     require_cuda(t)
     t = t.contiguous().to(torch.int64)
     out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
-    check(_lib.load().clpk_timestep_embedding(ptr(t), ptr(out), t.shape[0], dim, float(max_period), stream_ptr()),
-          "clpk_timestep_embedding")
+    if host_freqs:
+        f = timestep_frequencies(dim, float(max_period)).to(t.device)
+        check(_lib.load().clpk_timestep_embedding_table(ptr(t), ptr(f), ptr(out), t.shape[0], dim, stream_ptr()),
+              "clpk_timestep_embedding_table")
+    else:
+        check(_lib.load().clpk_timestep_embedding(ptr(t), ptr(out), t.shape[0], dim, float(max_period), stream_ptr()),
+              "clpk_timestep_embedding")
     return out
 
 

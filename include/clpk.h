@@ -75,6 +75,11 @@ int clpk_ddim_step(const float* x_dev, const float* eps_dev, const float* noise_
 
 /* timestep_embedding (PKG/models/unet.py:22-39): out[b, 0:half] = cos(t*f_k), out[b, half:2*half] = sin(t*f_k) */
 int clpk_timestep_embedding(const int64_t* t_dev, float* out_dev, int batch, int dim, float max_period, void* stream);
+/* Same with a caller-evaluated frequency table freqs_dev[dim / 2] (= exp(-ln(max_period) * k / half), unet.py:34): pass the
+ * table of the reference's own torch.exp to reproduce its embedding to ~1e-6 on any host (a 1-ulp difference between two
+ * expf implementations is amplified by t <= 999 to ~1e-4 otherwise). */
+int clpk_timestep_embedding_table(const int64_t* t_dev, const float* freqs_dev, float* out_dev, int batch, int dim,
+                                  void* stream);
 
 /* y[m,n] = act(sum_k x[m,k]*w[n,k] + b[n]) (+ add[m,n]); act: 0 none, 1 SiLU.  fp32.  nn.Linear of
  * unet.py:47-53 and blocks.py:19-20. */
@@ -220,6 +225,9 @@ int clpk_plan_create(const clpk_unet_config* cfg, int batch, int height, int wid
                      const char* const* names, const float* const* ptrs_dev, const int64_t* numels,
                      clpk_plan** out_plan);
 void clpk_plan_destroy(clpk_plan* plan);
+/* Optional: the plan evaluates the timestep embedding with this frequency table [time_dim / 2] (copied) instead of the
+ * device expf (see clpk_timestep_embedding_table).  Call before clpk_plan_prepare_ddim (a prepared loop is invalidated). */
+int clpk_plan_set_time_freqs(clpk_plan* plan, const float* freqs_dev);
 int64_t clpk_plan_device_bytes(const clpk_plan* plan);
 /* algorithmic FLOPs of one forward at the plan's batch (conv + linear, 2*MAC) */
 double clpk_plan_flops_per_forward(const clpk_plan* plan);

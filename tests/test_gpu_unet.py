@@ -289,9 +289,9 @@ def test_fused_groupnorm_paths_match_unfused(oracle, monkeypatch):
 
 
 def test_16bit_residual_stream_matches_fp32_stream(oracle, monkeypatch):
-    """Default plan (fp16 operands): the residual stream lives in fp16 only (CLPK_RES16, plan.cu).  Against the plan with
-    the fp32 stream (CLPK_RES16=0) and against the fp32 oracle, at a size with row-slab and generic-tile levels; bf16
-    operands keep the fp32 stream (the switch must not change their result)."""
+    """Default plan (fp16 operands): the residual stream of the wide levels (rows >= 128 px) lives in fp16 only (CLPK_RES16,
+    plan.cu).  Against the plan with the fp32 stream (CLPK_RES16=0), the plan with the 16-bit stream at every level, and the
+    fp32 oracle; bf16 operands keep the fp32 stream (the switch must not change their result)."""
     cfg = dict(z_dim=512, base=64, ch_mult=(1, 2, 2))
     g = torch.Generator().manual_seed(14)
     x = torch.randn(2, 3, 128, 128, generator=g)
@@ -306,10 +306,15 @@ def test_16bit_residual_stream_matches_fp32_stream(oracle, monkeypatch):
     net.release_plans()
     with torch.no_grad():
         ref = oracle.unet_forward(sd, cfg["ch_mult"], x, z, t)
-    assert not torch.equal(r16, r32)                                # the switch really changes the executed path
-    e16, e32 = oracle.rel_l2(r16, ref), oracle.rel_l2(r32, ref)
-    assert e32 < EPS_TOL and e16 < EPS_TOL and e16 < 2.0 * e32 + 1e-3, (e16, e32)
-    assert oracle.rel_l2(r16, r32) < 3e-3
+    monkeypatch.setenv("CLPK_RES16_MIN_W", "0")                     # the 16-bit stream at EVERY level (default: rows >= 128 px)
+    net.release_plans()
+    rall = net(x.cuda(), z.cuda(), t.cuda()).cpu()
+    monkeypatch.delenv("CLPK_RES16_MIN_W")
+    net.release_plans()
+    assert not torch.equal(r16, r32) and not torch.equal(rall, r16)  # the switches really change the executed path
+    e16, e32, eall = oracle.rel_l2(r16, ref), oracle.rel_l2(r32, ref), oracle.rel_l2(rall, ref)
+    assert e32 < EPS_TOL and e16 < EPS_TOL and eall < EPS_TOL and e16 < 2.0 * e32 + 1e-3 and eall < 2.0 * e32 + 1e-3, (e16, e32, eall)
+    assert oracle.rel_l2(r16, r32) < 3e-3 and oracle.rel_l2(rall, r32) < 3e-3
     net.operand_dtype = torch.bfloat16
     b_on = net(x.cuda(), z.cuda(), t.cuda()).cpu()
     monkeypatch.setenv("CLPK_RES16", "0")

@@ -26,6 +26,7 @@ LAYERS = [  # name, kind, H, W, Cin, Cout, film, resid
     ("up 32->64", 2, 32, 32, 512, 256, False, True),
     ("up 128->256", 2, 128, 128, 128, 128, False, True),
     ("out 128->3", 0, 256, 256, 128, 3, False, False),
+    ("stem 32->128", 3, 256, 256, 32, 128, False, False),   # pointwise GEMM over the im2col columns
 ]
 
 
@@ -34,6 +35,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", type=str, default="")
+    ap.add_argument("--fp32-stream", dest="res16", action="store_false", help="model-like epilogues of the fp32 residual stream")
     ap.add_argument("--model-like", action="store_true", help="epilogues as the plan uses them (16-bit conv1 output, fused GN stats)")
     args = ap.parse_args()
     dev = torch.device("cuda")
@@ -45,7 +47,8 @@ def main():
             continue
         b = args.batch
         x = torch.randn(b, h, w, cin, device=dev).to(torch.float16)
-        wt = (torch.randn(cin, cout, 4, 4, device=dev) if kind == 2 else torch.randn(cout, cin, 3, 3, device=dev)) * 0.03
+        wt = (torch.randn(cin, cout, 4, 4, device=dev) if kind == 2 else torch.randn(cout, cin, 1, 1, device=dev) if kind == 3
+              else torch.randn(cout, cin, 3, 3, device=dev)) * 0.03
         wp = ops.pack_conv_weight(wt, kind)
         bias = torch.randn(cout, device=dev)
         oh, ow = (h // 2, w // 2) if kind == 1 else ((2 * h, 2 * w) if kind == 2 else (h, w))
@@ -56,8 +59,11 @@ def main():
             kw["resid"] = torch.randn(b, oh, ow, cout, device=dev)
         nchw = cout % 16 != 0
         if args.model_like and not nchw:
-            # what the plan launches: conv1 keeps only the 16-bit copy, every producer emits GroupNorm partials
-            only16 = film
+            # what the plan launches: conv1 keeps only the 16-bit copy, every producer emits GroupNorm partials; with the
+            # 16-bit residual stream (default) every conv stores 16 bits only and a residual arrives as a 16-bit tile
+            only16 = film or args.res16
+            if resid and args.res16:
+                kw["resid"] = kw["resid"].to(torch.float16)
             run = lambda: ops.conv_igemm(x, wp, kind, cout, bias, want_f32=not only16, want_op=only16, gn_groups=8, **kw)  # noqa: E731
         else:
             run = lambda: ops.conv_igemm(x, wp, kind, cout, bias, want_f32=not nchw, want_nchw=nchw, **kw)  # noqa: E731

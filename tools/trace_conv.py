@@ -20,7 +20,8 @@ def main():
     dev = torch.device("cuda")
     b = 8
     x = torch.randn(b, h, w, cin, device=dev).to(torch.float16)
-    wt = (torch.randn(cin, cout, 4, 4, device=dev) if kind == 2 else torch.randn(cout, cin, 3, 3, device=dev)) * 0.03
+    wt = (torch.randn(cin, cout, 4, 4, device=dev) if kind == 2 else torch.randn(cout, cin, 1, 1, device=dev) if kind == 3
+          else torch.randn(cout, cin, 3, 3, device=dev)) * 0.03
     wp = ops.pack_conv_weight(wt, kind)
     bias = torch.randn(cout, device=dev)
     oh, ow = (h // 2, w // 2) if kind == 1 else ((2 * h, 2 * w) if kind == 2 else (h, w))
@@ -28,12 +29,12 @@ def main():
     if film:
         kw.update(film_scale1p=torch.ones(b, cout, device=dev), film_shift=torch.zeros(b, cout, device=dev))
     if resid:
-        kw["resid"] = torch.randn(b, oh, ow, cout, device=dev)
+        kw["resid"] = torch.randn(b, oh, ow, cout, device=dev).to(torch.float16)   # 16-bit residual stream (plan default)
     lib = _lib.load()
     lib.clpk_debug_trace.restype = C.c_int
     buf = (C.c_longlong * 8192)()
     for it in range(3):
-        ops.conv_igemm(x, wp, kind, cout, bias, want_f32=not film, want_op=film, gn_groups=8, **kw)
+        ops.conv_igemm(x, wp, kind, cout, bias, want_f32=False, want_op=True, gn_groups=8, **kw)
         n = lib.clpk_debug_trace(buf, 4096)
     ev = [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
     epi = [(t, c) for t, c in ev if t < 200]
