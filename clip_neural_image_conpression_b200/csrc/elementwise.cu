@@ -607,6 +607,7 @@ extern "C" int clpk_film_apply(const float* x, const float* scale1p, const float
 // int32 fixed-point coefficients (22 fractional bits) precomputed per (input size, output size) on the host
 // (eval/resample.py, bit-identical to PIL's doubles).  The tensor is viewed as [outer][in_size][inner] uint8:
 // horizontal pass of an HWC image = (H, W, C), vertical pass = (1, H, W*C).  Integer arithmetic -> bit exact.
+namespace clpk {
 __global__ void resample_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int* __restrict__ bounds,
                                    const int* __restrict__ kk, int ksize, long long outer, int in_size, int out_size, int inner) {
   const long long total = outer * out_size * inner;
@@ -636,6 +637,7 @@ __global__ void u8_hwc_to_float_chw_kernel(const uint8_t* __restrict__ src, floa
     dst[idx] = __fsub_rn(__fdiv_rn((float)src[((long long)y * w + x) * c + ch], 127.5f), 1.0f);
   }
 }
+}  // namespace clpk
 
 extern "C" int clpk_resample_u8(const uint8_t* src, uint8_t* dst, const int32_t* bounds, const int32_t* kk, int ksize,
                                 int64_t outer, int in_size, int out_size, int inner, void* stream) {

@@ -733,6 +733,8 @@ extern "C" int clpk_plan_set_time_freqs(clpk_plan* P, const float* freqs_dev) {
   const int half = P->cfg.time_dim / 2;
   if (!P->time_freqs) CLPK_TRY(P->alloc(&P->time_freqs, half));
   CLPK_CHECK_CUDA(cudaMemcpy(P->time_freqs, freqs_dev, (size_t)half * sizeof(float), cudaMemcpyDeviceToDevice));
+  CLPK_CHECK_CUDA(cudaStreamSynchronize(nullptr));  // device-to-device copies do not block the host: the table must be in
+                                                    // place before work on any (non-blocking) stream reads it
   P->steps = 0;   // a prepared DDIM loop holds time_proj(temb(t_i)) of the old table: prepare again
   return CLPK_OK;
 }
