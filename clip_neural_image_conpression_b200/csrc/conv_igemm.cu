@@ -1111,8 +1111,12 @@ bool igemm_xform_ok(int kind, int h_in, int w_in, int cin, int cout) {
   return slab_geometry_ok(kind, w_in, cin, igemm_block_n(igemm_cout_pad(cout))) && cin <= 1024;
 }
 int igemm_block_n(int cout_pad) {
+  // widest N tile (<= 256) that divides the padded Cout; env CLPK_IGEMM_MAXBN caps it (experiments: 128-wide tiles for the
+  // 256- / 512-channel layers give 2x the work items per launch at 2/3 of the MACs per operand byte)
+  int cap = 256;
+  { const char* e = getenv("CLPK_IGEMM_MAXBN"); if (e && atoi(e) >= 16 && atoi(e) <= 256) cap = atoi(e); }
   int best = 16;
-  for (int n = 16; n <= 256 && n <= cout_pad; n += 16)
+  for (int n = 16; n <= cap && n <= cout_pad; n += 16)
     if (cout_pad % n == 0) best = n;
   return best;
 }
