@@ -867,7 +867,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             __syncwarp();
             CLPK_TRACE(tr, 106);
             if (lane == 0 && !(CLPK_DBG(1))) {
-              tma_store_5d(&maps_out.m[tc.phase], sbuf, tc.n0 + c, tc.w0 + sub_w, 0, tc.h0 + sub_h, tc.b);
+              if (!(CLPK_DBG(1024))) tma_store_5d(&maps_out.m[tc.phase], sbuf, tc.n0 + c, tc.w0 + sub_w, 0, tc.h0 + sub_h, tc.b);
               bulk_commit_group();
             }
             slot_pending = !(CLPK_DBG(1));  // slot reuse is settled at the top of the next chunk

@@ -2,15 +2,18 @@
 // (PKG/diffusion/ddim.py:21-46) as a fixed launch sequence over plan-owned device memory, captured into a CUDA graph.
 //
 // HBM layout (all plan-owned, sized for the plan's fixed batch B and image size):
-//   X[l]  fp32 NHWC  residual stream of resolution level l (l = 0 .. n_levels); X[l] doubles as the skip tensor
+//   X[l]  fp32 NHWC  residual stream of resolution level l (l = 0 .. n_levels); X[l] doubles as the skip tensor.  NOT
+//         allocated for the levels whose stream is kept in 16 bits only (see res16_wanted / lv16 below: fp16 operands,
+//         rows of >= 128 pixels) — there X16[l] IS the stream: read as a 16-bit residual tile, updated in place
 //   Y     16-bit NHWC conv1 output of the current ResBlock (max size over levels); its GroupNorm statistics are taken
 //         from the fp32 accumulators in the conv1 epilogue, only the stored copy is rounded
-//   T     bf16 NHWC  GroupNorm+SiLU output = A operand of the ResBlock convs (max size)
-//   X16[l] 16-bit NHWC copy of X[l] = the A operand of the stride-2 / transposed convs, written by the conv2 epilogue of
-//         the last ResBlock of a level.  (With env CLPK_X16=1 EVERY producer of X[l] writes it and the GroupNorms on the
-//         residual stream read it instead of fp32 X: same HBM bytes, but measured slower — the extra direct 16-bit
-//         stores cost the smem/L1-bound conv epilogues more than the GroupNorm reads save.)
-//   packed bf16 weights [Cout][tap][Cin] per conv, fp32 bias / gamma / beta / Linear weights, FiLM weights of all
+//   T     16-bit NHWC  GroupNorm+SiLU output = A operand of the ResBlock convs (max size)
+//   X16[l] 16-bit NHWC: the stream itself (16-bit levels) or the copy of X[l] that is the A operand of the stride-2 /
+//         transposed convs, written by the conv2 epilogue of the last ResBlock of a level.  (With env CLPK_X16=1 EVERY
+//         producer of an fp32 X[l] also writes it and the GroupNorms on the residual stream read it instead of fp32 X:
+//         same HBM bytes, but measured slower — the extra direct 16-bit stores cost the conv epilogues more than the
+//         GroupNorm reads save.)
+//   packed 16-bit weights [Cout][tap][Cin] per conv, fp32 bias / gamma / beta / Linear weights, FiLM weights of all
 //   ResBlocks concatenated into one [2*sumC, time_dim] matrix so ONE small GEMV launch yields every (1+scale, shift).
 #include "conv_igemm.cuh"
 #include "kernels.cuh"

@@ -2,7 +2,7 @@
 
 torch is used for device memory and streams only; every computation happens in the CUDA kernels of csrc/.
 Layout notes: reference-facing tensors are NCHW fp32; the kernels' activations are NHWC (16-bit tensor-core operands —
-fp16 by default, bf16 selectable — and an fp32 residual stream).
+fp16 by default, bf16 selectable; the residual stream is fp32 or, at the wide levels of an fp16 plan, fp16 only).
 """
 from __future__ import annotations
 
