@@ -240,43 +240,6 @@ __device__ __forceinline__ void gn_chunk_reduce(const float (&sums)[16], int lan
   if ((lane & low_mask) == 0) reinterpret_cast<float*>(redw)[4 * (idx >> 1) + (idx & 1)] = r;  // .x = sum, .y = sumsq of pair idx/2
 }
 
-// ---- statistics per IMAGE RUN (IgemmParams::gn_mode == 1).  A CTA's tiles come in runs of the same image; instead of
-// reducing every chunk over the warp's lanes and folding every tile over the group's 4 warps, each thread keeps its shifted
-// (sum, sumsq) per (chunk of this warp, group pair) in registers for the whole run — racc[(ci * P + i) * 2 + {0, 1}] — and the
-// lane reduction / 4-warp fold / partial store happen ONCE per run (gn_run_flush).  The shift K of a (chunk, pair) is taken
-// from the first tile of the run that has valid rows and parked in the .z field of the run's red entry.
-template <int P>
-__device__ __forceinline__ void gn_row_acc(const float (&v)[32], bool valid, int lane, int ci, bool take_k, float4* redw,
-                                           float (&racc)[16]) {
-  constexpr int per = 32 / P;
-  constexpr int kMaxQ = 16 / (2 * P);   // chunks per warp this accumulator layout can hold
-#pragma unroll
-  for (int i = 0; i < P; ++i) {
-    float k;
-    if (take_k) {
-      k = __shfl_sync(0xffffffffu, v[i * per], 0);
-      if (lane == 0) reinterpret_cast<float*>(redw + i)[2] = k;
-    } else {
-      k = reinterpret_cast<const float*>(redw + i)[2];   // smem broadcast
-    }
-    const f32x2 kk = pack2(k, k);
-    f32x2 s1 = pack2(0.f, 0.f), s2 = s1;
-#pragma unroll
-    for (int j = 0; j < per; j += 2) {
-      const f32x2 d = sub2(pack2(v[i * per + j], v[i * per + j + 1]), kk);
-      s1 = add2(s1, d);
-      s2 = fma2(d, d, s2);
-    }
-    float a0, a1, b0, b1;
-    unpack2(s1, a0, a1);
-    unpack2(s2, b0, b1);
-    const float sa = valid ? a0 + a1 : 0.f, sb = valid ? b0 + b1 : 0.f;
-#pragma unroll
-    for (int q = 0; q < kMaxQ; ++q)
-      if (ci == q) { racc[(q * P + i) * 2] += sa; racc[(q * P + i) * 2 + 1] += sb; }
-  }
-}
-
 constexpr int kSlabABytes = 17 * 1024;  // (128 + 2) slab rows x 128 B = 16640, padded to the 1024-byte swizzle-atom pitch
 
 template <int BLOCK_K, int NCTA, bool kSlab, bool kXform, bool kRows2 = false>
@@ -717,15 +680,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t slot = 0, sphase = 0;           // staging slot of the current chunk and how often the ring has wrapped (parity)
     bool slot_pending = false;               // a store was committed whose slot-reuse bookkeeping is still to be done
     int cached_key = -1;
-    // statistics per image run (gn_mode 1, see gn_row_acc): accumulators, image of the run, valid rows accumulated, whether
-    // the shifts still have to be taken, red double-buffer parity
-    const bool gn_run = ep.gn_partial != nullptr && p.gn_mode == 1;
-    float racc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) racc[i] = 0.f;
-    int run_b = -1, run_par = 0;
-    float run_rows = 0.f;
-    bool run_fresh = false;
     // Residual sub-boxes are TMA-loaded straight into the staging slot that is later stored from (read-modify-write in
     // place).  Lane 0 keeps `A` of them in flight; (ld_tile, ld_c, ld_slot) is its load cursor.
     const bool res16 = p.chunked && (ep.resid_op != nullptr);  // 16-bit residual (operand format): 64-byte rows, 64B swizzle
@@ -759,64 +713,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     };
     if (res_tma && lane == 0 && !(CLPK_DBG(1)))
       for (int i = 0; i < A; ++i) issue_res_load();
-    // End of an image run (gn_mode 1): reduce the run's accumulators over the lanes (one 16-wide halving butterfly), park the
-    // warp's totals, ONE named barrier of the group's 4 warps, warp 0 of the group re-bases the 4 warps' shifted sums on a
-    // common K (exact algebra, fixed order) and writes partial[b][slot = this CTA (x gn_sub)][group] + counts[b][slot].  red is
-    // double-buffered by run parity: a warp writes red[par] again two runs later, i.e. after the barrier of the run in
-    // between, which the folding warp only reaches after its fold.
-    const int nchw = (p.block_n - 32 * eg + cstep - 1) / cstep;   // chunks of this warp per tile
-    auto gn_run_flush = [&](int b) {
-      const int par = run_par;
-      const float r = warp_reduce_scatter<16>(racc, lane);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) racc[i] = 0.f;
-      const int idx = scatter_owner_index<16>(lane);          // (lane & 1) == 0 lanes own value idx = (q * P + i) * 2 + which
-      const int q = idx >> (npairs_shift + 1), rest = idx & (2 * npairs - 1);
-      if ((lane & 1) == 0 && q < nchw)
-        reinterpret_cast<float*>(vec->red + vec->idx(par, eg, q, quarter) + (rest >> 1))[rest & 1] = r;
-      if (lane < nchw * npairs)
-        reinterpret_cast<float*>(vec->red + vec->idx(par, eg, lane >> npairs_shift, quarter) + (lane & (npairs - 1)))[3] = run_rows;
-      named_bar_sync(bar_id, 128);
-      if (quarter == 0 && lane < nchw * npairs) {
-        const int fci = lane >> npairs_shift, pr = lane & (npairs - 1);
-        const float4* rr = vec->red + vec->idx(par, eg, fci, 0) + pr;
-        const float cnt = (float)(cpg >= 32 ? 32 : cpg);  // channels behind one partial of this chunk
-        float k0 = 0.f, s1 = 0.f, s2 = 0.f, n = 0.f;
-        bool have = false;
-#pragma unroll
-        for (int wq = 0; wq < 4; ++wq) {
-          const float4 a = rr[wq * 8];   // (sum, sumsq, K, valid rows) of warp wq over the run
-          if (a.w > 0.f) {
-            if (!have) { k0 = a.z; have = true; }
-            const float d = a.z - k0;
-            const float nw = a.w * cnt;
-            s1 += fmaf(nw, d, a.x);
-            s2 += fmaf(nw * d, d, fmaf(2.f * d, a.x, a.y));
-            n += nw;
-          }
-        }
-        float mean = 0.f, m2 = 0.f;
-        if (have) {
-          const float inv_n = 1.0f / n;
-          mean = fmaf(s1, inv_n, k0);
-          m2 = fmaxf(fmaf(-s1 * inv_n, s1, s2), 0.f);
-        }
-        const int ch = 32 * eg + cstep * fci;   // (a single N tile in this mode: every tile's n0 is 0)
-        int g, sub;
-        if (cpg >= 32) {
-          if (p.gn_cpg_shift >= 0) { g = ch >> p.gn_cpg_shift; sub = (ch & (cpg - 1)) >> 5; }
-          else { g = ch / cpg; sub = (ch - g * cpg) >> 5; }
-        } else {
-          g = (ch >> p.gn_cpg_shift) + pr;   // cpg in {4, 8, 16}
-          sub = 0;
-        }
-        const int slotg = (int)blockIdx.x * p.gn_sub + sub;
-        float2* part = reinterpret_cast<float2*>(ep.gn_partial);
-        part[((long long)b * p.gn_slots + slotg) * p.gn_groups + g] = make_float2(mean, m2);
-        reinterpret_cast<float*>(part + (long long)p.batch * p.gn_slots * p.gn_groups)[(long long)b * p.gn_slots + slotg] = n;
-      }
-      run_par ^= 1;
-    };
     const uint32_t lead_tmem_empty0 = (NCTA == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[0]), 0u) : 0u;
     constexpr int kSub = kRows2 ? 2 : 1;     // row tiles per work item; TMEM holds 2 * kSub accumulators
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters)
@@ -850,14 +746,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         const int red_par = it & 1;
         const float nrows = ep.gn_partial ? (float)__popc(__ballot_sync(0xffffffffu, valid)) : 0.f;  // valid rows of this warp
-        if (gn_run && tc.ok && tc.b != run_b) {   // a new image starts: close the previous run
-          if (run_b >= 0) gn_run_flush(run_b);
-          run_b = tc.b;
-          run_rows = 0.f;
-          run_fresh = true;
-        }
-        const bool take_k = gn_run && run_fresh && nrows > 0.f;   // this tile supplies the run's shifts
-        run_rows += nrows;
         [[maybe_unused]] const bool tr = blockIdx.x == 0 && ew == 0 && lane == 0;  // traced warp (debug builds)
         CLPK_TRACE(tr, 100);
         mbar_wait(&bars->tmem_full[as], aphase);
@@ -932,13 +820,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 unpack2(add2(pack2(v[4 * j4 + 2], v[4 * j4 + 3]), pack2(q.z, q.w)), v[4 * j4 + 2], v[4 * j4 + 3]);
               }
             }
-            if (gn_run) {
-              float4* rk = vec->red + vec->idx(run_par, eg, ci, quarter);
-              if (cpg >= 32) gn_row_acc<1>(v, valid, lane, ci, take_k, rk, racc);
-              else if (cpg == 16) gn_row_acc<2>(v, valid, lane, ci, take_k, rk, racc);
-              else if (cpg == 8) gn_row_acc<4>(v, valid, lane, ci, take_k, rk, racc);
-              else gn_row_acc<8>(v, valid, lane, ci, take_k, rk, racc);
-            } else if (ep.gn_partial && !(CLPK_DBG(32))) {
+            if (ep.gn_partial && !(CLPK_DBG(32))) {
               // per-thread (sum, sumsq) of this row's 32 values split by consumer-GroupNorm group; the cross-lane fold
               // happens after the chunk's store has been issued (it is off the store's critical path)
               if (cpg >= 32) gn_row_sums<1>(v, valid, nrows, lane, gsums, redw);
@@ -992,7 +874,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (++slot == (uint32_t)S) { slot = 0; sphase ^= 1u; }
           }
           CLPK_TRACE(tr, 107);
-          if (ep.gn_partial && !gn_run && !(CLPK_DBG(33 | 512))) {
+          if (ep.gn_partial && !(CLPK_DBG(33 | 512))) {
             // fold the row sums over the warp's 32 rows; the owning lanes park the warp's partials for the fixed-order
             // 4-warp fold at the end of the tile
             __syncwarp();
@@ -1010,8 +892,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (NCTA == 2) mbar_arrive_cluster(lead_tmem_empty0 + (uint32_t)as * 8u);  // the issuer waits in the leader CTA
           else mbar_arrive(&bars->tmem_empty[as]);
         }
-        if (take_k) run_fresh = false;
-        if (ep.gn_partial && !gn_run && !(CLPK_DBG(33 | 512 | 256))) {
+        if (ep.gn_partial && !(CLPK_DBG(33 | 512 | 256))) {
           // one barrier per tile: the 4 warps' partials of every chunk of this group are parked in red_t; thread
           // (chunk ci, pair pr) folds them in fixed order.  red is double-buffered by tile parity: a thread can only write
           // red[it & 1] again (tile it + 2) after passing the barrier of tile it + 1, which the folding threads of tile it
@@ -1057,8 +938,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int slotg = mtile * p.gn_sub + sub;
             float2* part = reinterpret_cast<float2*>(ep.gn_partial);
             part[((long long)tc.b * p.gn_slots + slotg) * p.gn_groups + g] = make_float2(mean, m2);
-            // element count behind every pair of this slot, per image
-            reinterpret_cast<float*>(part + (long long)p.batch * p.gn_slots * p.gn_groups)[(long long)tc.b * p.gn_slots + slotg] = n;
+            // element count behind every triple of this slot: geometry only, so image 0's tiles publish it for all images
+            if (tc.b == 0)
+              reinterpret_cast<float*>(part + (long long)p.batch * p.gn_slots * p.gn_groups)[slotg] = n;
           }
         }
         CLPK_TRACE(tr, 109);
@@ -1100,7 +982,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         else mbar_arrive(&bars->tmem_empty[as]);
       }
     }
-    if (gn_run && run_b >= 0) gn_run_flush(run_b);   // the last image run of this CTA
     if (lane == 0 && st_tma) bulk_wait_group_all();  // all of this warp's stores retired before smem goes away
     CLPK_GTRACE(lane == 0 && ew == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2), 304);  // epilogue done
   }
@@ -1210,21 +1091,6 @@ static void tile_geometry(int kind, int h_in, int w_in, int* grid_h, int* grid_w
 // the chunked epilogue moves per-warp sub-boxes (32 tile rows) by TMA: 32 rows must form a rectangle of the tile
 static bool warp_subbox_ok(int wbox) { return wbox % 32 == 0 || 32 % wbox == 0; }
 
-// Fused-statistics mode of a conv with `cout` channels whose consumer GroupNorm sums gn_cpg channels per partial:
-//   1 = one partial per (CTA, image run): accumulators live in registers across the tiles of a run (gn_row_acc); needs a
-//       single N tile (so a CTA's tiles of one image form ONE run) and <= 16 accumulators per thread;
-//   0 = one partial per tile (lane reduction per chunk, 4-warp fold + named barrier every tile): position-independent
-//       partials, i.e. an image's statistics do not depend (not even in the last bit) on its place in the batch.
-// env CLPK_GN_MODE=0 forces 0.  (Flushing the mode-1 machinery after every tile was measured too: slower than mode 0.)
-int igemm_gn_mode(int cout, int gn_cpg) {
-  { const char* e = getenv("CLPK_GN_MODE"); if (e && atoi(e) == 0) return 0; }
-  if (gn_cpg <= 0) return 0;
-  const int cout_pad = igemm_cout_pad(cout), bn = igemm_block_n(cout_pad);
-  if (cout_pad != bn || bn % 32 != 0) return 0;
-  const int nchg = (bn / 32 + kEpiGroups - 1) / kEpiGroups, np = gn_cpg >= 32 ? 1 : 32 / gn_cpg;
-  return nchg * 2 * np <= 16 ? 1 : 0;
-}
-
 int igemm_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg) {
   if (gn_cpg <= 0 || cout % gn_cpg != 0 || cout % 32 != 0) return 0;
   if (!(gn_cpg == 4 || gn_cpg == 8 || gn_cpg == 16 || gn_cpg % 32 == 0)) return 0;
@@ -1233,7 +1099,6 @@ int igemm_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg) {
   tile_geometry(kind, h_in, w_in, &gh, &gw, &wbox, &hbox, &phases);
   if (!warp_subbox_ok(wbox)) return 0;
   const int sub = gn_cpg >= 32 ? gn_cpg / 32 : 1;
-  if (igemm_gn_mode(cout, gn_cpg) == 1) return num_sms() * sub;   // slot = CTA index (the grid never exceeds the SM count)
   return phases * ((gh + hbox - 1) / hbox) * ((gw + wbox - 1) / wbox) * sub;
 }
 static bool slab_geometry_ok(int kind, int w_in, int cin, int block_n) {
@@ -1489,14 +1354,13 @@ int igemm_setup(const void* x_bf16, const void* w_packed, int kind, int batch, i
       if (p.ep.out_f32 || any_resid) p.chunked = 0;  // (a 16-bit-only output falls back to direct stores from registers)
     }
   }
-  p.gn_groups = p.gn_slots = p.gn_mode = 0;
+  p.gn_groups = p.gn_slots = 0;
   p.gn_sub = 1;
   if (p.ep.gn_partial) {
     p.gn_slots = igemm_gn_slots(kind, h_in, w_in, cout, p.ep.gn_cpg);
     CLPK_REQUIRE(p.gn_slots > 0 && p.chunked,
                  "fused GroupNorm statistics unsupported for this conv (cout=%d cpg=%d)", cout, p.ep.gn_cpg);
     p.gn_groups = cout / p.ep.gn_cpg;
-    p.gn_mode = igemm_gn_mode(cout, p.ep.gn_cpg);
     p.gn_sub = p.ep.gn_cpg >= 32 ? p.ep.gn_cpg / 32 : 1;
     p.gn_cpg_shift = -1;
     for (int sft = 2; sft < 16; ++sft)

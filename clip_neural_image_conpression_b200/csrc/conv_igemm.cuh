@@ -46,7 +46,6 @@ struct IgemmParams {
   int chunked;              // 1: chunked epilogue (32 columns at a time: folded vectors, fused GN stats, staged TMA store of
                             // the fp32 output if there is one); 0: narrow direct path (the 3-channel `out` conv)
   int n_staging;            // epilogue staging buffers (4 warp slots each) for the TMA-store path, 0 = direct stores
-  int gn_mode;              // fused statistics: 0 = one partial per tile, 1 = one partial per (CTA, image run) (see gn_row_acc)
   int nacc, nacc_shift;     // TMEM accumulator ring depth (2 or 4) and its log2
   int slot_bytes;           // one warp slot: 32 rows x 128 B (4096: fp32 output / residual) or x 64 B (2048: all-16-bit epilogue)
   int res_ahead;            // residual chunks the epilogue leader keeps in flight ahead of the one being processed
@@ -98,7 +97,7 @@ int encode_tensor_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 // padded GEMM-N of a conv with `cout` output channels, and the UMMA N tile chosen for it
 int igemm_gn_slots(int kind, int h_in, int w_in, int cout, int gn_cpg);  // <= 0: unsupported
 // floats of a gn_partial buffer: batch * slots * pieces (mean, M2) pairs followed by `slots` element counts
-inline long long igemm_gn_partial_floats(int batch, int slots, int pieces) { return 2ll * batch * slots * pieces + (long long)batch * slots; }
+inline long long igemm_gn_partial_floats(int batch, int slots, int pieces) { return 2ll * batch * slots * pieces + slots; }
 int igemm_cout_pad(int cout);
 // can a conv of this geometry apply ep.in_scale / in_shift to its A operand in shared memory (row-slab mainloop)?
 bool igemm_xform_ok(int kind, int h_in, int w_in, int cin, int cout);

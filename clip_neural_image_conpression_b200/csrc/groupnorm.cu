@@ -206,63 +206,39 @@ __device__ __forceinline__ void gn_affine8(const float* __restrict__ gamma, cons
 }
 
 
-// Folds the partial statistics a conv epilogue wrote (conv_igemm.cu, "Fused GroupNorm statistics") into (mean, rstd)
+// Folds the per-tile statistics a conv epilogue wrote (conv_igemm.cu, "Fused GroupNorm statistics") into (mean, rstd)
 // of group g of image b; executed by one whole warp (lanes stride over the entries, fixed-order shuffle tree ->
-// deterministic).  partial[b][slot][piece] = (mean, M2 = sum (x - mean)^2) of the elements behind the entry: `pieces` pairs
-// per slot, group g owns pieces [g*m, (g+1)*m), m = pieces / groups (m > 1: group sizes such as 24 or 48 that the epilogue
-// sums in 8- or 16-channel pieces); counts[b][slot] = number of elements behind every pair of that slot for that image
-// (0: the slot holds nothing for this image — e.g. a CTA that processed no tile of it — and is skipped).
-// Every lane accumulates its entries relative to the mean of ITS first non-empty entry (Chan et al.: every accumulated
-// term is of the order of the spread of the means, fp32 is ample), turns them into a (n, mean, M2) triple, and the
-// triples are merged pairwise in a fixed tree:  n = n1 + n2, d = mean2 - mean1, mean = mean1 + d n2 / n,
-// M2 = M2_1 + M2_2 + d^2 n1 n2 / n.
-struct GnTriple { float n, mean, m2; };
-__device__ __forceinline__ GnTriple gn_merge(const GnTriple& a, const GnTriple& c) {   // a = the lower lane / warp
-  GnTriple r;
-  r.n = a.n + c.n;
-  if (r.n <= 0.f) { r.mean = 0.f; r.m2 = 0.f; return r; }
-  const float d = c.mean - a.mean, f = c.n / r.n;
-  r.mean = fmaf(d, f, a.mean);
-  r.m2 = a.m2 + c.m2 + d * d * (a.n * f);
-  return r;
-}
-__device__ __forceinline__ GnTriple gn_warp_triple(const float2* __restrict__ pp, const float* __restrict__ cnt, int first,
-                                                   int stride, int entries, int m, int pieces, int lane) {
-  float m0 = 0.f, A = 0.f, Q = 0.f, M = 0.f, N = 0.f;
-  bool have = false;
-#pragma unroll 4
-  for (int k = first; k < entries; k += stride) {
-    const int slot = k / m, j = k - slot * m;
-    const float2 v = __ldg(pp + (long long)slot * pieces + j);
-    const float n = __ldg(cnt + slot);
-    if (n > 0.f) {
-      if (!have) { m0 = v.x; have = true; }
-      const float d = v.x - m0, nd = n * d;
-      A += nd; Q = fmaf(nd, d, Q); M += v.y; N += n;
-    }
-  }
-  GnTriple t;
-  t.n = N;
-  const float dm = have ? A / N : 0.f;
-  t.mean = m0 + dm;
-  t.m2 = have ? fmaxf(M + fmaf(-A, dm, Q), 0.f) : 0.f;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    GnTriple u;
-    u.n = __shfl_xor_sync(0xffffffffu, t.n, o);
-    u.mean = __shfl_xor_sync(0xffffffffu, t.mean, o);
-    u.m2 = __shfl_xor_sync(0xffffffffu, t.m2, o);
-    t = (lane & o) ? gn_merge(u, t) : gn_merge(t, u);   // both lanes of a pair evaluate the same expression
-  }
-  return t;
-}
+// deterministic).  partial[b][slot][piece] = (tile mean, tile M2): `pieces` pairs per slot, group g owns pieces
+// [g*m, (g+1)*m), m = pieces / groups (m > 1: group sizes such as 24 or 48 that the epilogue sums in 8- or 16-channel
+// pieces); counts[slot] = elements behind every pair of that slot (geometry only, shared by all images).
+// Combination (Chan et al.) relative to the FIRST pair's mean m0, so every accumulated term is of the order of the spread
+// of the tile means (fp32 is ample):
+//   N = sum n, A = sum n (mean_i - m0), Q = sum n (mean_i - m0)^2, M = sum M2_i
+//   mean = m0 + A / N,   var = (M + Q - A^2 / N) / N
 __device__ __forceinline__ float2 gn_fold_partials(const float2* __restrict__ partial, const float* __restrict__ counts,
                                                    int b, int g, int slots, int pieces, int groups, float eps, int lane) {
   const int m = pieces / groups;
-  const GnTriple t = gn_warp_triple(partial + (long long)b * slots * pieces + g * m, counts + (long long)b * slots, lane, 32,
-                                    slots * m, m, pieces, lane);
-  const float var = fmaxf(t.m2 / t.n, 0.f);
-  return make_float2(t.mean, 1.0f / sqrtf(var + eps));
+  const float2* pp = partial + (long long)b * slots * pieces + g * m;
+  const float m0 = __ldg(pp).x;
+  float A = 0.f, Q = 0.f, M = 0.f, N = 0.f;
+#pragma unroll 4
+  for (int k = lane; k < slots * m; k += 32) {
+    const int slot = k / m, j = k - slot * m;
+    const float2 v = __ldg(pp + (long long)slot * pieces + j);
+    const float n = __ldg(counts + slot);
+    const float d = v.x - m0, nd = n * d;
+    A += nd; Q = fmaf(nd, d, Q); M += v.y; N += n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    A += __shfl_xor_sync(0xffffffffu, A, o);
+    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+    M += __shfl_xor_sync(0xffffffffu, M, o);
+    N += __shfl_xor_sync(0xffffffffu, N, o);
+  }
+  const float inv_n = 1.0f / N, dm = A * inv_n;
+  const float var = fmaxf((M + fmaf(-A, dm, Q)) * inv_n, 0.f);
+  return make_float2(m0 + dm, 1.0f / sqrtf(var + eps));
 }
 
 template <bool kIn16, bool kHoist>
@@ -337,18 +313,35 @@ gn_affine_kernel(const float2* __restrict__ partial, const float* __restrict__ g
   pdl_prologue_done();
   const int g = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* counts = reinterpret_cast<const float*>(partial + (long long)gridDim.y * slots * pieces) + (long long)b * slots;
+  const float* counts = reinterpret_cast<const float*>(partial + (long long)gridDim.y * slots * pieces);
   const int m = pieces / groups;
-  const GnTriple t = gn_warp_triple(partial + (long long)b * slots * pieces + g * m, counts, warp * 32 + lane, 128, slots * m, m,
-                                    pieces, lane);
-  if (lane == 0) part_s[warp] = make_float4(t.n, t.mean, t.m2, 0.f);
+  const float2* pp = partial + (long long)b * slots * pieces + g * m;
+  const float m0 = __ldg(pp).x;
+  float A = 0.f, Q = 0.f, M = 0.f, N = 0.f;
+#pragma unroll 4
+  for (int k = warp * 32 + lane; k < slots * m; k += 128) {
+    const int slot = k / m, j = k - slot * m;
+    const float2 v = __ldg(pp + (long long)slot * pieces + j);
+    const float n = __ldg(counts + slot);
+    const float d = v.x - m0, nd = n * d;
+    A += nd; Q = fmaf(nd, d, Q); M += v.y; N += n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    A += __shfl_xor_sync(0xffffffffu, A, o);
+    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+    M += __shfl_xor_sync(0xffffffffu, M, o);
+    N += __shfl_xor_sync(0xffffffffu, N, o);
+  }
+  if (lane == 0) part_s[warp] = make_float4(A, Q, M, N);
   __syncthreads();
   if (threadIdx.x == 0) {
-    GnTriple r{part_s[0].x, part_s[0].y, part_s[0].z};
+    float4 t = part_s[0];
 #pragma unroll
-    for (int w = 1; w < 4; ++w) r = gn_merge(r, GnTriple{part_s[w].x, part_s[w].y, part_s[w].z});
-    const float var = fmaxf(r.m2 / r.n, 0.f);
-    st_s = make_float2(r.mean, 1.0f / sqrtf(var + eps));
+    for (int w = 1; w < 4; ++w) { t.x += part_s[w].x; t.y += part_s[w].y; t.z += part_s[w].z; t.w += part_s[w].w; }
+    const float inv_n = 1.0f / t.w, dm = t.x * inv_n;
+    const float var = fmaxf((t.z + fmaf(-t.x, dm, t.y)) * inv_n, 0.f);
+    st_s = make_float2(m0 + dm, 1.0f / sqrtf(var + eps));
   }
   __syncthreads();
   const float2 st = st_s;

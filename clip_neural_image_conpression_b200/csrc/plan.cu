@@ -306,11 +306,7 @@ int setup_gn(clpk_plan* P, GnPlan* gn, int producer_kind, int prod_h_in, int pro
   gn->fused = gn->slots > 0;
   if (gn->fused) {
     float* buf = nullptr;
-    const long long nf = igemm_gn_partial_floats(P->B, gn->slots, gn->pieces) + 2;
-    CLPK_TRY(P->alloc(&buf, nf));
-    // zero-filled once: a slot the producer never writes for an image (a CTA that processes no tile of it) must read as
-    // "no elements" (count 0) in every fold
-    CLPK_CHECK_CUDA(cudaMemset(buf, 0, (size_t)nf * sizeof(float)));
+    CLPK_TRY(P->alloc(&buf, igemm_gn_partial_floats(P->B, gn->slots, gn->pieces) + 2));
     gn->partial = reinterpret_cast<float2*>(buf);
   }
   return CLPK_OK;

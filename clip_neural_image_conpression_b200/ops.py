@@ -242,9 +242,8 @@ def conv_igemm(x_nhwc_op: torch.Tensor, w_packed: torch.Tensor, kind: int, cout:
         slots = int(_lib.load().clpk_conv_gn_slots(kind, h, w, cout, cpg))
         if slots <= 0:
             raise ValueError(f"fused GroupNorm statistics unsupported for cout={cout}, groups={gn_groups}")
-        # [b][slots][groups] (mean, M2) pairs followed by [b][slots] element counts; zero-filled: slots the kernel does not
-        # write for an image count as empty (see include/clpk.h)
-        partial = torch.zeros(2 * b * slots * gn_groups + b * slots, dtype=torch.float32, device=dev)
+        # [b][slots][groups] (tile mean, tile M2) pairs followed by [slots] element counts (see include/clpk.h)
+        partial = torch.zeros(2 * b * slots * gn_groups + slots, dtype=torch.float32, device=dev)
     _conv("clpk_conv_igemm" if impl == "igemm" else "clpk_conv_direct", x_nhwc_op, w_packed, kind, cout, bias,
           film_scale1p, film_shift, resid16 if resid16 is not None else (_f32c(resid) if resid is not None else None),
           outs.get("f32"), outs.get("op"),
@@ -270,7 +269,7 @@ def groupnorm_affine(partial: torch.Tensor, batch: int, slots: int, gamma: torch
     [B, C] of GroupNorm(groups) in affine form."""
     require_cuda(partial, gamma, beta)
     c = gamma.numel()
-    pieces = (partial.numel() - batch * slots) // (2 * batch * slots)
+    pieces = (partial.numel() - slots) // (2 * batch * slots)
     scale = torch.empty((batch, c), dtype=torch.float32, device=partial.device)
     shift = torch.empty_like(scale)
     check(_lib.load().clpk_groupnorm_affine(ptr(partial), ptr(_f32c(gamma)), ptr(_f32c(beta)), ptr(scale), ptr(shift), batch,

@@ -137,12 +137,10 @@ typedef struct clpk_conv_epilogue {
   float* out_nchw;            /* dev NCHW fp32 or NULL            */
   int cout_valid;             /* channels really present (<= cout_pad) */
   /* Fused GroupNorm statistics of the FINAL output values (after bias / FiLM / residual), accumulated in the epilogue as
-   * shifted sums.  gn_partial = ZERO-INITIALISED float buffer of 2 * batch * slots * groups + batch * slots elements, slots =
-   * clpk_conv_gn_slots(...), groups = cout / gn_cpg:  [b][slot][g] float2 (mean, M2 = sum (x - mean)^2 of the elements behind
-   * the entry) followed by [b][slot] float element counts (0 = the slot holds nothing for that image: the kernel writes one
-   * entry per tile, or — single N tile — one per (CTA, image) it worked on, and leaves the rest untouched).  Fold with
-   * clpk_groupnorm_finalize or clpk_groupnorm_affine.  NULL = off.  Needs an NHWC output and gn_cpg in {4, 8, 16} or a
-   * multiple of 32. */
+   * shifted sums.  gn_partial = float buffer of 2 * batch * slots * groups + slots elements, slots =
+   * clpk_conv_gn_slots(...), groups = cout / gn_cpg:  [b][slot][g] float2 (tile mean, tile M2 = sum (x - mean)^2) followed
+   * by [slot] float element counts (geometry only, identical for every image).  Fold with clpk_groupnorm_finalize or
+   * clpk_groupnorm_affine.  NULL = off.  Needs an NHWC output and gn_cpg in {4, 8, 16} or a multiple of 32. */
   void* gn_partial;
   int gn_cpg;
   /* Input transform fused into the A-operand path — the consumer-side half of GroupNorm [+ SiLU] (blocks.py:41,43;
