@@ -21,6 +21,7 @@
 // warps 10..13 move accumulators TMEM -> D ring and do the shift-add + NCHW fp32 store.
 #include "conv_igemm.cuh"
 #include "kernels.cuh"
+#include "ddim_math.cuh"
 
 #include <algorithm>
 #include <mutex>
@@ -48,6 +49,11 @@ struct HeadParams {
   const float* shift;
   const float* bias;          // [3]
   float* out;                 // NCHW fp32 [batch][3][h][w]
+  // optional DDIM update fused into the epilogue (ddim.py:36-45): x <- update(x, eps) for the run's current step, in place
+  // on ddim_x (same NCHW shape as `out`, which still receives eps).  All three NULL = plain head.
+  float* ddim_x;
+  const float* ddim_coef;     // [steps][5]
+  const DdimRun* ddim_run;
 };
 
 struct __align__(8) HeadBarriers {
@@ -228,6 +234,19 @@ head_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int row = quarter * 32 + lane;          // pixel of the tile
     const float b0 = __ldg(p.bias), b1 = __ldg(p.bias + 1), b2 = __ldg(p.bias + 2);
     const long long plane = (long long)p.h * p.w;
+    // fused DDIM update: coefficients / noise source of the run's current step (the same values ddim_step_kernel reads)
+    const bool ddim = p.ddim_x != nullptr;
+    DdimCoef dk{};
+    int dstep = 0;
+    unsigned long long dseed = 0;
+    const float* dnz = nullptr;
+    if (ddim) {
+      dstep = p.ddim_run->step;
+      dseed = p.ddim_run->seed;
+      dk = ddim_load_coef(p.ddim_coef, dstep);
+      if (p.ddim_run->noise && dk.sigma > 0.f) dnz = p.ddim_run->noise + (long long)dstep * p.ddim_run->noise_step_stride;
+    }
+    const bool dstoch = dk.sigma > 0.f;
     // Tap row (r, s) of a D row is stored SHIFTED by 5 - s columns (source pixel q at index q + 5 - s), so the values output
     // pixel x needs from all 27 tap rows sit at the same 16-byte aligned index x + 4: four outputs per LDS.128.
     auto emit_row = [&](int g) {                  // output row g from D rows g-1, g, g+1 (all 128 epilogue threads)
@@ -235,6 +254,15 @@ head_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       float* o = p.out + ((long long)b * 3) * plane + (long long)y * p.w;
       for (int x = 4 * et; x < p.w; x += 4 * 128) {
         float4 a0 = make_float4(b0, b0, b0, b0), a1 = make_float4(b1, b1, b1, b1), a2 = make_float4(b2, b2, b2, b2);
+        // fused DDIM update: the three x loads are issued before the 27-tap shift-add so that their latency hides under it
+        const long long off = (o - p.out) + x;
+        float* xo = p.ddim_x + off;
+        float4 x0 = a0, x1 = a0, x2 = a0;
+        if (ddim) {
+          x0 = *reinterpret_cast<const float4*>(xo);
+          x1 = *reinterpret_cast<const float4*>(xo + plane);
+          x2 = *reinterpret_cast<const float4*>(xo + 2 * plane);
+        }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const int yy = y + r - 1;
@@ -254,6 +282,11 @@ head_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         *reinterpret_cast<float4*>(o + x) = a0;
         *reinterpret_cast<float4*>(o + plane + x) = a1;
         *reinterpret_cast<float4*>(o + 2 * plane + x) = a2;
+        if (ddim) {   // x <- update(x, eps): element offsets / Philox counters exactly those of ddim_step_kernel
+          *reinterpret_cast<float4*>(xo) = ddim_update4(x0, a0, dk, dstoch, dnz, off >> 2, dstep, dseed);
+          *reinterpret_cast<float4*>(xo + plane) = ddim_update4(x1, a1, dk, dstoch, dnz, (off + plane) >> 2, dstep, dseed);
+          *reinterpret_cast<float4*>(xo + 2 * plane) = ddim_update4(x2, a2, dk, dstoch, dnz, (off + 2 * plane) >> 2, dstep, dseed);
+        }
       }
     };
     int it = 0;
@@ -319,7 +352,8 @@ bool head_conv_supported(int h, int w, int c, int cout) {
 }
 
 int launch_head_conv(const void* x_op, const float* scale, const float* shift, const void* w_packed, const float* bias,
-                     float* out_nchw, int batch, int h, int w, int c, int op_dtype, cudaStream_t stream, int max_stages) {
+                     float* out_nchw, int batch, int h, int w, int c, int op_dtype, cudaStream_t stream, int max_stages,
+                     float* ddim_x, const float* ddim_coef, const DdimRun* ddim_run) {
   CLPK_REQUIRE(head_conv_supported(h, w, c, 3), "fused head kernel unsupported for W=%d C=%d", w, c);
   static std::mutex mu;
   static bool attr_done[64] = {};
@@ -343,6 +377,7 @@ int launch_head_conv(const void* x_op, const float* scale, const float* shift, c
   p.band = (p.rows_total + num_sms() - 1) / num_sms();
   p.op_f16 = (op_dtype == CLPK_OP_F16) ? 1 : 0;
   p.dpitch = w + 8;
+  p.ddim_x = ddim_x; p.ddim_coef = ddim_coef; p.ddim_run = ddim_run;
   p.scale = scale; p.shift = shift; p.bias = bias; p.out = out_nchw;
   const CUtensorMapDataType dt = p.op_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap map_a, map_w;

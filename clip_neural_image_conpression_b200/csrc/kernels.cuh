@@ -51,7 +51,8 @@ int launch_gn_apply(const float* x, const float* gamma, const float* beta, const
 // head_conv.cu
 bool head_conv_supported(int h, int w, int c, int cout);
 int launch_head_conv(const void* x_op, const float* scale, const float* shift, const void* w_packed, const float* bias,
-                     float* out_nchw, int batch, int h, int w, int c, int op_dtype, cudaStream_t stream, int max_stages = 0);
+                     float* out_nchw, int batch, int h, int w, int c, int op_dtype, cudaStream_t stream, int max_stages = 0,
+                     float* ddim_x = nullptr, const float* ddim_coef = nullptr, const DdimRun* ddim_run = nullptr);
 int launch_pack_head_weight(const float* w, void* out_op, int c, int op_dtype, cudaStream_t stream);
 
 // conv_in.cu

@@ -133,6 +133,7 @@ struct clpk_plan {
   bool head_fused = false;   // out_norm + out conv as the single head_conv kernel (env CLPK_HEAD_FUSED, default 1)
   uint16_t* head_w = nullptr;  // [32][base] packed head weight (head_conv.cu)
   int head_stages = 0;       // experiments: cap of the head kernel's A ring (env CLPK_HEAD_STAGES at plan creation)
+  bool head_ddim = false;    // DDIM steps: the head kernel also applies the update x <- f(x, eps) (env CLPK_HEAD_DDIM, default 1)
   bool x16_gn = false;       // env CLPK_X16=1: GroupNorms on the residual stream read X16 instead of fp32 X
   std::vector<char> lv16;    // per level: the residual stream lives in X16[l] ONLY (fp16), no fp32 X[l] (see res16_wanted)
   bool s16(int level) const { return lv16[level] != 0; }
@@ -354,7 +355,8 @@ int run_resblock(clpk_plan* P, ResBlockPlan& rb, cudaStream_t s) {
 }
 
 // everything after the conditioning vector: in_conv ... out   (unet.py:88-105).  film = [B, film_n].
-int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s, cudaEvent_t cond_ready = nullptr) {
+// ddim_x != nullptr (DDIM steps with the fused head kernel): the head also updates ddim_x in place (ddim.py:36-45)
+int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s, cudaEvent_t cond_ready = nullptr, float* ddim_x = nullptr) {
   const clpk_unet_config& c = P->cfg;
   P->prof_mark(kProfConvIn, s);  // stem (unet.py:88): im2col columns + pointwise GEMM on the tensor cores
   int src = launch_stem_im2col(x_nchw, P->stem_cols, P->B, c.img_ch, P->H, P->W, c.op_dtype, s);
@@ -380,7 +382,8 @@ int forward_body(clpk_plan* P, const float* x_nchw, cudaStream_t s, cudaEvent_t 
   if (P->head_fused) {
     CLPK_TIMED(P, kProfConvOther, s,
                launch_head_conv(P->X16[0], P->out_gn.scale, P->out_gn.shift, P->head_w, P->out_conv.bias, P->eps_buf, P->B,
-                                P->H, P->W, c.base, c.op_dtype, s, P->head_stages));  // out(out_norm(x)) -> eps_buf (NCHW)
+                                P->H, P->W, c.base, c.op_dtype, s, P->head_stages, ddim_x, ddim_x ? P->coef_tab : nullptr,
+                                ddim_x ? P->run_dev : nullptr));  // out(out_norm(x)) -> eps_buf (NCHW) [+ DDIM update]
   } else {
     CLPK_TIMED(P, kProfConvOther, s, igemm_launch(P->out_conv.L, s));  // -> eps_buf (NCHW)
   }
@@ -573,6 +576,8 @@ extern "C" int clpk_plan_create(const clpk_unet_config* cfg, int batch, int heig
                     head_conv_supported(height, width, cfg->base, cfg->img_ch);
     const char* hs = getenv("CLPK_HEAD_STAGES");
     P->head_stages = hs ? atoi(hs) : 0;
+    const char* hd = getenv("CLPK_HEAD_DDIM");
+    P->head_ddim = !(hd && atoi(hd) == 0);
   }
   if (P->head_fused) {  // out_norm is applied inside head_conv: only the (scale, shift) table is computed
     P->out_gn.in_consumer = true;
@@ -778,9 +783,13 @@ static int ddim_step_body(clpk_plan* P, cudaStream_t s) {
   CLPK_TIMED(P, kProfCond, sc, launch_cond_combine(P->zemb, P->ht_tab, P->run_dev, P->hcond, P->B, td, sc));
   CLPK_TRY(film_from_h(P, sc));
   if (fork) CLPK_CHECK_CUDA(cudaEventRecord(P->ev_join, sc));
-  CLPK_TRY(forward_body(P, P->x_buf, s, fork ? P->ev_join : nullptr));
-  const long long n = (long long)P->B * P->cfg.img_ch * P->H * P->W;
-  CLPK_TIMED(P, kProfDdim, s, launch_ddim_step(P->x_buf, P->eps_buf, P->coef_tab, P->run_dev, P->x_buf, n, s));
+  // the stem has consumed x_buf (im2col) long before the head runs, so the head may update it in place
+  const bool fused = P->head_fused && P->head_ddim;
+  CLPK_TRY(forward_body(P, P->x_buf, s, fork ? P->ev_join : nullptr, fused ? P->x_buf : nullptr));
+  if (!fused) {
+    const long long n = (long long)P->B * P->cfg.img_ch * P->H * P->W;
+    CLPK_TIMED(P, kProfDdim, s, launch_ddim_step(P->x_buf, P->eps_buf, P->coef_tab, P->run_dev, P->x_buf, n, s));
+  }
   return CLPK_OK;
 }
 
@@ -865,7 +874,7 @@ extern "C" int clpk_ddim_sample(clpk_plan* P, const float* z, float* x, const fl
     if (x_trace) CLPK_CHECK_CUDA(cudaMemcpyAsync(x_trace + (size_t)i * n, P->x_buf, nb, cudaMemcpyDeviceToDevice, s));
     if (P->graph_exec) {
       CLPK_CHECK_CUDA(cudaGraphLaunch(P->graph_exec, s));
-      count_launch(P->launches_fwd - 5 + 2 + 2);
+      count_launch(P->launches_fwd - 5 + 2 + ((P->head_fused && P->head_ddim) ? 1 : 2));  // cond (2) + forward + update / advance
     } else {
       CLPK_TRY(ddim_step_body(P, s));
       CLPK_TRY(launch_ddim_advance(P->run_dev, s));

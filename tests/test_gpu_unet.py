@@ -321,3 +321,36 @@ def test_16bit_residual_stream_matches_fp32_stream(oracle, monkeypatch):
     net.release_plans()
     b_off = net(x.cuda(), z.cuda(), t.cuda()).cpu()
     assert torch.equal(b_on, b_off)
+
+
+def test_ddim_update_fused_into_head_matches_standalone_kernel(oracle, monkeypatch):
+    """Default plan: the head kernel applies the DDIM update x <- f(x, eps) in its epilogue (CLPK_HEAD_DDIM, plan.cu).  Same
+    element math, same Philox counters as ddim_step_kernel -> the sampled images are bit-identical to the plan that runs
+    the stand-alone update kernel, deterministic (eta = 0) and stochastic (in-kernel noise and caller-supplied noise)."""
+    cfg = dict(z_dim=512, base=64, ch_mult=(1, 2))
+    net, _ = make_net(oracle, cfg, seed=31, out_gain=0.1)
+    g = torch.Generator().manual_seed(32)
+    z = torch.nn.functional.normalize(torch.randn(2, 512, generator=g), dim=-1).cuda()
+    x_T = torch.randn(2, 3, 64, 64, generator=g).cuda()
+    noise = torch.randn(6, 2, 3, 64, 64, generator=g).cuda()
+
+    def runs():
+        out = [_sampler(0.0).sample(net, z, (2, 3, 64, 64), steps=6, x_T=x_T)]
+        s = _sampler(1e-3)
+        s.seed = 5
+        out.append(s.sample(net, z, (2, 3, 64, 64), steps=6, x_T=x_T))
+        out.append(_sampler(1e-3).sample(net, z, (2, 3, 64, 64), steps=6, x_T=x_T, noise=noise))
+        tr = {}
+        out.append(_sampler(0.0).sample(net, z, (2, 3, 64, 64), steps=6, x_T=x_T, trace=tr))
+        out += [tr["eps"], tr["x"]]
+        return [o.clone() for o in out]
+
+    fused = runs()
+    monkeypatch.setenv("CLPK_HEAD_DDIM", "0")
+    net.release_plans()
+    plain = runs()
+    monkeypatch.delenv("CLPK_HEAD_DDIM")
+    net.release_plans()
+    for a, b in zip(fused, plain):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
+    assert not torch.equal(fused[0], fused[1])      # the stochastic path really adds noise
