@@ -354,3 +354,40 @@ def test_ddim_update_fused_into_head_matches_standalone_kernel(oracle, monkeypat
     for a, b in zip(fused, plain):
         assert torch.isfinite(a).all() and torch.equal(a, b)
     assert not torch.equal(fused[0], fused[1])      # the stochastic path really adds noise
+
+
+@pytest.mark.parametrize("base,mult,b,h,w", [
+    (32, (1, 2), 2, 16, 16),          # tiny image: 8 x 8 at the coarse level, tiles mostly masked
+    (32, (1, 2), 3, 40, 40),          # 40-pixel rows: 32-pixel tiles with masked columns at every level
+    (32, (1, 2), 2, 72, 56),          # non-square, ragged boxes
+    (64, (1, 2), 1, 136, 264),        # row-slab level with a partial second segment (264 = 2 x 128 + 8), 16-bit stream level
+    (64, (1, 2, 2), 2, 264, 136),     # three levels, tall image, widths 136 / 68 / 34
+])
+def test_non_square_and_ragged_image_sizes(oracle, base, mult, b, h, w):
+    """Image sizes that are not multiples of the 128-pixel tile (nor square): every level's masking / partial TMA boxes, the
+    fused statistics' element counts and the head kernel's bands against the fp32 oracle."""
+    from clip_neural_image_conpression_b200.models import CLIPCondUNet
+    sd = oracle.make_state_dict(512, base, mult, seed=1, out_gain=1.0)
+    net = CLIPCondUNet(z_dim=512, base=base, ch_mult=mult)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(b, 3, h, w, generator=g)
+    z = torch.nn.functional.normalize(torch.randn(b, 512, generator=g), dim=-1)
+    t = torch.randint(0, 1000, (b,), generator=g)
+    e = net(x.cuda(), z.cuda(), t.cuda()).cpu()
+    with torch.no_grad():
+        ref = oracle.unet_forward(sd, mult, x, z, t)
+    assert torch.isfinite(e).all()
+    for i in range(b):
+        assert oracle.rel_l2(e[i], ref[i]) < EPS_TOL / 4, (i, oracle.rel_l2(e[i], ref[i]))
+
+
+def test_unsupported_base_width_is_a_clean_error(oracle):
+    """The plan needs base % 32 == 0 (16-bit K-major rows, 32-column epilogue chunks): anything else must raise, not
+    fall back or corrupt memory."""
+    from clip_neural_image_conpression_b200._lib import ClpkError
+    from clip_neural_image_conpression_b200.models import CLIPCondUNet
+    net = CLIPCondUNet(z_dim=512, base=48, ch_mult=(1, 2)).cuda().eval()
+    with pytest.raises(ClpkError, match="multiple of 32"):
+        net(torch.randn(1, 3, 64, 64).cuda(), torch.randn(1, 512).cuda(), torch.tensor([5]).cuda())
