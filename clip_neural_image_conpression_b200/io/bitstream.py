@@ -100,3 +100,17 @@ def read_bitstreams(paths: Iterable[Path], threads: int = 16) -> np.ndarray:
         if r.shape[0] != d:
             raise ValueError(f"{p}: {r.shape[0]} codes, expected {d}")
     return np.stack(rows)
+
+
+def write_bitstreams(codes: np.ndarray, paths: Iterable[Path], threads: int = 16) -> None:
+    """Batched writer: uint8 [N, D] -> N .clp files, byte-identical to N write_bitstream calls (the per-vector loop of
+    PKG/cli/encode_images.py:79-83).  zstd and file IO release the GIL, so a small thread pool overlaps them."""
+    paths = list(paths)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    if codes.ndim != 2 or codes.shape[0] != len(paths):
+        raise ValueError(f"codes {codes.shape} do not match {len(paths)} paths")
+    if not paths:
+        return
+    dim = codes.shape[1]
+    with ThreadPoolExecutor(max_workers=max(1, min(threads, len(paths)))) as ex:
+        list(ex.map(lambda ip: write_bitstream(codes[ip[0]].tobytes(), dim, ip[1]), enumerate(paths)))

@@ -1,6 +1,7 @@
 """End-to-end on the GPU through the reference-facing surface: synthetic store on disk (.clp + codec_meta.npz +
 manifest.json + weights .pt) -> reconstruct_diffusion / eval CLIs."""
 import json
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -154,3 +155,55 @@ def test_decode_codes_matches_per_image_decoding(tmp_path, oracle):
     solo = torch.cat([decode_codes(net, sampler, q[i:i + 1], scale, zero, 32, steps=5, batch=1, x_T=x_T[i:i + 1]) for i in range(5)])
     assert oracle.psnr_float(full.cpu(), solo.cpu()) > 60.0
     assert decode_codes(net, sampler, q[:0], scale, zero, 32, steps=5, batch=4).shape == (0, 3, 32, 32)
+
+
+def test_write_store_matches_the_reference_store_layout(tmp_path, oracle, golden):
+    """pipeline.write_store = the store-writing tail of the reference's encode CLI (encode_images.py:75-87) with the
+    quantiser on the device: codec_meta.npz, every .clp file and manifest.json equal what the oracle's restatement of the
+    reference arithmetic + the reference's container format produce — bit for bit — and the store decodes back."""
+    from clip_neural_image_conpression_b200.io.bitstream import read_bitstreams
+    from clip_neural_image_conpression_b200.pipeline import write_store
+    g = torch.Generator().manual_seed(9)
+    n, d = 37, 512
+    feats = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1).numpy()
+    feats[3, 7] = feats[:, 7].max() + 0.5                            # an outlier sets one channel's range
+    imgs = [str(tmp_path / "imgs" / f"pic_{i:03d}.jpg") for i in range(n)]
+    manifest = write_store(feats, imgs, tmp_path / "store", threads=5)
+    scale, zero = oracle.quant_fit(feats)
+    meta = np.load(tmp_path / "store" / "codec_meta.npz")
+    assert set(meta.files) == {"scale", "zero", "dim"} and meta["dim"].dtype == np.int32 and int(meta["dim"]) == d
+    assert meta["scale"].dtype == np.float32 and np.array_equal(meta["scale"], scale) and np.array_equal(meta["zero"], zero)
+    on_disk = json.loads((tmp_path / "store" / "manifest.json").read_text(encoding="utf-8"))
+    assert on_disk == manifest and len(manifest) == n
+    assert manifest[5] == {"image": imgs[5], "bitstream": str(tmp_path / "store" / "pic_005.clp")}
+    codes = read_bitstreams([m["bitstream"] for m in manifest])
+    ref_codes = np.stack([oracle.quant_encode(feats[i], scale, zero) for i in range(n)])
+    assert np.array_equal(codes, ref_codes)
+    for i in (0, 17, 36):                                            # container bytes == the oracle's restatement of the format
+        assert Path(manifest[i]["bitstream"]).read_bytes() == oracle.clp_encode(ref_codes[i].tobytes())
+    with pytest.raises(SystemExit):
+        write_store(np.zeros((0, d), np.float32), [], tmp_path / "empty")
+
+
+def test_cli_encode_features_then_eval_round_trip(tmp_path, oracle, capsys):
+    """encode_features CLI (store writer) -> eval CLI (store reader + decoder): the codec round trip through files only."""
+    from clip_neural_image_conpression_b200.cli import encode_features as cli_enc
+    from clip_neural_image_conpression_b200.cli import eval as cli_eval
+    from PIL import Image
+    g = torch.Generator().manual_seed(10)
+    n = 3
+    feats = torch.nn.functional.normalize(torch.randn(n, 512, generator=g), dim=-1).numpy()
+    np.save(tmp_path / "f.npy", feats)
+    imgs = []
+    rng = np.random.default_rng(1)
+    for i in range(n):
+        Image.fromarray(rng.integers(0, 256, (32, 32, 3), dtype=np.uint8)).save(tmp_path / f"im{i}.png")
+        imgs.append(str(tmp_path / f"im{i}.png"))
+    (tmp_path / "list.txt").write_text("\n".join(imgs) + "\n")
+    cli_enc.main(["--features", str(tmp_path / "f.npy"), "--image_list", str(tmp_path / "list.txt"), "--out_dir", str(tmp_path / "store")])
+    assert f"Done. Stored {n} vectors in" in capsys.readouterr().out
+    torch.save(oracle.make_state_dict(512, 32, (1, 2), seed=0, out_gain=0.1), tmp_path / "w.pt")
+    cli_eval.main(["--store_dir", str(tmp_path / "store"), "--weights", str(tmp_path / "w.pt"), "--size", "32", "--steps", "3",
+                   "--base", "32", "--ch_mult", "1", "2", "--seed", "0", "--batch", "2", "--out_json", str(tmp_path / "m.json")])
+    rows = json.loads((tmp_path / "m.json").read_text())
+    assert [r["image"] for r in rows] == imgs and all(np.isfinite(r["psnr"]) for r in rows)

@@ -106,6 +106,15 @@ def test_bitstream_round_trip_and_reference_files(tmp_path, golden):
         paths.append(tmp_path / f"m{i}.clp")
     assert np.array_equal(bitstream.read_bitstreams(paths, threads=3), g["codes"][:7])
     assert bitstream.read_bitstreams([]).shape[0] == 0
+    # batched writer == the reference's per-vector loop (encode_images.py:79-83): byte-identical files, any thread count
+    wpaths = [tmp_path / f"w{i}.clp" for i in range(7)]
+    bitstream.write_bitstreams(g["codes"][:7], wpaths, threads=3)
+    for a, b in zip(paths, wpaths):
+        assert a.read_bytes() == b.read_bytes()
+    assert wpaths[0].read_bytes() == g["clp0"].tobytes()            # == the file the reference's own writer produced
+    bitstream.write_bitstreams(np.zeros((0, 512), np.uint8), [])
+    with pytest.raises(ValueError, match="do not match"):
+        bitstream.write_bitstreams(g["codes"][:3], wpaths[:2])
 
 
 def test_shard_bounds_partition():
