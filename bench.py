@@ -417,8 +417,11 @@ def run_b200_arm(args):
                                    f"the 1024-image STRONG-scaling store decode (BASELINE configs[2]) is under extra_configs.config3_store1024",
                        "batch_per_gpu": B, "global_batch": B * world, "ddim_steps": T, "z_dim": ARCH["z_dim"],
                        "weights": "random init (seed 0), out.* x0.1",
-                       "precision": f"{args.operand} tensor-core operands, fp32 accumulation (TMEM), fp32 residual stream and GroupNorm statistics", "sharding": f"dp{world} by image, no collective in the DDIM loop; per step one all_gather of the uint8 reconstructions + one fp64 all_reduce of PSNR + SSIM sums (NCCL) when n_gpus > 1",
-                       "l2": "inputs larger than L2: every level-0 activation tensor is 134 MB at batch 8 (three of them live per ResBlock, ~2 GB touched per DDIM step) vs the 126 MB L2; no flush needed"},
+                       "precision": f"{args.operand} tensor-core operands, fp32 accumulation (TMEM), fp32 GroupNorm statistics, residual stream "
+                                    + ("fp16 at the levels with rows >= 128 px, fp32 below" if args.operand == "f16" else "fp32"), "sharding": f"dp{world} by image, no collective in the DDIM loop; per step one all_gather of the uint8 reconstructions + one fp64 all_reduce of PSNR + SSIM sums (NCCL) when n_gpus > 1",
+                       "l2": (f"inputs larger than L2: every level-0 activation tensor is {B * S * S * ARCH['base'] * 2 / 1e6:.0f} MB at batch {B} "
+                              f"(three of them live per ResBlock) vs the 126 MB L2; no flush "
+                              + ("needed" if B * S * S * ARCH["base"] * 2 > 126e6 else "done although they FIT in L2 at this batch: not a headline configuration"))},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(codes_host.numel() + x_T_host.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() + metric_host.numel() * 8)},
